@@ -1,0 +1,74 @@
+// Internal layout of the opaque at_index / at_kmeans objects and the canonical fp32 arithmetic every
+// search kernel shares.
+#pragma once
+#include "at_common.cuh"
+#include <cuda_fp16.h>
+
+struct at_index {
+    int d = 0;
+    int k = 0;      // centroids currently held
+    int kcap = 0;   // allocation, in centroids
+    float *c = nullptr;    // (kcap, d) fp32 centroids
+    float *cn = nullptr;   // (kcap) canonical |c|^2
+    // tcgen05 operands (d == 64 only): per 128-centroid tile, two 128x64 fp16 K-major SWIZZLE_128B images
+    // (hi and lo halves of -2*16*c), see at_assign_tc.cu
+    __half *op = nullptr;  // (ktiles * 2 * 128 * 64) halves
+    float *cn_pad = nullptr;  // (ktiles*128) |c|^2, +inf for padding columns
+    int ktiles = 0;
+};
+
+struct at_kmeans {
+    int d = 0, k = 0;
+    at_index *index = nullptr;
+    // fixed-point accumulation (at_kmeans_begin)
+    int e_sum = 0, e_obj = 0;
+    int64_t n_total = 0;
+    bool begun = false;
+    // workspaces sized for the largest n_local seen
+    int64_t ncap = 0;
+    int32_t *labels = nullptr;
+    float *dist = nullptr;
+    int32_t *order = nullptr;
+    int64_t *off = nullptr;     // k+1
+    unsigned long long *cursor = nullptr;  // k
+    float *hassign = nullptr;   // k
+    float *newc = nullptr;      // (k, d) scratch for finalize
+};
+
+namespace at {
+
+// ---- canonical sums --------------------------------------------------------------------------
+// A length-d sum (of squares, or of products) is always associated the same way:
+//   16 partials q_l, l = (t/4) % 16, each a sequential FMA chain over its elements in ascending t,
+//   combined by the xor butterfly  l^8, l^4, l^2, l^1.
+// This shape is what a 16-lane shuffle reduction over float4 chunks produces, is invariant under rotating
+// the chunk order, and can be evaluated by one thread with static register indices.
+__device__ __forceinline__ float tree16(const float (&q)[16]) {
+    float a[8], b[4], c2[2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = __fadd_rn(q[i], q[i + 8]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = __fadd_rn(a[i], a[i + 4]);
+#pragma unroll
+    for (int i = 0; i < 2; i++) c2[i] = __fadd_rn(b[i], b[i + 2]);
+    return __fadd_rn(c2[0], c2[1]);
+}
+
+__device__ __forceinline__ float half16_sum(float v) {  // xor butterfly over a 16-lane group
+    v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
+    v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return v;
+}
+
+// normalize_vectors' scalar: 1 / (sqrt(S) + 1e-10) is NOT formed; numpy divides by (norm + 1e-10).
+__device__ __forceinline__ float l2_denominator(float sumsq) { return __fadd_rn(__fsqrt_rn(sumsq), 1e-10f); }
+
+// Implemented in at_assign_tc.cu.  Returns AT_ERR_UNSUPPORTED when the shape is outside the tensor path.
+int assign_tc_prepare(at_index *ix, cudaStream_t st);
+int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32,
+                     int64_t *labels64, float *dist, cudaStream_t st);
+bool assign_tc_supported(const at_index *ix);
+
+}  // namespace at

@@ -1,0 +1,647 @@
+// libat_b200: flat L2 index (exact fp32 SIMT search), k-means accumulate / finalize.
+//
+// Reference semantics restated here (upstream faiss v1.8.0, reached from processors/cluster_creator.py:42-58
+// and processors/spec_tokenizer.py:77):
+//   search      exhaustive_L2sqr_blas: |x|^2 + |c|^2 - 2<x,c>, clamp at 0, strict '<' (lowest index wins)
+//   accumulate  compute_centroids' per-cluster sums and counts (here: exact fixed-point, order independent)
+//   finalize    c = sum * (1/count); split_clusters with std::mt19937(1234), EPS = 1/1024
+#include "at_index.cuh"
+
+#include <math.h>
+#include <new>
+
+namespace at {
+
+// ---------------------------------------------------------------------------------------------
+// normalize_vectors: half-warp per row, canonical sum of squares.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_row_l2norm(const float *__restrict__ x, int64_t n, int d, float *__restrict__ out) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    int g = threadIdx.x & 15;
+    bool live = row < n;
+    const float *xr = x + (live ? row : 0) * d;
+    float q = 0.f;
+    if (live) {
+        for (int base = 4 * g; base < d; base += 64) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (base + e < d) {
+                    float v = xr[base + e];
+                    q = fmaf(v, v, q);
+                }
+            }
+        }
+    }
+    float s = half16_sum(q);
+    if (!live) return;
+    float den = l2_denominator(s);
+    for (int base = 4 * g; base < d; base += 64) {
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (base + e < d) out[row * d + base + e] = __fdiv_rn(xr[base + e], den);
+    }
+}
+
+// canonical |c|^2, one thread per centroid (k is small)
+__global__ void k_centroid_norms(const float *__restrict__ c, int k, int d, float *__restrict__ cn) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    float q[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) q[l] = 0.f;
+    const float *cj = c + (int64_t)j * d;
+    for (int base = 0; base < d; base += 64) {
+#pragma unroll
+        for (int t = 0; t < 64; t++) {
+            if (base + t < d) {
+                float v = cj[base + t];
+                q[(t >> 2) & 15] = fmaf(v, v, q[(t >> 2) & 15]);
+            }
+        }
+    }
+    cn[j] = tree16(q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact fp32 search, one thread per row, row held in registers (zero padded to DP).
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(128) k_assign_simt(const float *__restrict__ x, int64_t n, int d,
+                                                     const float *__restrict__ c,
+                                                     const float *__restrict__ cn, int k, int l2norm,
+                                                     int32_t *__restrict__ labels32,
+                                                     int64_t *__restrict__ labels64,
+                                                     float *__restrict__ dist) {
+    constexpr int KT = 32;
+    __shared__ __align__(16) float ctile[KT][DP];
+    __shared__ float cns[KT];
+    const int tid = threadIdx.x;
+    const int64_t row = (int64_t)blockIdx.x * 128 + tid;
+    const bool live = row < n;
+
+    float xr[DP];
+#pragma unroll
+    for (int t = 0; t < DP; t++) xr[t] = 0.f;
+    if (live) {
+        const float *xp = x + row * d;
+        if ((d & 3) == 0) {
+#pragma unroll
+            for (int t = 0; t < DP; t += 4) {
+                if (t < d) {
+                    float4 v = *reinterpret_cast<const float4 *>(xp + t);
+                    xr[t] = v.x, xr[t + 1] = v.y, xr[t + 2] = v.z, xr[t + 3] = v.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < DP; t++)
+                if (t < d) xr[t] = xp[t];
+        }
+    }
+    float q[16];
+    if (l2norm) {
+#pragma unroll
+        for (int l = 0; l < 16; l++) q[l] = 0.f;
+#pragma unroll
+        for (int t = 0; t < DP; t++) q[(t >> 2) & 15] = fmaf(xr[t], xr[t], q[(t >> 2) & 15]);
+        float den = l2_denominator(tree16(q));
+#pragma unroll
+        for (int t = 0; t < DP; t++) xr[t] = __fdiv_rn(xr[t], den);
+    }
+#pragma unroll
+    for (int l = 0; l < 16; l++) q[l] = 0.f;
+#pragma unroll
+    for (int t = 0; t < DP; t++) q[(t >> 2) & 15] = fmaf(xr[t], xr[t], q[(t >> 2) & 15]);
+    const float xn = tree16(q);
+
+    float best = INFINITY;
+    int bj = 0;
+    for (int j0 = 0; j0 < k; j0 += KT) {
+        const int kt = min(KT, k - j0);
+        for (int i = tid; i < KT * DP; i += 128) {
+            int jj = i / DP, t = i % DP;
+            ctile[jj][t] = (jj < kt && t < d) ? c[(int64_t)(j0 + jj) * d + t] : 0.f;
+        }
+        if (tid < KT) cns[tid] = tid < kt ? cn[j0 + tid] : INFINITY;
+        __syncthreads();
+        for (int jj = 0; jj < kt; jj++) {
+#pragma unroll
+            for (int l = 0; l < 16; l++) q[l] = 0.f;
+#pragma unroll
+            for (int t = 0; t < DP; t += 4) {
+                float4 cv = *reinterpret_cast<const float4 *>(&ctile[jj][t]);
+                const int l = (t >> 2) & 15;
+                q[l] = fmaf(xr[t], cv.x, q[l]);
+                q[l] = fmaf(xr[t + 1], cv.y, q[l]);
+                q[l] = fmaf(xr[t + 2], cv.z, q[l]);
+                q[l] = fmaf(xr[t + 3], cv.w, q[l]);
+            }
+            float dis = l2_expanded(xn, cns[jj], tree16(q));
+            if (dis < best) {
+                best = dis;
+                bj = j0 + jj;
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        if (labels32) labels32[row] = bj;
+        if (labels64) labels64[row] = bj;
+        if (dist) dist[row] = best;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k-means accumulate: counts + objective, offsets, placement, exact gather-sum.
+// ---------------------------------------------------------------------------------------------
+// accum layout (int64 words): [0, k*d) sums, [k*d, k*d+k) counts, [k*d+k] objective.
+__global__ void k_objective(const float *__restrict__ dist, int64_t n, float obj_scale,
+                            unsigned long long *__restrict__ obj_word) {
+    long long local = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        local += __float2ll_rn(dist[i] * obj_scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ long long ws[32];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) ws[w] = local;
+    __syncthreads();
+    if (w == 0) {
+        long long v = lane < (int)(blockDim.x >> 5) ? ws[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(obj_word, (unsigned long long)v);
+    }
+}
+
+__global__ void k_counts(const int32_t *__restrict__ labels, int64_t n, unsigned long long *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // warp-uniform trip count so the full-mask match below is always convergent
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+        const int64_t i = base + lane;
+        const int l = i < n ? labels[i] : -1 - lane;
+        // warp-aggregate identical labels before touching L2
+        unsigned peers = __match_any_sync(0xffffffffu, l);
+        if (l >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&counts[l], (unsigned long long)__popc(peers));
+    }
+}
+
+// exclusive scan of the k local counts -> off[0..k], cursor[j] = off[j].  One block of 1024 threads.
+__global__ void k_scan_counts(const unsigned long long *__restrict__ counts, int k, int64_t *__restrict__ off,
+                              unsigned long long *__restrict__ cursor) {
+    __shared__ long long part[1024];
+    const int tid = threadIdx.x;
+    const int per = (k + 1023) / 1024;
+    const int j0 = tid * per, j1 = min(k, j0 + per);
+    long long s = 0;
+    for (int j = j0; j < j1; j++) s += (long long)counts[j];
+    part[tid] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        long long v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    long long run = part[tid] - s;
+    for (int j = j0; j < j1; j++) {
+        off[j] = run;
+        cursor[j] = (unsigned long long)run;
+        run += (long long)counts[j];
+    }
+    if (tid == 1023) off[k] = part[1023];
+}
+
+// order[cursor[label]++] = row  (order within a cluster is arbitrary: the sums below are exact integers)
+__global__ void k_place(const int32_t *__restrict__ labels, int64_t n, unsigned long long *__restrict__ cursor,
+                        int32_t *__restrict__ order) {
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+        const int64_t i = base + lane;
+        const int l = i < n ? labels[i] : -1 - lane;
+        unsigned peers = __match_any_sync(0xffffffffu, l);
+        int leader = __ffs(peers) - 1;
+        unsigned long long pos = 0;
+        if (l >= 0 && lane == leader) pos = atomicAdd(&cursor[l], (unsigned long long)__popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (l >= 0) order[pos + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
+    }
+}
+
+// Each warp owns an equal slice of the cluster-grouped order[] array and accumulates x rows as int64
+// fixed point (x * 2^e_sum), flushing to sums[c] with 64-bit atomics whenever the cluster changes.
+template <int DPL>  // dims per lane = ceil(d / 32)
+__global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x, int d,
+                                                    const int32_t *__restrict__ order,
+                                                    const int64_t *__restrict__ off, int k, int64_t n,
+                                                    float scale, unsigned long long *__restrict__ sums) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t per = (n + nwarps - 1) / nwarps;
+    const int64_t p0 = warp * per;
+    const int64_t p1 = min(n, p0 + per);
+    if (p0 >= p1) return;
+    // cluster of p0: largest c with off[c] <= p0
+    int lo = 0, hi = k;  // invariant off[lo] <= p0 < off[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= p0) lo = mid; else hi = mid;
+    }
+    int c = lo;
+    int64_t cend = off[c + 1];
+    long long acc[DPL];
+#pragma unroll
+    for (int u = 0; u < DPL; u++) acc[u] = 0;
+
+    constexpr int U = 8;
+    for (int64_t p = p0; p < p1; p += U) {
+        int32_t rows[U];
+        float v[U][DPL];
+#pragma unroll
+        for (int u = 0; u < U; u++) rows[u] = (p + u < p1) ? order[p + u] : -1;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int w = 0; w < DPL; w++) {
+                int t = lane + 32 * w;
+                v[u][w] = (rows[u] >= 0 && t < d) ? x[(int64_t)rows[u] * d + t] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (p + u >= p1) break;
+            while (p + u >= cend) {  // warp-uniform
+#pragma unroll
+                for (int w = 0; w < DPL; w++) {
+                    int t = lane + 32 * w;
+                    if (t < d && acc[w] != 0) atomicAdd(&sums[(int64_t)c * d + t], (unsigned long long)acc[w]);
+                    acc[w] = 0;
+                }
+                c++;
+                cend = off[c + 1];
+            }
+#pragma unroll
+            for (int w = 0; w < DPL; w++) acc[w] += __float2ll_rn(v[u][w] * scale);
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < DPL; w++) {
+        int t = lane + 32 * w;
+        if (t < d && acc[w] != 0) atomicAdd(&sums[(int64_t)c * d + t], (unsigned long long)acc[w]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: division, statistics, split_clusters.  One block.
+// ---------------------------------------------------------------------------------------------
+struct Mt19937 {
+    uint32_t mt[624];
+    int idx;
+    __device__ void seed(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    __device__ uint32_t next() {
+        if (idx >= 624) {
+            for (int i = 0; i < 624; i++) {
+                uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+                uint32_t v = mt[(i + 397) % 624] ^ (y >> 1);
+                if (y & 1u) v ^= 0x9908b0dfu;
+                mt[i] = v;
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    // faiss RandomGenerator::rand_float: mt() / float(mt.max())
+    __device__ float rand_float() { return __fdiv_rn((float)next(), 4294967296.0f); }
+};
+
+__global__ void __launch_bounds__(1024) k_finalize(const long long *__restrict__ accum, int k, int d,
+                                                   int64_t n_total, double inv_sum_scale,
+                                                   double inv_obj_scale, float *__restrict__ centroids,
+                                                   float *__restrict__ hassign, float *__restrict__ stats) {
+    __shared__ Mt19937 rng;
+    __shared__ double s_imb[32];
+    __shared__ int s_empty[32];
+    const int tid = threadIdx.x;
+    const int64_t kd = (int64_t)k * d;
+    double imb = 0.0;
+    int nempty = 0;
+    for (int c = tid; c < k; c += blockDim.x) {
+        long long cnt = accum[kd + c];
+        hassign[c] = (float)cnt;
+        imb += (double)cnt * (double)cnt;
+        nempty += cnt == 0;
+    }
+    for (int64_t i = tid; i < kd; i += blockDim.x) {
+        int c = (int)(i / d);
+        long long cnt = accum[kd + c];
+        float v = 0.f;
+        if (cnt != 0) {
+            // compute_centroids: c[j] = sum * (1 / hassign)
+            float sum = __double2float_rn(__ll2double_rn(accum[i]) * inv_sum_scale);
+            float norm = __fdiv_rn(1.0f, (float)cnt);
+            v = __fmul_rn(sum, norm);
+        }
+        centroids[i] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        imb += __shfl_xor_sync(0xffffffffu, imb, o);
+        nempty += __shfl_xor_sync(0xffffffffu, nempty, o);
+    }
+    if ((tid & 31) == 0) s_imb[tid >> 5] = imb, s_empty[tid >> 5] = nempty;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0;
+        int ne = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_imb[w], ne += s_empty[w];
+        int nsplit = 0;
+        if (ne > 0) {
+            // faiss::split_clusters (Clustering.cpp), sequential by construction
+            rng.seed(1234u);
+            for (int ci = 0; ci < k; ci++) {
+                if (hassign[ci] == 0.f) {
+                    int cj = 0;
+                    for (;; cj = (cj + 1) % k) {
+                        float p = (float)(((double)hassign[cj] - 1.0) / (double)(float)(n_total - k));
+                        float r = rng.rand_float();
+                        if (r < p) break;
+                    }
+                    for (int j = 0; j < d; j++) {
+                        float v = centroids[(int64_t)cj * d + j];
+                        float up = __fmul_rn(v, 1.0009765625f), dn = __fmul_rn(v, 0.9990234375f);
+                        centroids[(int64_t)ci * d + j] = (j % 2 == 0) ? up : dn;
+                        centroids[(int64_t)cj * d + j] = (j % 2 == 0) ? dn : up;
+                    }
+                    hassign[ci] = hassign[cj] / 2;
+                    hassign[cj] -= hassign[ci];
+                    nsplit++;
+                }
+            }
+        }
+        if (stats) {
+            stats[0] = (float)((double)accum[kd + k] * inv_obj_scale);
+            stats[1] = (float)nsplit;
+            stats[2] = (float)(tot * (double)k / ((double)n_total * (double)n_total));
+            stats[3] = (float)ne;
+        }
+    }
+}
+
+static int launch_simt(const at_index *ix, const float *x, int64_t n, int l2norm, int32_t *l32, int64_t *l64,
+                       float *dist, cudaStream_t st) {
+    unsigned blocks = (unsigned)ceil_div(n, 128);
+    if (ix->d <= 16)
+        k_assign_simt<16><<<blocks, 128, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l2norm, l32, l64, dist);
+    else if (ix->d <= 32)
+        k_assign_simt<32><<<blocks, 128, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l2norm, l32, l64, dist);
+    else if (ix->d <= 64)
+        k_assign_simt<64><<<blocks, 128, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l2norm, l32, l64, dist);
+    else if (ix->d <= 128)
+        k_assign_simt<128><<<blocks, 128, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l2norm, l32, l64, dist);
+    else {
+        set_error("search: d=%d > 128 is not covered by this build", ix->d);
+        return AT_ERR_UNSUPPORTED;
+    }
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+static int index_search(at_index *ix, const float *x, int64_t n, int l2norm, int algo, int32_t *l32,
+                        int64_t *l64, float *dist, cudaStream_t st) {
+    if (n == 0) return AT_OK;
+    bool tc = false;
+    if (algo == AT_ALGO_TENSOR) {
+        if (!assign_tc_supported(ix)) {
+            set_error("search: tensor path needs d == 64 and k >= 16 (d=%d, k=%d)", ix->d, ix->k);
+            return AT_ERR_UNSUPPORTED;
+        }
+        tc = true;
+    } else if (algo == AT_ALGO_AUTO) {
+        tc = assign_tc_supported(ix) && ix->k >= 64;
+    }
+    if (tc) return assign_tc_search(ix, x, n, l2norm, l32, l64, dist, st);
+    return launch_simt(ix, x, n, l2norm, l32, l64, dist, st);
+}
+
+}  // namespace at
+
+using namespace at;
+
+extern "C" {
+
+int at_row_l2norm(const float *x, int64_t n, int d, float *out, void *stream) {
+    AT_REQUIRE(x && out && n >= 0 && d > 0, "at_row_l2norm: bad arguments");
+    if (n == 0) return AT_OK;
+    k_row_l2norm<<<(unsigned)ceil_div(n * 16, 256), 256, 0, (cudaStream_t)stream>>>(x, n, d, out);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+// ----------------------------------------------------------------------------------- index
+int at_index_create(int d, at_index **index) {
+    AT_REQUIRE(index && d > 0, "at_index_create: bad arguments");
+    AT_REQUIRE(d <= 128, "at_index_create: d=%d > 128 is not covered by this build", d);
+    int dev;
+    AT_CUDA_OK(cudaGetDevice(&dev));
+    at_index *ix = new (std::nothrow) at_index();
+    if (!ix) return AT_ERR_NOMEM;
+    ix->d = d;
+    *index = ix;
+    return AT_OK;
+}
+
+int at_index_destroy(at_index *ix) {
+    if (!ix) return AT_OK;
+    cudaFree(ix->c);
+    cudaFree(ix->cn);
+    cudaFree(ix->op);
+    cudaFree(ix->cn_pad);
+    delete ix;
+    return AT_OK;
+}
+
+int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *stream) {
+    AT_REQUIRE(ix && centroids && k > 0, "at_index_set_centroids: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k > ix->kcap) {
+        AT_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(ix->c), cudaFree(ix->cn), cudaFree(ix->op), cudaFree(ix->cn_pad);
+        ix->c = ix->cn = ix->cn_pad = nullptr;
+        ix->op = nullptr;
+        ix->kcap = 0;
+        int ktiles = (k + 127) / 128;
+        AT_CUDA_OK(cudaMalloc(&ix->c, sizeof(float) * (size_t)k * ix->d));
+        AT_CUDA_OK(cudaMalloc(&ix->cn, sizeof(float) * (size_t)k));
+        if (ix->d == 64) {
+            AT_CUDA_OK(cudaMalloc(&ix->op, sizeof(__half) * (size_t)ktiles * 2 * 128 * 64));
+            AT_CUDA_OK(cudaMalloc(&ix->cn_pad, sizeof(float) * (size_t)ktiles * 128));
+        }
+        ix->kcap = k;
+    }
+    ix->k = k;
+    ix->ktiles = (k + 127) / 128;
+    if (centroids != ix->c)
+        AT_CUDA_OK(cudaMemcpyAsync(ix->c, centroids, sizeof(float) * (size_t)k * ix->d, cudaMemcpyDeviceToDevice, st));
+    k_centroid_norms<<<(k + 127) / 128, 128, 0, st>>>(ix->c, k, ix->d, ix->cn);
+    AT_LAUNCH_OK();
+    if (assign_tc_supported(ix)) return assign_tc_prepare(ix, st);
+    return AT_OK;
+}
+
+int at_index_ntotal(const at_index *ix) { return ix ? ix->k : 0; }
+const float *at_index_centroids(const at_index *ix) { return ix ? ix->c : nullptr; }
+
+int at_index_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int algo, int32_t *labels32,
+                    int64_t *labels64, float *dist, void *stream) {
+    AT_REQUIRE(ix && (x || n == 0) && n >= 0, "at_index_search: bad arguments");
+    AT_REQUIRE(ix->k > 0, "at_index_search: index is empty");
+    return index_search(ix, x, n, l2norm_rows, algo, labels32, labels64, dist, (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------------- k-means
+int at_kmeans_create(int d, int k, at_kmeans **out) {
+    AT_REQUIRE(out && d > 0 && k > 0, "at_kmeans_create: bad arguments");
+    at_kmeans *km = new (std::nothrow) at_kmeans();
+    if (!km) return AT_ERR_NOMEM;
+    km->d = d, km->k = k;
+    int rc = at_index_create(d, &km->index);
+    if (rc != AT_OK) {
+        delete km;
+        return rc;
+    }
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&km->off, sizeof(int64_t) * (size_t)(k + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&km->cursor, sizeof(unsigned long long) * (size_t)k);
+    if (e == cudaSuccess) e = cudaMalloc(&km->hassign, sizeof(float) * (size_t)k);
+    if (e == cudaSuccess) e = cudaMalloc(&km->newc, sizeof(float) * (size_t)k * d);
+    if (e != cudaSuccess) {
+        set_error("at_kmeans_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+        at_kmeans_destroy(km);
+        return AT_ERR_CUDA;
+    }
+    *out = km;
+    return AT_OK;
+}
+
+int at_kmeans_destroy(at_kmeans *km) {
+    if (!km) return AT_OK;
+    at_index_destroy(km->index);
+    cudaFree(km->labels), cudaFree(km->dist), cudaFree(km->order);
+    cudaFree(km->off), cudaFree(km->cursor), cudaFree(km->hassign), cudaFree(km->newc);
+    delete km;
+    return AT_OK;
+}
+
+int at_kmeans_set_centroids(at_kmeans *km, const float *centroids, void *stream) {
+    AT_REQUIRE(km && centroids, "at_kmeans_set_centroids: bad arguments");
+    return at_index_set_centroids(km->index, centroids, km->k, stream);
+}
+
+const float *at_kmeans_centroids(const at_kmeans *km) { return km ? km->index->c : nullptr; }
+
+int at_kmeans_get_centroids(const at_kmeans *km, float *out, void *stream) {
+    AT_REQUIRE(km && out && km->index->k == km->k, "at_kmeans_get_centroids: bad arguments or centroids not set");
+    AT_CUDA_OK(cudaMemcpyAsync(out, km->index->c, sizeof(float) * (size_t)km->k * km->d, cudaMemcpyDeviceToDevice,
+                               (cudaStream_t)stream));
+    return AT_OK;
+}
+
+static int ceil_log2_d(double v) {
+    int e = 0;
+    if (!(v > 0)) return 0;
+    frexp(v, &e);  // v = m * 2^e, m in [0.5, 1)
+    return e;      // v < 2^e
+}
+
+int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total) {
+    AT_REQUIRE(km && n_total > 0 && max_abs >= 0 && isfinite(max_abs), "at_kmeans_begin: bad arguments");
+    int nb = ceil_log2_d((double)n_total + 1.0);
+    int mb = ceil_log2_d((double)max_abs);
+    km->e_sum = 61 - nb - mb;  // |x * 2^e| < 2^(61-nb); n_total rows sum below 2^61
+    if (km->e_sum > 100) km->e_sum = 100;
+    double maxd = 4.0 * km->d * (double)max_abs * (double)max_abs;  // |x - c|^2 <= d (2 max_abs)^2
+    km->e_obj = 61 - nb - ceil_log2_d(maxd);
+    if (km->e_obj > 100) km->e_obj = 100;
+    km->n_total = n_total;
+    km->begun = true;
+    return AT_OK;
+}
+
+int64_t at_kmeans_accum_words(const at_kmeans *km) { return km ? (int64_t)km->k * km->d + km->k + 1 : 0; }
+
+static int km_reserve(at_kmeans *km, int64_t n, cudaStream_t st) {
+    if (n <= km->ncap) return AT_OK;
+    AT_CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(km->labels), cudaFree(km->dist), cudaFree(km->order);
+    km->labels = km->order = nullptr, km->dist = nullptr, km->ncap = 0;
+    AT_CUDA_OK(cudaMalloc(&km->labels, sizeof(int32_t) * (size_t)n));
+    AT_CUDA_OK(cudaMalloc(&km->dist, sizeof(float) * (size_t)n));
+    AT_CUDA_OK(cudaMalloc(&km->order, sizeof(int32_t) * (size_t)n));
+    km->ncap = n;
+    return AT_OK;
+}
+
+int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2norm_rows, int algo,
+                         int64_t *accum, int32_t *labels32, void *stream) {
+    AT_REQUIRE(km && accum && n_local >= 0 && (x || n_local == 0), "at_kmeans_accumulate: bad arguments");
+    AT_REQUIRE(km->begun, "at_kmeans_accumulate: call at_kmeans_begin first");
+    AT_REQUIRE(km->index->k == km->k, "at_kmeans_accumulate: centroids not set");
+    AT_REQUIRE(!l2norm_rows, "at_kmeans_accumulate: normalise once with at_row_l2norm (rows are re-read every iteration)");
+    AT_REQUIRE(n_local < (1LL << 31), "at_kmeans_accumulate: more than 2^31 local rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = km->k, d = km->d;
+    const int64_t kd = (int64_t)k * d;
+    AT_CUDA_OK(cudaMemsetAsync(accum, 0, sizeof(int64_t) * (size_t)(kd + k + 1), st));
+    if (n_local == 0) return AT_OK;
+    int rc = km_reserve(km, n_local, st);
+    if (rc != AT_OK) return rc;
+    int32_t *labels = labels32 ? labels32 : km->labels;
+    rc = index_search(km->index, x, n_local, 0, algo, labels, nullptr, km->dist, st);
+    if (rc != AT_OK) return rc;
+    unsigned long long *acc = (unsigned long long *)accum;
+    int blocks = sm_count() * 8;
+    k_counts<<<blocks, 256, 0, st>>>(labels, n_local, acc + kd);
+    AT_LAUNCH_OK();
+    k_objective<<<blocks, 256, 0, st>>>(km->dist, n_local, ldexpf(1.0f, km->e_obj), acc + kd + k);
+    AT_LAUNCH_OK();
+    k_scan_counts<<<1, 1024, 0, st>>>(acc + kd, k, km->off, km->cursor);
+    AT_LAUNCH_OK();
+    k_place<<<blocks, 256, 0, st>>>(labels, n_local, km->cursor, km->order);
+    AT_LAUNCH_OK();
+    const float scale = ldexpf(1.0f, km->e_sum);
+    int gblocks = sm_count() * 8;  // 8 warps per block
+    int dpl = (d + 31) / 32;
+    if (dpl <= 1)
+        k_gather_sum<1><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, acc);
+    else if (dpl == 2)
+        k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, acc);
+    else
+        k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, acc);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, float *stats, void *stream) {
+    AT_REQUIRE(km && accum && n_total > 0, "at_kmeans_finalize: bad arguments");
+    AT_REQUIRE(km->begun, "at_kmeans_finalize: call at_kmeans_begin first");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_finalize<<<1, 1024, 0, st>>>((const long long *)accum, km->k, km->d, n_total, ldexp(1.0, -km->e_sum),
+                                   ldexp(1.0, -km->e_obj), km->newc, km->hassign, stats);
+    AT_LAUNCH_OK();
+    return at_index_set_centroids(km->index, km->newc, km->k, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,555 @@
+// libat_b200 stage 1: waveform -> STFT power -> HTK mel -> dB -> per-clip min-max (-> row L2 norm).
+//
+// Replaces, for a whole batch of clips in one launch, what the reference does one clip at a time through
+// torchaudio (processors/spectrogram_generator.py:123-131):
+//   MelSpectrogram.forward  -> torch.stft (reflect pad n_fft/2, periodic Hann, onesided) -> |X|^2 -> fb matmul
+//   AmplitudeToDB.forward   -> 10*log10(clamp(x, 1e-10))
+//   normalize_spectrogram   -> (s - min s) / (max s - min s) over the clip
+//   check_for_nan_inf       -> bad flag
+//
+// Kernel shape (one persistent CTA of 16 warps per SM, clips dealt round-robin):
+//   * a warp owns one "job": 1024 complex points = G complex FFTs of n_fft points, each packing TWO real
+//     frames (frame a -> real part, frame b -> imaginary part), so no arithmetic is spent on the redundant
+//     half of a real-input transform;
+//   * n_fft = 32 * N2 is split Cooley-Tukey style: an N2-point FFT inside each lane's registers, a twiddle
+//     multiply, one 32x32 transpose through the warp's private shared-memory tile, a 32-point FFT in registers;
+//   * the two frames are separated with one shuffle per bin (Z[k], conj Z[n_fft-k]) and their power written
+//     to a shared power tile; 16 jobs fill the tile;
+//   * the mel projection runs thread-per-(frame, filter) over the tile using the filterbank's sparsity
+//     (each triangular filter touches only its own bin range), then 10*log10, a transposed shared tile and
+//     coalesced 128-bit stores; min/max are tracked on the way out;
+//   * after the clip's last frame the CTA normalises the clip's tile in place (it is still in L2).
+#include "at_common.cuh"
+#include "at_index.cuh"
+
+#include <math.h>
+#include <new>
+#include <vector>
+
+struct at_mel_plan {
+    int sample_rate = 0, n_fft = 0, hop = 0, n_mels = 0, normalize = 0;
+    int log2nf = 0;
+    // device constants
+    float *win = nullptr;     // n_fft
+    float2 *tw = nullptr;     // N2 * 32 inter-pass twiddles [k2][n1]
+    int *fstart = nullptr;    // n_mels: first bin of each filter's support
+    int *fcnt = nullptr;      // n_mels: bins in the support
+    int *woff = nullptr;      // n_mels: offset into wt
+    float *wt = nullptr;      // concatenated non-zero weights, pre-scaled by 1/4
+    // host copies
+    std::vector<float> h_win, h_fb;
+    // staging for the _host entry point
+    float *stage_in[2] = {nullptr, nullptr};
+    float *stage_out[2] = {nullptr, nullptr};
+    int32_t *stage_bad[2] = {nullptr, nullptr};
+    int64_t stage_clips = 0, stage_samples = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+};
+
+namespace at {
+
+// ---------------------------------------------------------------------------------------------
+// compile-time twiddles: W_32^m = (c32(m), -s32(m)), m in [0, 16)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr float c32(int m) {
+    switch (m & 31) {
+        case 0: return 1.0f;
+        case 1: return 0.98078528040323044913f;
+        case 2: return 0.92387953251128675613f;
+        case 3: return 0.83146961230254523708f;
+        case 4: return 0.70710678118654752440f;
+        case 5: return 0.55557023301960222474f;
+        case 6: return 0.38268343236508977173f;
+        case 7: return 0.19509032201612826785f;
+        case 8: return 0.0f;
+        case 9: return -0.19509032201612826785f;
+        case 10: return -0.38268343236508977173f;
+        case 11: return -0.55557023301960222474f;
+        case 12: return -0.70710678118654752440f;
+        case 13: return -0.83146961230254523708f;
+        case 14: return -0.92387953251128675613f;
+        case 15: return -0.98078528040323044913f;
+        default: return 0.0f;
+    }
+}
+// sin(2 pi m / 32) for m in [0, 16): cos(pi/2 - x) below the quarter turn, cos(x - pi/2) above it
+__host__ __device__ constexpr float s32(int m) { return m <= 8 ? c32(8 - m) : c32(m - 8); }
+
+__host__ __device__ constexpr int brev(int p, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; i++) r |= ((p >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+
+// In-place radix-2 decimation-in-frequency FFT of N points held in registers (all indices static after
+// unrolling).  Output position p holds frequency brev(p).
+template <int N>
+__device__ __forceinline__ void fft_dif(float *re, float *im) {
+    constexpr float R = 0.70710678118654752440f;
+#pragma unroll
+    for (int h = N / 2; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int b = 0; b < N; b += 2 * h) {
+#pragma unroll
+            for (int j = 0; j < h; j++) {
+                const int m = j * (16 / h);  // W_{2h}^j = W_32^m
+                const float ar = re[b + j], ai = im[b + j];
+                const float br = re[b + j + h], bi = im[b + j + h];
+                re[b + j] = ar + br;
+                im[b + j] = ai + bi;
+                const float tr = ar - br, ti = ai - bi;
+                if (m == 0) {
+                    re[b + j + h] = tr;
+                    im[b + j + h] = ti;
+                } else if (m == 8) {  // -i
+                    re[b + j + h] = ti;
+                    im[b + j + h] = -tr;
+                } else if (m == 4) {  // (1 - i)/sqrt2
+                    re[b + j + h] = (tr + ti) * R;
+                    im[b + j + h] = (ti - tr) * R;
+                } else if (m == 12) {  // (-1 - i)/sqrt2
+                    re[b + j + h] = (ti - tr) * R;
+                    im[b + j + h] = -(tr + ti) * R;
+                } else {  // (tr + i ti)(c - i s)
+                    const float c = c32(m), s = s32(m);
+                    re[b + j + h] = fmaf(tr, c, ti * s);
+                    im[b + j + h] = fmaf(ti, c, -(tr * s));
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int64_t reflect_index(int64_t s, int64_t L) {
+    if (s < 0) s = -s;
+    if (s >= L) s = 2 * (L - 1) - s;
+    return s;
+}
+
+constexpr int MEL_WARPS = 16;
+constexpr int MEL_THREADS = MEL_WARPS * 32;
+constexpr int XCH_STRIDE = 33;                          // float2 per exchange row (32 + 1 pad)
+constexpr int XCH_WARP_F2 = 32 * XCH_STRIDE;            // float2 per warp
+constexpr int XCH_BYTES = MEL_WARPS * XCH_WARP_F2 * 8;  // 135,168
+
+template <int LOG2NF>
+struct MelCfg {
+    static constexpr int NF = 1 << LOG2NF;
+    static constexpr int N2 = NF / 32;       // in-lane FFT size of pass 1
+    static constexpr int LOG2N2 = LOG2NF - 5;
+    static constexpr int G = 32 / N2;        // complex FFTs per job
+    static constexpr int FR = 2 * G;         // real frames per job
+    static constexpr int BF = MEL_WARPS * FR;  // frames per batch
+    static constexpr int NB = NF / 2 + 1;    // bins
+    static constexpr int P_FLOATS = BF * NB;
+    static constexpr size_t SMEM = (size_t)XCH_BYTES + (size_t)P_FLOATS * 4 + (size_t)N2 * 32 * 8 + (size_t)NF * 4;
+};
+
+template <int LOG2NF>
+__global__ void __launch_bounds__(MEL_THREADS, 1)
+k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets,
+      const int64_t *__restrict__ frame_offsets, int64_t uniform_samples, int B, int hop, int n_mels,
+      int normalize, const float *__restrict__ g_win, const float2 *__restrict__ g_tw,
+      const int *__restrict__ fstart, const int *__restrict__ fcnt, const int *__restrict__ woff,
+      const float *__restrict__ wt, float *__restrict__ out, float *__restrict__ out_l2,
+      int32_t *__restrict__ bad_flags) {
+    using C = MelCfg<LOG2NF>;
+    constexpr int NF = C::NF, N2 = C::N2, G = C::G, FR = C::FR, BF = C::BF, NB = C::NB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *xch_all = reinterpret_cast<float2 *>(smem_raw);
+    float *dtile = reinterpret_cast<float *>(smem_raw);  // aliases the exchange region (mel stage only)
+    float *ptile = reinterpret_cast<float *>(smem_raw + XCH_BYTES);
+    float2 *s_tw = reinterpret_cast<float2 *>(smem_raw + XCH_BYTES + (size_t)C::P_FLOATS * 4);
+    float *s_win = reinterpret_cast<float *>(smem_raw + XCH_BYTES + (size_t)C::P_FLOATS * 4 + (size_t)N2 * 32 * 8);
+    __shared__ float s_red[2][MEL_WARPS];
+    __shared__ int s_flag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < N2 * 32; i += MEL_THREADS) s_tw[i] = g_tw[i];
+    for (int i = tid; i < NF; i += MEL_THREADS) s_win[i] = g_win[i];
+    __syncthreads();
+
+    float2 *xch = xch_all + warp * XCH_WARP_F2;
+    const int dstride = n_mels + 1;
+    // pass-2 role of this lane: complex FFT g2, residue k2
+    const int g2 = lane / N2, k2 = lane % N2;
+    const int partner = g2 * N2 + ((N2 - k2) & (N2 - 1));
+
+    for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
+        const int64_t s0 = sample_offsets ? sample_offsets[clip] : (int64_t)clip * uniform_samples;
+        const int64_t L = sample_offsets ? sample_offsets[clip + 1] - s0 : uniform_samples;
+        const int64_t T = 1 + L / hop;
+        const int64_t f0 = frame_offsets ? frame_offsets[clip] : (int64_t)clip * (1 + uniform_samples / hop);
+        const float *x = wave + s0;
+        float *dst = out + f0 * n_mels;
+        if (L <= NF / 2) {  // torch's reflect pad raises: pad must be smaller than the input
+            if (tid == 0 && bad_flags) bad_flags[clip] = 2;
+            continue;
+        }
+        float vmin = INFINITY, vmax = -INFINITY;
+        int nonfinite = 0;
+
+        for (int64_t t0 = 0; t0 < T; t0 += BF) {
+            // ------------------------------------------------------------ phase A: FFT -> power tile
+            {
+                float zr[32], zi[32];
+                const int64_t tj = t0 + (int64_t)warp * FR;
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        const int64_t f = tj + 2 * g + half;
+                        float *dstv = half ? zi : zr;
+                        const int64_t start = f * hop - NF / 2;
+                        if (f < T && start >= 0 && start + NF <= L) {
+#pragma unroll
+                            for (int n2 = 0; n2 < N2; n2++)
+                                dstv[g * N2 + n2] = __ldg(x + start + lane + 32 * n2) * s_win[lane + 32 * n2];
+                        } else if (f < T) {
+#pragma unroll
+                            for (int n2 = 0; n2 < N2; n2++)
+                                dstv[g * N2 + n2] =
+                                    __ldg(x + reflect_index(start + lane + 32 * n2, L)) * s_win[lane + 32 * n2];
+                        } else {
+#pragma unroll
+                            for (int n2 = 0; n2 < N2; n2++) dstv[g * N2 + n2] = 0.f;
+                        }
+                    }
+                }
+                // pass 1: N2-point FFTs over n2, then twiddle W_NF^(n1*k2), then transpose
+#pragma unroll
+                for (int g = 0; g < G; g++) fft_dif<N2>(zr + g * N2, zi + g * N2);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+#pragma unroll
+                    for (int p = 0; p < N2; p++) {
+                        const int kk = brev(p, C::LOG2N2);
+                        const float2 w = s_tw[kk * 32 + lane];
+                        const float a = zr[g * N2 + p], b = zi[g * N2 + p];
+                        float2 v;
+                        v.x = fmaf(a, w.x, -(b * w.y));
+                        v.y = fmaf(a, w.y, b * w.x);
+                        xch[(g * N2 + kk) * XCH_STRIDE + lane] = v;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++) {
+                    const float2 v = xch[lane * XCH_STRIDE + n1];
+                    zr[n1] = v.x;
+                    zi[n1] = v.y;
+                }
+                __syncwarp();
+                // pass 2: 32-point FFT over n1; position p holds k1 = brev5(p); Z[N2*k1 + k2]
+                fft_dif<32>(zr, zi);
+                // separate the two real frames and store |.|^2 (the 1/4 lives in the mel weights)
+                float *pa = ptile + (size_t)(warp * FR + 2 * g2) * NB;
+                float *pb = pa + NB;
+#pragma unroll
+                for (int k1 = 0; k1 < 16; k1++) {
+                    const float Zr = zr[brev(k1, 5)], Zi = zi[brev(k1, 5)];
+                    const float qr = k2 == 0 ? zr[brev((32 - k1) & 31, 5)] : zr[brev(31 - k1, 5)];
+                    const float qi = k2 == 0 ? zi[brev((32 - k1) & 31, 5)] : zi[brev(31 - k1, 5)];
+                    const float pr = __shfl_sync(0xffffffffu, qr, partner);
+                    const float pi = __shfl_sync(0xffffffffu, qi, partner);
+                    const float ar = Zr + pr, ai = Zi - pi, br = Zi + pi, bi = pr - Zr;
+                    pa[N2 * k1 + k2] = fmaf(ar, ar, ai * ai);
+                    pb[N2 * k1 + k2] = fmaf(br, br, bi * bi);
+                }
+                if (k2 == 0) {  // Nyquist bin: Z[NF/2] is its own partner
+                    const float Zr = zr[brev(16, 5)], Zi = zi[brev(16, 5)];
+                    pa[NF / 2] = 4.f * Zr * Zr;
+                    pb[NF / 2] = 4.f * Zi * Zi;
+                }
+            }
+            __syncthreads();
+            // ------------------------------------------------------------ phase C: sparse mel + dB
+            {
+                constexpr int FG = BF / 32;  // frame groups of 32
+                for (int item = warp; item < FG * n_mels; item += MEL_WARPS) {
+                    const int fg = item % FG, m = item / FG;
+                    const int f = fg * 32 + lane;
+                    const float *prow = ptile + (size_t)f * NB;
+                    const int k0 = fstart[m], cnt = fcnt[m];
+                    const float *w = wt + woff[m];
+                    float acc = 0.f;
+                    for (int i = 0; i < cnt; i++) acc = fmaf(__ldg(w + i), prow[k0 + i], acc);
+                    dtile[f * dstride + m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
+                }
+            }
+            __syncthreads();
+            // ------------------------------------------------------------ phase D: coalesced write-out
+            {
+                const int64_t nf = min((int64_t)BF, T - t0);
+                const int total = (int)nf * n_mels;
+                float *o = dst + t0 * n_mels;
+                for (int i = tid; i < total; i += MEL_THREADS) {
+                    const int f = i / n_mels, m = i - f * n_mels;
+                    const float v = dtile[f * dstride + m];
+                    vmin = fminf(vmin, v);
+                    vmax = fmaxf(vmax, v);
+                    nonfinite |= !isfinite(v);
+                    o[i] = v;
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---------------------------------------------------------------- clip epilogue
+        vmin = warp_min(vmin);
+        vmax = warp_max(vmax);
+        if (lane == 0) s_red[0][warp] = vmin, s_red[1][warp] = vmax;
+        if (tid == 0) s_flag = 0;
+        __syncthreads();
+        float mn = s_red[0][0], mx = s_red[1][0];
+#pragma unroll
+        for (int w = 1; w < MEL_WARPS; w++) mn = fminf(mn, s_red[0][w]), mx = fmaxf(mx, s_red[1][w]);
+        if (normalize || out_l2) {
+            // half-warp per frame row; chunk class g handles elements 4g..4g+3 (+64, +128, ...)
+            const float range = __fsub_rn(mx, mn);
+            const int g = tid & 15;
+            for (int64_t r = tid >> 4; r < T; r += MEL_THREADS / 16) {
+                float *row = dst + r * n_mels;
+                float q = 0.f;
+                for (int base = 4 * g; base < n_mels; base += 64) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (base + e < n_mels) {
+                            float v = __ldcg(row + base + e);
+                            if (normalize) {
+                                v = __fdiv_rn(__fsub_rn(v, mn), range);
+                                nonfinite |= !isfinite(v);
+                                row[base + e] = v;
+                            }
+                            q = fmaf(v, v, q);
+                        }
+                    }
+                }
+                if (out_l2) {
+                    const float den = l2_denominator(half16_sum(q));
+                    float *orow = out_l2 + (f0 + r) * n_mels;
+                    for (int base = 4 * g; base < n_mels; base += 64) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            if (base + e < n_mels) {
+                                // final value of the row (this thread wrote it just above when normalising)
+                                orow[base + e] = __fdiv_rn(__ldcg(row + base + e), den);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (nonfinite) s_flag = 1;
+        __syncthreads();
+        if (tid == 0 && bad_flags) bad_flags[clip] = s_flag;
+        __syncthreads();
+    }
+}
+
+static void build_filterbank_htk(int sample_rate, int n_fft, int n_mels, std::vector<float> &fb) {
+    // torchaudio.functional.melscale_fbanks(n_freqs, 0, sr/2, n_mels, sr, norm=None, mel_scale="htk")
+    // (functional.py:518-587), evaluated in double and rounded once.
+    const int nb = n_fft / 2 + 1;
+    const double f_max = (double)(sample_rate / 2);  // MelScale default f_max = float(sample_rate // 2)
+    const double m_min = 2595.0 * log10(1.0 + 0.0 / 700.0);
+    const double m_max = 2595.0 * log10(1.0 + f_max / 700.0);
+    std::vector<double> f_pts(n_mels + 2);
+    for (int i = 0; i < n_mels + 2; i++) {
+        double m = m_min + (m_max - m_min) * (double)i / (double)(n_mels + 1);
+        f_pts[i] = 700.0 * (pow(10.0, m / 2595.0) - 1.0);
+    }
+    fb.assign((size_t)nb * n_mels, 0.f);
+    for (int k = 0; k < nb; k++) {
+        double freq = (double)(sample_rate / 2) * (double)k / (double)(nb - 1);
+        for (int m = 0; m < n_mels; m++) {
+            double down = (freq - f_pts[m]) / (f_pts[m + 1] - f_pts[m]);
+            double up = (f_pts[m + 2] - freq) / (f_pts[m + 2] - f_pts[m + 1]);
+            double v = down < up ? down : up;
+            fb[(size_t)k * n_mels + m] = v > 0.0 ? (float)v : 0.f;
+        }
+    }
+}
+
+static int upload_constants(at_mel_plan *p) {
+    const int nf = p->n_fft, nb = nf / 2 + 1, nm = p->n_mels, n2 = nf / 32;
+    // CSR by filter of the dense (nb, nm) filterbank; support = [first non-zero, last non-zero]
+    std::vector<int> fstart(nm), fcnt(nm), woff(nm);
+    std::vector<float> wt;
+    for (int m = 0; m < nm; m++) {
+        int lo = nb, hi = -1;
+        for (int k = 0; k < nb; k++)
+            if (p->h_fb[(size_t)k * nm + m] != 0.f) {
+                if (k < lo) lo = k;
+                hi = k;
+            }
+        fstart[m] = hi < 0 ? 0 : lo;
+        fcnt[m] = hi < 0 ? 0 : hi - lo + 1;
+        woff[m] = (int)wt.size();
+        for (int k = fstart[m]; k < fstart[m] + fcnt[m]; k++) wt.push_back(0.25f * p->h_fb[(size_t)k * nm + m]);
+    }
+    if (wt.empty()) wt.push_back(0.f);
+    std::vector<float2> tw((size_t)n2 * 32);
+    for (int kk = 0; kk < n2; kk++)
+        for (int n1 = 0; n1 < 32; n1++) {
+            double a = -2.0 * M_PI * (double)((n1 * kk) % nf) / (double)nf;
+            tw[(size_t)kk * 32 + n1] = make_float2((float)cos(a), (float)sin(a));
+        }
+    cudaFree(p->wt);
+    p->wt = nullptr;
+    AT_CUDA_OK(cudaMalloc(&p->wt, sizeof(float) * wt.size()));
+    if (!p->win) {
+        AT_CUDA_OK(cudaMalloc(&p->win, sizeof(float) * nf));
+        AT_CUDA_OK(cudaMalloc(&p->tw, sizeof(float2) * tw.size()));
+        AT_CUDA_OK(cudaMalloc(&p->fstart, sizeof(int) * nm));
+        AT_CUDA_OK(cudaMalloc(&p->fcnt, sizeof(int) * nm));
+        AT_CUDA_OK(cudaMalloc(&p->woff, sizeof(int) * nm));
+    }
+    AT_CUDA_OK(cudaMemcpy(p->win, p->h_win.data(), sizeof(float) * nf, cudaMemcpyHostToDevice));
+    AT_CUDA_OK(cudaMemcpy(p->tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice));
+    AT_CUDA_OK(cudaMemcpy(p->fstart, fstart.data(), sizeof(int) * nm, cudaMemcpyHostToDevice));
+    AT_CUDA_OK(cudaMemcpy(p->fcnt, fcnt.data(), sizeof(int) * nm, cudaMemcpyHostToDevice));
+    AT_CUDA_OK(cudaMemcpy(p->woff, woff.data(), sizeof(int) * nm, cudaMemcpyHostToDevice));
+    AT_CUDA_OK(cudaMemcpy(p->wt, wt.data(), sizeof(float) * wt.size(), cudaMemcpyHostToDevice));
+    return AT_OK;
+}
+
+template <int LOG2NF>
+static int launch_mel(at_mel_plan *p, const float *wave, const int64_t *so, const int64_t *fo, int64_t us, int B,
+                      float *out, float *out_l2, int32_t *bad, cudaStream_t st) {
+    using C = MelCfg<LOG2NF>;
+    static bool configured = false;
+    if (!configured) {
+        AT_CUDA_OK(cudaFuncSetAttribute(k_mel<LOG2NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    int grid = sm_count();
+    if (grid > B) grid = B;
+    if (grid < 1) grid = 1;
+    k_mel<LOG2NF><<<grid, MEL_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->win,
+                                                     p->tw, p->fstart, p->fcnt, p->woff, p->wt, out, out_l2, bad);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+}  // namespace at
+
+using namespace at;
+
+extern "C" {
+
+int at_mel_plan_create(int sample_rate, int n_fft, int hop_length, int n_mels, int normalize, at_mel_plan **plan) {
+    AT_REQUIRE(plan, "at_mel_plan_create: null plan pointer");
+    AT_REQUIRE(sample_rate > 0 && hop_length > 0 && n_mels > 0, "at_mel_plan_create: bad arguments");
+    if (!(n_fft == 256 || n_fft == 512 || n_fft == 1024)) {
+        set_error("at_mel_plan_create: n_fft=%d is not covered (256, 512, 1024 are)", n_fft);
+        return AT_ERR_UNSUPPORTED;
+    }
+    if (n_mels > 256) {
+        set_error("at_mel_plan_create: n_mels=%d > 256 is not covered", n_mels);
+        return AT_ERR_UNSUPPORTED;
+    }
+    int dev;
+    AT_CUDA_OK(cudaGetDevice(&dev));
+    at_mel_plan *p = new (std::nothrow) at_mel_plan();
+    if (!p) return AT_ERR_NOMEM;
+    p->sample_rate = sample_rate, p->n_fft = n_fft, p->hop = hop_length, p->n_mels = n_mels, p->normalize = normalize;
+    p->log2nf = ilog2(n_fft);
+    p->h_win.resize(n_fft);
+    for (int n = 0; n < n_fft; n++) p->h_win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)n_fft));
+    build_filterbank_htk(sample_rate, n_fft, n_mels, p->h_fb);
+    int rc = upload_constants(p);
+    if (rc != AT_OK) {
+        at_mel_plan_destroy(p);
+        return rc;
+    }
+    *plan = p;
+    return AT_OK;
+}
+
+int at_mel_plan_set_constants_host(at_mel_plan *p, const float *window, const float *fb) {
+    AT_REQUIRE(p, "at_mel_plan_set_constants_host: null plan");
+    if (window) p->h_win.assign(window, window + p->n_fft);
+    if (fb) p->h_fb.assign(fb, fb + (size_t)(p->n_fft / 2 + 1) * p->n_mels);
+    AT_CUDA_OK(cudaDeviceSynchronize());
+    return upload_constants(p);
+}
+
+int at_mel_plan_destroy(at_mel_plan *p) {
+    if (!p) return AT_OK;
+    cudaFree(p->win), cudaFree(p->tw), cudaFree(p->fstart), cudaFree(p->fcnt), cudaFree(p->woff), cudaFree(p->wt);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(p->stage_in[i]), cudaFree(p->stage_out[i]), cudaFree(p->stage_bad[i]);
+        if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
+    }
+    delete p;
+    return AT_OK;
+}
+
+int64_t at_mel_num_frames(const at_mel_plan *p, int64_t n_samples) {
+    if (!p || n_samples < 0) return -1;
+    return 1 + n_samples / p->hop;
+}
+
+int at_mel_forward(at_mel_plan *p, const float *wave, const int64_t *sample_offsets, const int64_t *frame_offsets,
+                   int64_t uniform_samples, int B, float *out, float *out_l2, int32_t *bad_flags, void *stream) {
+    AT_REQUIRE(p && wave && out && B >= 0, "at_mel_forward: bad arguments");
+    AT_REQUIRE((sample_offsets == nullptr) == (frame_offsets == nullptr),
+               "at_mel_forward: pass both offset arrays or neither");
+    AT_REQUIRE(sample_offsets || uniform_samples > 0, "at_mel_forward: uniform_samples must be > 0 without offsets");
+    if (B == 0) return AT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p->log2nf) {
+        case 8: return launch_mel<8>(p, wave, sample_offsets, frame_offsets, uniform_samples, B, out, out_l2, bad_flags, st);
+        case 9: return launch_mel<9>(p, wave, sample_offsets, frame_offsets, uniform_samples, B, out, out_l2, bad_flags, st);
+        case 10: return launch_mel<10>(p, wave, sample_offsets, frame_offsets, uniform_samples, B, out, out_l2, bad_flags, st);
+    }
+    set_error("at_mel_forward: unsupported n_fft");
+    return AT_ERR_UNSUPPORTED;
+}
+
+int at_mel_forward_host(at_mel_plan *p, const float *wave, int64_t uniform_samples, int B, float *out,
+                        int32_t *bad_flags) {
+    AT_REQUIRE(p && wave && out && B >= 0 && uniform_samples > 0, "at_mel_forward_host: bad arguments");
+    if (B == 0) return AT_OK;
+    const int64_t T = 1 + uniform_samples / p->hop;
+    // chunk = a few waves of the persistent grid, bounded to ~256 MB of samples per buffer
+    int64_t chunk = (int64_t)sm_count() * 2;
+    const int64_t max_chunk = (256LL << 20) / (uniform_samples * 4) > 0 ? (256LL << 20) / (uniform_samples * 4) : 1;
+    if (chunk > max_chunk) chunk = max_chunk;
+    if (chunk > B) chunk = B;
+    if (p->stage_clips < chunk || p->stage_samples != uniform_samples) {
+        AT_CUDA_OK(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; i++) {
+            cudaFree(p->stage_in[i]), cudaFree(p->stage_out[i]), cudaFree(p->stage_bad[i]);
+            p->stage_in[i] = p->stage_out[i] = nullptr, p->stage_bad[i] = nullptr;
+            AT_CUDA_OK(cudaMalloc(&p->stage_in[i], sizeof(float) * (size_t)(chunk * uniform_samples)));
+            AT_CUDA_OK(cudaMalloc(&p->stage_out[i], sizeof(float) * (size_t)(chunk * T * p->n_mels)));
+            AT_CUDA_OK(cudaMalloc(&p->stage_bad[i], sizeof(int32_t) * (size_t)chunk));
+            if (!p->streams[i]) AT_CUDA_OK(cudaStreamCreateWithFlags(&p->streams[i], cudaStreamNonBlocking));
+        }
+        p->stage_clips = chunk, p->stage_samples = uniform_samples;
+    }
+    int buf = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, buf ^= 1) {
+        const int64_t nb = B - b0 < chunk ? B - b0 : chunk;
+        cudaStream_t st = p->streams[buf];  // stream order serialises reuse of this buffer
+        AT_CUDA_OK(cudaMemcpyAsync(p->stage_in[buf], wave + b0 * uniform_samples,
+                                   sizeof(float) * (size_t)(nb * uniform_samples), cudaMemcpyHostToDevice, st));
+        AT_CUDA_OK(cudaMemsetAsync(p->stage_bad[buf], 0, sizeof(int32_t) * (size_t)nb, st));
+        int rc = at_mel_forward(p, p->stage_in[buf], nullptr, nullptr, uniform_samples, (int)nb, p->stage_out[buf],
+                                nullptr, p->stage_bad[buf], st);
+        if (rc != AT_OK) return rc;
+        AT_CUDA_OK(cudaMemcpyAsync(out + b0 * T * p->n_mels, p->stage_out[buf],
+                                   sizeof(float) * (size_t)(nb * T * p->n_mels), cudaMemcpyDeviceToHost, st));
+        if (bad_flags)
+            AT_CUDA_OK(cudaMemcpyAsync(bad_flags + b0, p->stage_bad[buf], sizeof(int32_t) * (size_t)nb,
+                                       cudaMemcpyDeviceToHost, st));
+    }
+    AT_CUDA_OK(cudaStreamSynchronize(p->streams[0]));
+    AT_CUDA_OK(cudaStreamSynchronize(p->streams[1]));
+    return AT_OK;
+}
+
+}  // extern "C"

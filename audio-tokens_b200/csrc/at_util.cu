@@ -1,0 +1,192 @@
+// libat_b200: error plumbing, device info, bincount, abs-max, synthetic clips.
+#include "at_common.cuh"
+
+#include <string.h>
+#include <random>
+
+namespace at {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = -1;
+    if (cached < 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        cached = n;
+    }
+    return cached;
+}
+
+__global__ void k_absmax(const float *__restrict__ x, int64_t n, float *__restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    m = warp_max(m);
+    // non-negative floats order like their bit patterns
+    if ((threadIdx.x & 31) == 0) atomicMax((int *)out, __float_as_int(m));
+}
+
+__global__ void k_bincount(const int32_t *__restrict__ labels, int64_t n, int k,
+                           unsigned long long *__restrict__ counts) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int l = labels[i];
+        if (l >= 0 && l < k) atomicAdd(&counts[l], 1ULL);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic clips: integer-only twin of oracle/synth_ref.py.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+
+struct SynthPartial {
+    uint32_t hp, inc, phi0;
+    int amp;
+};
+
+__global__ void k_synth(uint32_t seed, int64_t first, int64_t n_samples, const int16_t *__restrict__ table,
+                        float *__restrict__ out) {
+    __shared__ SynthPartial part[8];
+    __shared__ int s_P, s_noise, s_gain;
+    __shared__ uint32_t s_h0;
+    __shared__ int16_t s_tab[4096];
+    int64_t clip = blockIdx.y;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) s_tab[i] = table[i];
+    if (threadIdx.x == 0) {
+        uint32_t h0 = hash32(seed * 0x9E3779B1u + (uint32_t)(first + clip));
+        h0 = hash32(h0 ^ 0x85EBCA6Bu);
+        s_h0 = h0;
+        s_P = 3 + (int)(hash32(h0 + 1u) % 6u);
+        s_noise = 16 + (int)(hash32(h0 + 2u) % 240u);
+        s_gain = 96 + (int)(hash32(h0 + 3u) % 160u);
+        for (int p = 0; p < s_P; p++) {
+            uint32_t hp = hash32(h0 + 16u + (uint32_t)p);
+            uint32_t hq = hash32(hp);
+            part[p].hp = hp;
+            part[p].inc = (15600000u + ((hq >> 8) & 0xFFFFFFu)) << (hp % 7u);
+            part[p].phi0 = hash32(hp + 0x1234567u);
+            part[p].amp = 512 + (int)(hash32(hq + 7u) % 3584u);
+        }
+    }
+    __syncthreads();
+    const int P = s_P, na = s_noise, gain = s_gain;
+    const uint32_t h0 = s_h0;
+    float *dst = out + clip * n_samples;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_samples; n += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t un = (uint32_t)n;
+        uint32_t seg = un >> 13;
+        int r = (int)(un & 8191u);
+        int total = 0;
+        for (int p = 0; p < P; p++) {
+            uint32_t phase = part[p].phi0 + un * part[p].inc;
+            int s = s_tab[phase >> 20];
+            uint32_t hp = part[p].hp;
+            int e0 = (int)(hash32((hp ^ (seg * 0x9E3779B1u)) + 0x55u) % 384u) - 128;
+            int e1 = (int)(hash32((hp ^ ((seg + 1u) * 0x9E3779B1u)) + 0x55u) % 384u) - 128;
+            e0 = e0 < 0 ? 0 : e0;
+            e1 = e1 < 0 ? 0 : e1;
+            int env = (e0 * (8192 - r) + e1 * r) >> 13;
+            total += (((s * part[p].amp) >> 12) * env) >> 8;
+        }
+        total = (total * gain) >> 9;
+        uint32_t hn = hash32(h0 ^ hash32(un + 0x68E31DA4u));
+        int nz = (int)(hn % (uint32_t)(2 * na + 1)) - na;
+        int v = total + nz;
+        v = v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
+        dst[n] = (float)v * (1.0f / 32768.0f);
+    }
+}
+
+}  // namespace at
+
+using namespace at;
+
+extern "C" {
+
+int at_version(void) { return AT_B200_VERSION; }
+
+const char *at_last_error(void) { return g_err; }
+
+int at_device_info(int *sm, int *major, int *minor) {
+    int dev = 0;
+    AT_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    AT_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+    if (sm) *sm = p.multiProcessorCount;
+    if (major) *major = p.major;
+    if (minor) *minor = p.minor;
+    return AT_OK;
+}
+
+int at_absmax(const float *x, int64_t n_elems, float *out_dev, void *stream) {
+    AT_REQUIRE(x && out_dev && n_elems >= 0, "at_absmax: bad arguments");
+    AT_CUDA_OK(cudaMemsetAsync(out_dev, 0, sizeof(float), (cudaStream_t)stream));
+    if (n_elems == 0) return AT_OK;
+    int blocks = (int)(ceil_div(n_elems, 256 * 8) < (int64_t)sm_count() * 8 ? ceil_div(n_elems, 256 * 8) : (int64_t)sm_count() * 8);
+    if (blocks < 1) blocks = 1;
+    k_absmax<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elems, out_dev);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+int at_bincount(const int32_t *labels, int64_t n, int k, int64_t *counts, void *stream) {
+    AT_REQUIRE(labels && counts && n >= 0 && k > 0, "at_bincount: bad arguments");
+    AT_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int64_t) * (size_t)k, (cudaStream_t)stream));
+    if (n == 0) return AT_OK;
+    int blocks = sm_count() * 4;
+    if (blocks < 1) blocks = 1;
+    k_bincount<<<blocks, 256, 0, (cudaStream_t)stream>>>(labels, n, k, (unsigned long long *)counts);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+int at_rand_perm_host(int32_t *perm, int64_t n, int64_t seed) {
+    AT_REQUIRE(perm && n >= 0 && n < (1LL << 31), "at_rand_perm_host: bad arguments");
+    std::mt19937 mt((unsigned)seed);
+    for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+    for (int64_t i = 0; i + 1 < n; i++) {
+        int64_t i2 = i + (int64_t)((uint64_t)mt() % (uint64_t)(n - i));
+        int32_t t = perm[i];
+        perm[i] = perm[i2];
+        perm[i2] = t;
+    }
+    return AT_OK;
+}
+
+int at_synth_clips(uint32_t seed, int64_t first_index, int64_t count, int64_t n_samples,
+                   const int16_t *sine_table4096, float *out, void *stream) {
+    AT_REQUIRE(sine_table4096 && out && count >= 0 && n_samples > 0, "at_synth_clips: bad arguments");
+    AT_REQUIRE(n_samples < (1LL << 31), "at_synth_clips: n_samples too large");
+    int64_t done = 0;
+    while (done < count) {  // gridDim.y limit
+        int64_t chunk = count - done < 32768 ? count - done : 32768;
+        int bx = (int)(ceil_div(n_samples, 256 * 16) < 64 ? ceil_div(n_samples, 256 * 16) : 64);
+        dim3 grid(bx, (unsigned)chunk);
+        k_synth<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, first_index + done, n_samples, sine_table4096,
+                                                          out + done * n_samples);
+        AT_LAUNCH_OK();
+        done += chunk;
+    }
+    return AT_OK;
+}
+
+}  // extern "C"

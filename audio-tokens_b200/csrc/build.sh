@@ -1,0 +1,17 @@
+#!/bin/bash
+# Builds libat_b200.so for sm_100a, in-tree (audio-tokens_b200/at_b200/libat_b200.so).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../at_b200/libat_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /usr/bin/g++
+       -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -Xptxas -v)
+mkdir -p "$HERE/obj"
+pids=()
+for f in at_util at_kmeans at_mel at_assign_tc; do
+  ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" > "$HERE/obj/$f.log" 2>&1 || { cat "$HERE/obj/$f.log"; exit 1; } ) &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -shared -o "$OUT" "$HERE"/obj/at_util.o "$HERE"/obj/at_kmeans.o "$HERE"/obj/at_mel.o "$HERE"/obj/at_assign_tc.o -lcudart
+echo "built $OUT"

@@ -1,0 +1,162 @@
+/*
+ * audio_tokens_b200.h -- C ABI of the B200-native audio-tokens hot path.
+ *
+ * One shared library (libat_b200.so, built from audio-tokens_b200/csrc) replaces the three library
+ * call sites of danavery/audio-tokens' preprocessing path.  Every entry point takes plain pointers and
+ * sizes; there are no torch / numpy types here.  Unless a name ends in `_host`, all data pointers are
+ * DEVICE pointers owned by the caller and every call is stream-ordered on the `stream` argument
+ * (a cudaStream_t passed as void*; NULL = the legacy default stream).  Calls return 0 on success or a
+ * negative at_status; at_last_error() gives the thread-local message.  The library owns only the opaque
+ * plan / index / k-means objects, freed by *_destroy.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with AT_ERR_CUDA.
+ *
+ * Reference interface each group replaces (paths relative to the reference repo):
+ *
+ *   at_mel_*     processors/spectrogram_generator.py:28-34 (MelSpectrogram + AmplitudeToDB construction),
+ *                :123-126 generate_mel_spectrogram, :128-131 normalize_spectrogram, :133-146 check_for_nan_inf;
+ *                i.e. torchaudio.transforms.MelSpectrogram / AmplitudeToDB on (1, L) tensors.
+ *   at_row_l2norm  processors/cluster_creator.py:64-66 and processors/spec_tokenizer.py:106-109
+ *                (normalize_vectors: v / (||v|| + 1e-10)).
+ *   at_index_*   faiss.IndexFlatL2(d) / .add / .search(x, 1) as used in processors/spec_tokenizer.py:123-127,77
+ *                and inside faiss.Kmeans.train (processors/cluster_creator.py:54-56).
+ *   at_kmeans_*  faiss.Kmeans(d, k, niter=, ...).train(x[, init_centroids]) -> Clustering::train
+ *                (processors/cluster_creator.py:42-58): one Lloyd iteration = accumulate (+ optional
+ *                all-reduce by the caller) + finalize.
+ *   at_synth_*   no reference counterpart: synthetic 16-bit-PCM clips for tests and benchmarks.
+ */
+#ifndef AUDIO_TOKENS_B200_H
+#define AUDIO_TOKENS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AT_B200_VERSION 100 /* 0.1.0 */
+
+typedef enum at_status {
+    AT_OK = 0,
+    AT_ERR_INVALID = -1,     /* bad argument (null pointer, unsupported n_fft / d, k > limits ...) */
+    AT_ERR_CUDA = -2,        /* a CUDA runtime call failed (including: no device) */
+    AT_ERR_UNSUPPORTED = -3, /* valid request the kernels do not cover (stated in the message) */
+    AT_ERR_NOMEM = -4
+} at_status;
+
+int at_version(void);
+const char *at_last_error(void);
+/* sm_count / compute capability of the current device; AT_ERR_CUDA when there is none. */
+int at_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1: waveform -> mel dB spectrogram (+ optional per-clip min-max, + optional row L2 norm)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct at_mel_plan at_mel_plan;
+
+/* MelSpectrogram(sample_rate, n_mels, n_fft, hop_length) + AmplitudeToDB() with torchaudio defaults:
+ * periodic Hann (win_length = n_fft), center + reflect pad, power 2, HTK filterbank, f_min 0,
+ * f_max sample_rate/2, norm None, 10*log10(max(x,1e-10)).  n_fft in {256, 512, 1024}; n_mels <= 256.
+ * normalize != 0 applies (s - min s) / (max s - min s) over each clip (normalize_spectrogram). */
+int at_mel_plan_create(int sample_rate, int n_fft, int hop_length, int n_mels, int normalize, at_mel_plan **plan);
+/* Optional: replace the built-in constants by the caller's (HOST pointers): window[n_fft] and the dense
+ * filterbank fb[(n_fft/2+1) * n_mels] (row = frequency bin), e.g. the tensors torchaudio itself builds. */
+int at_mel_plan_set_constants_host(at_mel_plan *plan, const float *window, const float *fb);
+int at_mel_plan_destroy(at_mel_plan *plan);
+/* 1 + n_samples / hop_length (center=True). */
+int64_t at_mel_num_frames(const at_mel_plan *plan, int64_t n_samples);
+
+/* B clips.  Clip b occupies wave[sample_offsets[b] .. sample_offsets[b+1]) and writes frames
+ * out[frame_offsets[b] .. frame_offsets[b+1]) x n_mels, FRAME-MAJOR ([T][n_mels], the physical layout of
+ * the reference's fortran_order (n_mels, T) .npy files).  sample_offsets / frame_offsets are DEVICE arrays
+ * of B+1 int64; pass NULL for both to mean B uniform clips of `uniform_samples` samples each.
+ * bad_flags[b] (may be NULL): 0 ok, 1 tile holds NaN/Inf (the reference drops the clip), 2 clip shorter than
+ * n_fft/2+1 samples (torch's reflect pad raises).  out_l2 (may be NULL) receives the row-L2-normalised copy
+ * x / (||x|| + 1e-10) that ClusterCreator / SpecTokenizer would compute next. */
+int at_mel_forward(at_mel_plan *plan, const float *wave, const int64_t *sample_offsets,
+                   const int64_t *frame_offsets, int64_t uniform_samples, int B, float *out,
+                   float *out_l2, int32_t *bad_flags, void *stream);
+
+/* Same with HOST buffers (pinned or pageable) and uniform clips: chunks of clips are copied H2D, transformed
+ * and copied back D2H on two streams so copies overlap compute.  Blocks until the result is in out. */
+int at_mel_forward_host(at_mel_plan *plan, const float *wave, int64_t uniform_samples, int B, float *out,
+                        int32_t *bad_flags);
+
+/* ------------------------------------------------------------------------------------------------
+ * normalize_vectors
+ * ---------------------------------------------------------------------------------------------- */
+int at_row_l2norm(const float *x, int64_t n, int d, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 3 (and the inner search of stage 2): nearest centroid under FAISS's
+ * |x|^2 + |c|^2 - 2<x,c> (clamped at 0), lowest index wins exact ties.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct at_index at_index;
+
+enum { AT_ALGO_AUTO = 0, AT_ALGO_SIMT = 1, AT_ALGO_TENSOR = 2 };
+
+int at_index_create(int d, at_index **index);
+int at_index_destroy(at_index *index);
+/* IndexFlatL2.reset() + add(k, centroids): copies the (k, d) fp32 centroids and prepares the operands
+ * (norms; for the tcgen05 path the split-fp16 tiles). */
+int at_index_set_centroids(at_index *index, const float *centroids, int k, void *stream);
+int at_index_ntotal(const at_index *index);
+/* fp32 (k, d) centroids currently held (device pointer, valid until the next set / destroy). */
+const float *at_index_centroids(const at_index *index);
+/* search(x, 1).  l2norm_rows != 0 applies normalize_vectors to each row while loading.
+ * Any of labels32 / labels64 / dist may be NULL.  algo: AT_ALGO_*; AUTO picks the tcgen05 kernel when
+ * d == 64 and k >= 64, else the exact fp32 SIMT kernel.  Both return the argmin of the same fp32 formula
+ * (the tensor path re-checks its top-2 candidates with it). */
+int at_index_search(at_index *index, const float *x, int64_t n, int l2norm_rows, int algo,
+                    int32_t *labels32, int64_t *labels64, float *dist, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2: k-means Lloyd iterations (faiss::Clustering semantics)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct at_kmeans at_kmeans;
+
+int at_kmeans_create(int d, int k, at_kmeans **km);
+int at_kmeans_destroy(at_kmeans *km);
+/* Set / read the current (k, d) fp32 centroids (device pointers). */
+int at_kmeans_set_centroids(at_kmeans *km, const float *centroids, void *stream);
+const float *at_kmeans_centroids(const at_kmeans *km);
+/* Copy the current (k, d) centroids into a caller-owned device buffer. */
+int at_kmeans_get_centroids(const at_kmeans *km, float *out, void *stream);
+/* Must be called once per training set before accumulate: fixes the fixed-point scale of the exact
+ * (order-independent) sums from max |x| and the global row count. max_abs: HOST float, the max |x_ij| over
+ * ALL ranks' rows (at_absmax computes the local one). */
+int at_absmax(const float *x, int64_t n_elems, float *out_dev, void *stream);
+int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total);
+/* Number of int64 words in the accumulator buffer: k*d sums + k counts + 1 objective. */
+int64_t at_kmeans_accum_words(const at_kmeans *km);
+/* Search the local rows against the current centroids and accumulate per-cluster fixed-point sums, counts
+ * and the objective into accum (device int64[at_kmeans_accum_words], overwritten).  labels32 may be NULL.
+ * Sums are exact integers, so adding the buffers of several ranks (all-reduce SUM on int64) gives a result
+ * that does not depend on the rank count or on summation order. */
+int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2norm_rows, int algo,
+                         int64_t *accum, int32_t *labels32, void *stream);
+/* compute_centroids' division + split_clusters (mt19937(1234), EPS = 1/1024) + index refresh from the
+ * (already all-reduced) accum.  stats (device float[4], may be NULL): objective, nsplit, imbalance factor,
+ * number of empty clusters before the split. */
+int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, float *stats, void *stream);
+
+/* faiss::rand_perm(perm, n, seed) (faiss/utils/random.cpp): forward Fisher-Yates driven by std::mt19937(seed),
+ * i2 = i + mt() % (n - i).  HOST function, HOST pointer.  Used for FAISS's training-set subsample (seed 1234)
+ * and random-point initialisation (seed 1235). */
+int at_rand_perm_host(int32_t *perm, int64_t n, int64_t seed);
+
+/* ------------------------------------------------------------------------------------------------
+ * Token histogram (SpecTokenizer.analyze_tokens' Counter) and int32 -> int64 widening
+ * ---------------------------------------------------------------------------------------------- */
+int at_bincount(const int32_t *labels, int64_t n, int k, int64_t *counts, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic clips (bit-identical to oracle/synth_ref.py given the same sine table)
+ * ---------------------------------------------------------------------------------------------- */
+int at_synth_clips(uint32_t seed, int64_t first_index, int64_t count, int64_t n_samples,
+                   const int16_t *sine_table4096, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIO_TOKENS_B200_H */

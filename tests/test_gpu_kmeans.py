@@ -1,0 +1,226 @@
+"""GPU parity of stages 2-3 (at_index_*, at_kmeans_* through the C ABI) against the FAISS restatement."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames(n_clips=40, L=22050 * 2, seed=4242):
+    """L2-normalised mel frames from synthetic clips (the real input distribution of stages 2-3)."""
+    import torch
+    from at_b200 import MelPlan, synth_clips
+
+    plan = MelPlan(22050, 1024, 512, 64, True)
+    w = synth_clips(seed, 0, n_clips, L)
+    spec, bad, l2 = plan.forward(w, want_l2=True)
+    assert (bad == 0).all()
+    return spec.reshape(-1, 64).contiguous(), l2.reshape(-1, 64).contiguous()
+
+
+def _check_labels(labels, x, c, what):
+    """Token parity gate: equal to the fp32 FAISS-formula oracle except rows whose top-2 gap is tiny."""
+    from oracle import faiss_ref
+
+    ref, d1, d2 = faiss_ref.assign_l2_scalar(x, c)
+    l64, e1, e2 = faiss_ref.assign_l2_f64(x, c)
+    gap32 = (d2 - d1) / np.maximum(d1, 1e-30)
+    gap64 = (e2 - e1) / np.maximum(e1, 1e-30)
+    mism = labels != ref
+    rate_1e6 = float((mism & (gap32 >= 1e-6)).mean())
+    print(f"{what}: n={len(labels)} mismatches={int(mism.sum())} outside-1e-6-carve-out rate={rate_1e6:.2e}")
+    # every mismatching row must be a near tie of the expanded fp32 formula
+    assert (gap64[mism] < 1e-4).all(), (what, gap64[mism].max())
+    assert rate_1e6 < 1e-4
+    return ref
+
+
+def test_row_l2norm_matches_numpy():
+    import torch
+    from at_b200 import row_l2norm
+    from oracle import mel_ref
+
+    x = torch.rand(1000, 64, device="cuda")
+    x[3] = 0
+    got = row_l2norm(x).cpu().numpy()
+    np.testing.assert_allclose(got, mel_ref.normalize_rows(x.cpu().numpy()), rtol=2e-6, atol=1e-9)
+    assert (got[3] == 0).all()
+    for d in (7, 16, 100):
+        y = torch.randn(33, d, device="cuda")
+        np.testing.assert_allclose(row_l2norm(y).cpu().numpy(), mel_ref.normalize_rows(y.cpu().numpy()), rtol=2e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("k", [1, 5, 256, 500])
+def test_search_simt_matches_oracle(k):
+    import torch
+    from at_b200 import FlatL2, _lib
+
+    spec, l2 = _frames(20)
+    x = l2[:20000]
+    c = x[torch.randperm(x.shape[0], generator=torch.Generator().manual_seed(k))[:k].cuda()].contiguous()
+    ix = FlatL2(64)
+    ix.set_centroids(c)
+    lab, dist = ix.search(x, algo=_lib.ALGO_SIMT)
+    ref = _check_labels(lab.cpu().numpy(), x.cpu().numpy(), c.cpu().numpy(), f"simt k={k}")
+    # fused normalisation == normalise then search
+    lab2, dist2 = ix.search(spec[:20000], l2norm_rows=True, algo=_lib.ALGO_SIMT)
+    assert torch.equal(lab, lab2) and torch.equal(dist, dist2)
+    # int64 labels
+    lab3, _ = ix.search(x, algo=_lib.ALGO_SIMT, labels_dtype=torch.int64)
+    assert lab3.dtype == torch.int64 and torch.equal(lab3.int(), lab)
+    from oracle import faiss_ref
+
+    _, d1, _ = faiss_ref.assign_l2_f64(x.cpu().numpy(), c.cpu().numpy())
+    np.testing.assert_allclose(dist.cpu().numpy(), d1, rtol=5e-3, atol=5e-7)
+
+
+@pytest.mark.parametrize("d", [8, 33, 128])
+def test_search_other_dims(d):
+    import torch
+    from at_b200 import FlatL2, _lib
+
+    g = torch.Generator(device="cuda").manual_seed(d)
+    x = torch.rand(3001, d, device="cuda", generator=g)
+    c = torch.rand(77, d, device="cuda", generator=g)
+    ix = FlatL2(d)
+    ix.set_centroids(c)
+    lab, dist = ix.search(x, algo=_lib.ALGO_SIMT)
+    _check_labels(lab.cpu().numpy(), x.cpu().numpy(), c.cpu().numpy(), f"simt d={d}")
+
+
+def test_lowest_index_wins_exact_ties_and_empty_input():
+    import torch
+    from at_b200 import FlatL2
+
+    c = torch.zeros(4, 64, device="cuda")
+    c[1] = 1.0
+    c[3] = 1.0
+    ix = FlatL2(64)
+    ix.set_centroids(c)
+    lab, _ = ix.search(torch.ones(130, 64, device="cuda"))
+    assert (lab == 1).all()
+    lab, _ = ix.search(torch.ones(0, 64, device="cuda"))
+    assert lab.numel() == 0
+
+
+def test_faiss_like_index_api():
+    import torch
+    from at_b200 import IndexFlatL2
+    from oracle import faiss_ref
+
+    _, l2 = _frames(10)
+    x = l2[:5000].cpu().numpy()
+    c = x[::50].copy()
+    a = IndexFlatL2(64)
+    a.add(c)
+    D, I = a.search(x, 1)
+    assert D.shape == (5000, 1) and I.shape == (5000, 1) and I.dtype == np.int64 and D.dtype == np.float32
+    assert a.ntotal == len(c)
+    _check_labels(I[:, 0], x, c, "IndexFlatL2")
+
+
+def test_lloyd_single_step_teacher_forced():
+    """Tier (i) of the centroid gate: from the oracle's centroids C_t, one device step gives C_{t+1} within
+    1e-4 (relative L2 per centroid) on every centroid not touched by a label mismatch; same nsplit."""
+    import torch
+    from at_b200 import LloydTrainer
+    from oracle import faiss_ref
+
+    _, l2 = _frames(40)
+    x = l2.cpu().numpy()
+    n, k = x.shape[0], 256
+    cents = x[faiss_ref.rand_perm(n, 1235)[:k]]
+    tr = LloydTrainer(64, k)
+    tr.begin(l2)
+    stats = torch.zeros(4, device="cuda")
+    labels = torch.empty(n, dtype=torch.int32, device="cuda")
+    for it in range(4):
+        ref = faiss_ref.lloyd_step(x, cents, exact=True)
+        tr.set_centroids(torch.from_numpy(cents).cuda())
+        tr.step(l2, stats, labels)
+        got = tr.get_centroids().cpu().numpy()
+        lab = labels.cpu().numpy()
+        touched = np.zeros(k, dtype=bool)
+        mism = lab != ref["labels"]
+        touched[lab[mism]] = True
+        touched[ref["labels"][mism]] = True
+        s = stats.cpu().numpy()
+        assert int(s[1]) == ref["nsplit"]
+        rel = np.linalg.norm(got - ref["centroids"], axis=1) / np.maximum(np.linalg.norm(ref["centroids"], axis=1), 1e-30)
+        print(f"iter {it}: mismatched rows {int(mism.sum())}, touched {int(touched.sum())}, max rel (untouched) {rel[~touched].max():.2e}, obj {s[0]:.6g} vs {ref['obj']:.6g}")
+        assert (rel[~touched] <= 1e-4).all()
+        assert mism.mean() < 1e-4
+        assert abs(s[0] - ref["obj"]) <= 1e-4 * abs(ref["obj"])
+        cents = ref["centroids"]
+
+
+def test_split_clusters_on_device_matches_oracle():
+    """Force empty clusters: duplicate centroids lose every tie to the lower index."""
+    import torch
+    from at_b200 import LloydTrainer
+    from oracle import faiss_ref
+
+    _, l2 = _frames(10)
+    x = l2.cpu().numpy()
+    k = 32
+    cents = x[faiss_ref.rand_perm(x.shape[0], 1235)[:k]].copy()
+    cents[5] = cents[2]
+    cents[17] = cents[2]
+    cents[31] = cents[30]
+    ref = faiss_ref.lloyd_step(x, cents, exact=True)
+    assert ref["nsplit"] == 3
+    tr = LloydTrainer(64, k)
+    tr.begin(l2)
+    tr.set_centroids(torch.from_numpy(cents).cuda())
+    stats = torch.zeros(4, device="cuda")
+    tr.step(l2, stats)
+    s = stats.cpu().numpy()
+    assert int(s[1]) == 3 and int(s[3]) == 3
+    got = tr.get_centroids().cpu().numpy()
+    np.testing.assert_allclose(got, ref["centroids"], rtol=1e-4, atol=1e-7)
+    assert abs(s[2] - faiss_ref.imbalance_factor(ref["counts"])) < 1e-3
+
+
+def test_kmeans_faiss_api_free_running():
+    """Tier (ii): same seeded subsample / init / niter as the oracle; report centroid agreement."""
+    from at_b200 import Kmeans
+    from oracle import faiss_ref
+
+    _, l2 = _frames(40)
+    x = l2.cpu().numpy()  # 40 clips * 87 frames = 3480 rows
+    k = 8                 # 3480 > 8 * 256 -> FAISS subsamples to 2048 rows
+    km = Kmeans(64, k, niter=10, verbose=False, gpu=True)
+    obj = km.train(x)
+    ref = faiss_ref.Kmeans(64, k, niter=10)
+    ref.exact_search = True
+    robj = ref.train(x)
+    assert km.centroids.shape == (k, 64) and km.centroids.dtype == np.float32
+    assert len(km.iteration_stats) == 10 and obj == km.obj[-1]
+    rel = np.linalg.norm(km.centroids - ref.centroids, axis=1) / np.linalg.norm(ref.centroids, axis=1)
+    print("free-running: fraction of centroids within 1e-4:", float((rel <= 1e-4).mean()), "rel obj diff", abs(obj - robj) / robj)
+    assert (rel <= 1e-4).mean() >= 0.75
+    assert abs(obj - robj) <= 1e-3 * robj
+    # continuing from given centroids (the reference's second 10k-file batch, cluster_creator.py:55-56)
+    km2 = Kmeans(64, k, niter=1)
+    km2.train(x, init_centroids=km.centroids)
+    ref2 = faiss_ref.Kmeans(64, k, niter=1)
+    ref2.exact_search = True
+    ref2.train(x, init_centroids=km.centroids)
+    np.testing.assert_allclose(km2.centroids, ref2.centroids, rtol=1e-4, atol=1e-7)
+    with pytest.raises(AttributeError):
+        Kmeans(64, k, bogus=1)
+    with pytest.raises(RuntimeError):
+        Kmeans(64, 100).train(x[:10])
+    bad = x.copy()
+    bad[0, 0] = np.inf
+    with pytest.raises(RuntimeError):
+        Kmeans(64, k).train(bad)
+
+
+def test_bincount():
+    import torch
+    from at_b200 import _lib
+
+    lab = torch.randint(0, 300, (100000,), dtype=torch.int32, device="cuda")
+    counts = torch.empty(300, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.load().at_bincount(_lib.ptr(lab), lab.numel(), 300, _lib.ptr(counts), _lib.stream_ptr()))
+    assert torch.equal(counts, torch.bincount(lab.long(), minlength=300))
