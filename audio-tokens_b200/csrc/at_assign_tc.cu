@@ -1,10 +1,523 @@
-// placeholder until the tcgen05 kernel lands
+// libat_b200: nearest-centroid search on the 5th-generation tensor cores (tcgen05 + TMEM), d == 64.
+//
+// Replaces the blocked sgemm + top-1 scan of faiss::exhaustive_L2sqr_blas (reached from
+// processors/spec_tokenizer.py:77 and, inside faiss.Kmeans.train, processors/cluster_creator.py:54-56).
+//
+// Arithmetic.  The tensor core evaluates, for a tile of 128 rows x 128 centroids,
+//     acc = S^2 * ( |x|^2 + |c|^2 - 2 <x, c> )
+// in ONE chain of 13 tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
+//     x_hi * c_hi  +  x_hi * c_lo  +  x_lo * c_hi          (fp16 hi/lo split of S*x and -2*S*c: ~22 mantissa bits)
+//   + [xn pieces | 2^12 2^12 2^12] * [2^12 2^12 2^12 | cn pieces]   (one extra K=16 step carrying both norms)
+// so the epilogue only has to keep a per-row top-2.  The two candidates are then re-evaluated with the library's
+// canonical fp32 formula (at_index.cuh), the very one the exact SIMT kernel uses, and the smaller wins (lowest
+// index on exact ties).  Token ids therefore agree with the fp32 path except when three or more centroids lie
+// within ~1e-7 (absolute, unit-norm data) of the minimum.
+//
+// Roofline note: 2*N*K*64 algorithmic flops are executed as 3.25x that many fp16 MMA flops.
+//
+// Structure: persistent CTAs (one per SM), 12 warps:
+//   warp 0  lane 0   bulk-copies (cp.async.bulk, TMA engine) the fp32 row tile (128 x 64, contiguous 32 KB)
+//   warp 1  lane 0   issues tcgen05.mma, commits to mbarriers
+//   warp 2           TMEM allocation / deallocation
+//   warp 3  lane 0   bulk-copies centroid operand tiles (36 KB each, pre-swizzled in HBM/L2) into a 3-stage ring
+//   warps 4-7        convert the fp32 tile: optional row L2 normalisation, |x|^2, fp16 hi/lo split written
+//                    straight into the SWIZZLE_128B K-major layout the MMA descriptors expect
+//   warps 8-11       epilogue: tcgen05.ld the accumulator, packed (distance | column) top-2 with FMNMX3,
+//                    fp32 re-check, labels / distances out
 #include "at_index.cuh"
+
 namespace at {
-bool assign_tc_supported(const at_index *) { return false; }
-int assign_tc_prepare(at_index *, cudaStream_t) { return AT_OK; }
-int assign_tc_search(at_index *, const float *, int64_t, int, int32_t *, int64_t *, float *, cudaStream_t) {
-    set_error("tensor path not built");
-    return AT_ERR_UNSUPPORTED;
+
+constexpr int TC_THREADS = 384;
+constexpr int TM = 128;          // rows per tile (UMMA M)
+constexpr int TN = 128;          // centroids per tile (UMMA N)
+constexpr int B_STAGES = 3;
+constexpr uint32_t A_MAIN_BYTES = TM * 128;              // 128 rows x 64 fp16
+constexpr uint32_t AUG_BYTES = TM * 32;                  // 128 rows x 16 fp16, no-swizzle core matrices
+constexpr uint32_t A_BUF_BYTES = 2 * A_MAIN_BYTES + AUG_BYTES;   // hi | lo | aug = 36,864
+constexpr uint32_t B_TILE_BYTES = 2 * TN * 128 + TN * 32;        // hi | lo | aug = 36,864
+constexpr uint32_t XF_BYTES = TM * 64 * 4;                       // 32,768
+
+// shared memory map (dynamic, 1024-B aligned base)
+constexpr uint32_t OFF_XF = 0;
+constexpr uint32_t OFF_A = OFF_XF + XF_BYTES;                    // 2 buffers
+constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 3 stages  (OFF_A, OFF_B multiples of 1024)
+constexpr uint32_t OFF_BAR = OFF_B + B_STAGES * B_TILE_BYTES;    // mbarriers
+constexpr uint32_t OFF_FLAGS = OFF_BAR + 256;                    // row fallback flags 2 x 128 bytes
+constexpr uint32_t TC_SMEM = OFF_FLAGS + 256 + 1024;             // + slack for manual 1024-B alignment
+static_assert(OFF_A % 1024 == 0 && OFF_B % 1024 == 0 && A_BUF_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "align");
+
+enum {
+    BAR_XF_FULL = 0, BAR_XF_EMPTY = 1,
+    BAR_A_FULL = 2,   // +2
+    BAR_A_EMPTY = 4,  // +2
+    BAR_B_FULL = 6,   // +3
+    BAR_B_EMPTY = 9,  // +3
+    BAR_ACC_FULL = 12,   // +2
+    BAR_ACC_EMPTY = 14,  // +2
+    BAR_COUNT = 16
+};
+
+constexpr float AUG_ONE = 4096.0f;            // 2^12, exact in fp16
+constexpr float AUG_INV = 1.0f / 4096.0f;
+constexpr float PAD_NORM = 30000.0f;          // aug entry of padding columns: acc ~ 1.2e8, never selected
+constexpr float ROW_LIMIT = 1024.0f;          // |S*x| above this -> exact fallback for the row
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major operand descriptors (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 <<46 | layout <<61
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {  // rows of 128 B, 8-row swizzle atoms 1024 B apart
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t addr) {  // 8x16B core matrices: K-adjacent 128 B apart, row groups 256 B
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+// kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, N at [17,23) >> 3, M at [24,29) >> 4
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// value split into three fp16 pieces (p1 + p2 + p3 ~ v to ~33 bits)
+__device__ __forceinline__ void split3(float v, __half &p1, __half &p2, __half &p3) {
+    p1 = __float2half_rn(v);
+    float r = v - __half2float(p1);
+    p2 = __float2half_rn(r);
+    r -= __half2float(p2);
+    p3 = __float2half_rn(r);
+}
+
+// byte offset of 16-byte chunk `chunk` (0..7) of row r in a SWIZZLE_128B K-major tile
+__device__ __host__ __forceinline__ uint32_t sw128_off(int r, int chunk) { return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4); }
+// byte offset of 16-byte K-chunk kc (0..1) of row r in the no-swizzle aug tile
+__device__ __host__ __forceinline__ uint32_t aug_off(int r, int kc) { return (uint32_t)(r >> 3) * 256u + (uint32_t)kc * 128u + (uint32_t)(r & 7) * 16u; }
+
+// ------------------------------------------------------------------------------------------ operand prep
+__global__ void k_tc_scale(const float *__restrict__ c, int n, float *__restrict__ scale) {
+    __shared__ float red[32];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(c[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, red[w]);
+        int e = 0;
+        if (m > 0.f && isfinite(m)) {
+            int ex;
+            frexpf(m, &ex);  // m < 2^ex
+            e = 7 - ex;      // m * 2^e in [64, 128)
+        }
+        float S = ldexpf(1.0f, e);
+        scale[0] = S;
+        scale[1] = S * S * AUG_INV;
+    }
+}
+
+// one thread per (padded centroid, 16-byte chunk): chunks 0..7 main columns, chunk 8 = aug
+__global__ void k_tc_prep(const float *__restrict__ c, const float *__restrict__ cn, int k, int ktiles,
+                          const float *__restrict__ scale, unsigned char *__restrict__ op) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = idx / 9, chunk = idx % 9;
+    if (j >= ktiles * TN) return;
+    const float S = scale[0], S2A = scale[1];
+    unsigned char *tile = op + (size_t)(j / TN) * B_TILE_BYTES;
+    const int r = j % TN;
+    if (chunk < 8) {
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            float v = j < k ? -2.0f * S * c[(size_t)j * 64 + chunk * 8 + e] : 0.f;
+            hi[e] = __float2half_rn(v);
+            lo[e] = __float2half_rn(v - __half2float(hi[e]));
+        }
+        *reinterpret_cast<uint4 *>(tile + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(tile + TN * 128 + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(lo);
+    } else {
+        __align__(16) __half a[8];
+        const __half one = __float2half_rn(AUG_ONE), zero = __float2half_rn(0.f);
+        a[0] = a[1] = a[2] = one;
+        if (j < k) {
+            split3(cn[j] * S2A, a[3], a[4], a[5]);
+        } else {
+            a[3] = __float2half_rn(PAD_NORM), a[4] = zero, a[5] = zero;
+        }
+        a[6] = a[7] = zero;
+        unsigned char *aug = tile + 2 * TN * 128;
+        *reinterpret_cast<uint4 *>(aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
+        *reinterpret_cast<uint4 *>(aug + aug_off(r, 1)) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+// canonical fp32 distance of row x (registers, already normalised) to centroid j
+__device__ __forceinline__ float exact_dist(const float (&xr)[64], float xn, const float *__restrict__ c,
+                                            const float *__restrict__ cn, int j) {
+    const float4 *cj = reinterpret_cast<const float4 *>(c + (size_t)j * 64);
+    float q[16];
+#pragma unroll
+    for (int l = 0; l < 16; l++) {
+        float4 v = __ldg(cj + l);
+        float s = xr[4 * l] * v.x;
+        s = fmaf(xr[4 * l + 1], v.y, s);
+        s = fmaf(xr[4 * l + 2], v.z, s);
+        s = fmaf(xr[4 * l + 3], v.w, s);
+        q[l] = s;
+    }
+    return l2_expanded(xn, __ldg(cn + j), tree16(q));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned char *__restrict__ op, int ktiles,
+            int k, const float *__restrict__ c, const float *__restrict__ cn, const float *__restrict__ scale,
+            int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ uint32_t s_tmem_base;
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char *sm = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t bar0 = base + OFF_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    unsigned char *flags = sm + OFF_FLAGS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (n + TM - 1) / TM;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        mbar_init(BAR(BAR_XF_FULL), 1);
+        mbar_init(BAR(BAR_XF_EMPTY), 4);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(BAR(BAR_A_FULL + i), 4);
+            mbar_init(BAR(BAR_A_EMPTY + i), 1);
+            mbar_init(BAR(BAR_ACC_FULL + i), 1);
+            mbar_init(BAR(BAR_ACC_EMPTY + i), 4);
+        }
+        for (int i = 0; i < B_STAGES; i++) {
+            mbar_init(BAR(BAR_B_FULL + i), 1);
+            mbar_init(BAR(BAR_B_EMPTY + i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+
+    if (warp == 0) {
+        // ================================================================== row-tile producer
+        if (lane == 0) {
+            for (int64_t i = 0; i < my_tiles; i++) {
+                const int64_t tile = blockIdx.x + i * gridDim.x;
+                const int64_t r0 = tile * TM;
+                const uint32_t rows = (uint32_t)min((int64_t)TM, n - r0);
+                mbar_wait(BAR(BAR_XF_EMPTY), (uint32_t)((i & 1) ^ 1));
+                mbar_expect_tx(BAR(BAR_XF_FULL), rows * 256u);
+                bulk_g2s(base + OFF_XF, x + r0 * 64, rows * 256u, BAR(BAR_XF_FULL));
+            }
+        }
+    } else if (warp == 3) {
+        // ================================================================== centroid-tile producer
+        if (lane == 0) {
+            uint32_t s = 0;
+            for (int64_t i = 0; i < my_tiles; i++) {
+                for (int jt = 0; jt < ktiles; jt++, s++) {
+                    const uint32_t st = s % B_STAGES, ph = (s / B_STAGES) & 1;
+                    mbar_wait(BAR(BAR_B_EMPTY + st), ph ^ 1);
+                    mbar_expect_tx(BAR(BAR_B_FULL + st), B_TILE_BYTES);
+                    bulk_g2s(base + OFF_B + st * B_TILE_BYTES, op + (size_t)jt * B_TILE_BYTES, B_TILE_BYTES,
+                             BAR(BAR_B_FULL + st));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            uint32_t s = 0, u = 0;
+            for (int64_t i = 0; i < my_tiles; i++) {
+                const uint32_t ab = (uint32_t)(i & 1);
+                mbar_wait(BAR(BAR_A_FULL + ab), (uint32_t)((i >> 1) & 1));
+                const uint32_t a_hi = base + OFF_A + ab * A_BUF_BYTES, a_lo = a_hi + A_MAIN_BYTES, a_aug = a_lo + A_MAIN_BYTES;
+                for (int jt = 0; jt < ktiles; jt++, s++, u++) {
+                    const uint32_t st = s % B_STAGES, bph = (s / B_STAGES) & 1;
+                    const uint32_t buf = u & 1, aph = (u >> 1) & 1;
+                    mbar_wait(BAR(BAR_B_FULL + st), bph);
+                    mbar_wait(BAR(BAR_ACC_EMPTY + buf), aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = base + OFF_B + st * B_TILE_BYTES, b_lo = b_hi + TN * 128, b_aug = b_lo + TN * 128;
+                    const uint32_t d = tmem + buf * TN;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) umma_f16(d, desc_sw128(a_hi + kk * 32), desc_sw128(b_hi + kk * 32), IDESC, kk > 0);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) umma_f16(d, desc_sw128(a_hi + kk * 32), desc_sw128(b_lo + kk * 32), IDESC, 1);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) umma_f16(d, desc_sw128(a_lo + kk * 32), desc_sw128(b_hi + kk * 32), IDESC, 1);
+                    umma_f16(d, desc_nosw(a_aug), desc_nosw(b_aug), IDESC, 1);
+                    umma_commit(BAR(BAR_B_EMPTY + st));
+                    umma_commit(BAR(BAR_ACC_FULL + buf));
+                }
+                umma_commit(BAR(BAR_A_EMPTY + ab));
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================================================== converters
+        const int cw = warp - 4;
+        const int half = lane >> 4, g = lane & 15;
+        const float S = scale[0], S2A = scale[1];
+        for (int64_t i = 0; i < my_tiles; i++) {
+            const int64_t tile = blockIdx.x + i * gridDim.x;
+            const int rows = (int)min((int64_t)TM, n - tile * TM);
+            const uint32_t ab = (uint32_t)(i & 1);
+            mbar_wait(BAR(BAR_XF_FULL), (uint32_t)(i & 1));
+            mbar_wait(BAR(BAR_A_EMPTY + ab), (uint32_t)(((i >> 1) & 1) ^ 1));
+            unsigned char *a_hi = sm + OFF_A + ab * A_BUF_BYTES, *a_lo = a_hi + A_MAIN_BYTES, *a_aug = a_lo + A_MAIN_BYTES;
+            const float4 *xf = reinterpret_cast<const float4 *>(sm + OFF_XF);
+#pragma unroll 4
+            for (int it = 0; it < 16; it++) {
+                const int r = cw * 32 + it * 2 + half;
+                float4 v = r < rows ? xf[r * 16 + g] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (l2norm) {
+                    float q = v.x * v.x;
+                    q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
+                    const float den = l2_denominator(half16_sum(q));
+                    v.x = __fdiv_rn(v.x, den), v.y = __fdiv_rn(v.y, den), v.z = __fdiv_rn(v.z, den), v.w = __fdiv_rn(v.w, den);
+                }
+                float q = v.x * v.x;
+                q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
+                const float xn = half16_sum(q);
+                float sx = S * v.x, sy = S * v.y, sz = S * v.z, sw = S * v.w;
+                float amax = fmaxf(fmaxf(fabsf(sx), fabsf(sy)), fmaxf(fabsf(sz), fabsf(sw)));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+                const bool fallback = !(amax <= ROW_LIMIT);  // also catches NaN
+                if (fallback) sx = sy = sz = sw = 0.f;
+                __half2 h01 = __floats2half2_rn(sx, sy), h23 = __floats2half2_rn(sz, sw);
+                float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                __half2 l01 = __floats2half2_rn(sx - f01.x, sy - f01.y), l23 = __floats2half2_rn(sz - f23.x, sw - f23.y);
+                const uint32_t off = sw128_off(r, g >> 1) + (uint32_t)(g & 1) * 8u;
+                *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(*reinterpret_cast<uint32_t *>(&h01), *reinterpret_cast<uint32_t *>(&h23));
+                *reinterpret_cast<uint2 *>(a_lo + off) = make_uint2(*reinterpret_cast<uint32_t *>(&l01), *reinterpret_cast<uint32_t *>(&l23));
+                if (g == 0) {
+                    __align__(16) __half a[8];
+                    const __half one = __float2half_rn(AUG_ONE), zero = __float2half_rn(0.f);
+                    split3(fallback ? 0.f : xn * S2A, a[0], a[1], a[2]);
+                    a[3] = a[4] = a[5] = one;
+                    a[6] = a[7] = zero;
+                    *reinterpret_cast<uint4 *>(a_aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
+                    *reinterpret_cast<uint4 *>(a_aug + aug_off(r, 1)) = make_uint4(0, 0, 0, 0);
+                    flags[ab * 128 + r] = fallback ? 1 : 0;
+                }
+            }
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(BAR(BAR_XF_EMPTY));
+                mbar_arrive(BAR(BAR_A_FULL + ab));
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================================================== epilogue
+        const int ew = warp - 8;  // == warp % 4: the TMEM lane quadrant this warp may read
+        const int row_in_tile = ew * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        constexpr float BIG = 3.0e38f;
+        uint32_t u = 0;
+        for (int64_t i = 0; i < my_tiles; i++) {
+            const int64_t tile = blockIdx.x + i * gridDim.x;
+            const int64_t row = tile * TM + row_in_tile;
+            float g1 = BIG, g2 = BIG;
+            int j1 = 0, j2 = 0;
+            int fallback = 0;
+            for (int jt = 0; jt < ktiles; jt++, u++) {
+                const uint32_t buf = u & 1, ph = (u >> 1) & 1;
+                mbar_wait(BAR(BAR_ACC_FULL + buf), ph);
+                tc_fence_after();
+                if (jt == 0) fallback = flags[(i & 1) * 128 + row_in_tile];
+                float t1 = BIG, t2 = BIG;
+#pragma unroll
+                for (int cb = 0; cb < TN; cb += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem + lane_addr + buf * TN + cb, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const float ka = __uint_as_float((r[e] & 0xFFFFFF80u) | (uint32_t)(cb + e));
+                        const float kb = __uint_as_float((r[e + 1] & 0xFFFFFF80u) | (uint32_t)(cb + e + 1));
+                        const float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
+                        t2 = fmin3(t2, hi, fmaxf(t1, lo));
+                        t1 = fminf(t1, lo);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + buf));
+                if (t1 < g1) {
+                    if (t2 < g1) g2 = t2, j2 = jt; else g2 = g1, j2 = j1;
+                    g1 = t1, j1 = jt;
+                } else if (t1 < g2) {
+                    g2 = t1, j2 = jt;
+                }
+            }
+            if (row < n) {
+                // fp32 re-check of the two candidates with the canonical formula
+                float xr[64];
+                const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
+#pragma unroll
+                for (int l = 0; l < 16; l++) {
+                    float4 v = __ldg(xp + l);
+                    xr[4 * l] = v.x, xr[4 * l + 1] = v.y, xr[4 * l + 2] = v.z, xr[4 * l + 3] = v.w;
+                }
+                float q[16];
+                if (l2norm) {
+#pragma unroll
+                    for (int l = 0; l < 16; l++) {
+                        float s = xr[4 * l] * xr[4 * l];
+                        s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
+                        q[l] = s;
+                    }
+                    const float den = l2_denominator(tree16(q));
+#pragma unroll
+                    for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
+                }
+#pragma unroll
+                for (int l = 0; l < 16; l++) {
+                    float s = xr[4 * l] * xr[4 * l];
+                    s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
+                    q[l] = s;
+                }
+                const float xn = tree16(q);
+                int best;
+                float bd;
+                if (!fallback) {
+                    int ca = j1 * TN + (int)(__float_as_uint(g1) & 127u);
+                    int cbb = j2 * TN + (int)(__float_as_uint(g2) & 127u);
+                    if (ca >= k) ca = 0;      // cannot happen for finite data; keeps the loads in bounds
+                    if (cbb >= k) cbb = ca;
+                    const float da = exact_dist(xr, xn, c, cn, ca);
+                    const float db = exact_dist(xr, xn, c, cn, cbb);
+                    const bool take_b = db < da || (db == da && cbb < ca);
+                    best = take_b ? cbb : ca;
+                    bd = take_b ? db : da;
+                } else {  // out-of-range row: exact scan (rare)
+                    best = 0, bd = INFINITY;
+                    for (int j = 0; j < k; j++) {
+                        const float dj = exact_dist(xr, xn, c, cn, j);
+                        if (dj < bd) bd = dj, best = j;
+                    }
+                }
+                if (labels32) labels32[row] = best;
+                if (labels64) labels64[row] = best;
+                if (dist) dist[row] = bd;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16 && ix->op != nullptr; }
+
+int assign_tc_prepare(at_index *ix, cudaStream_t st) {
+    if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, 2 * sizeof(float)));
+    k_tc_scale<<<1, 1024, 0, st>>>(ix->c, ix->k * 64, ix->tc_scale);
+    AT_LAUNCH_OK();
+    const int total = ix->ktiles * TN * 9;
+    k_tc_prep<<<(total + 255) / 256, 256, 0, st>>>(ix->c, ix->cn, ix->k, ix->ktiles, ix->tc_scale,
+                                                  reinterpret_cast<unsigned char *>(ix->op));
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32, int64_t *labels64,
+                     float *dist, cudaStream_t st) {
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) {
+        set_error("search: tensor path needs 16-byte aligned rows");
+        return AT_ERR_UNSUPPORTED;
+    }
+    static bool configured = false;
+    if (!configured) {
+        AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        configured = true;
+    }
+    const int64_t ntiles = (n + TM - 1) / TM;
+    int grid = sm_count();
+    if (grid > ntiles) grid = (int)ntiles;
+    if (grid < 1) grid = 1;
+    k_assign_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(x, n, l2norm_rows, reinterpret_cast<const unsigned char *>(ix->op),
+                                                  ix->ktiles, ix->k, ix->c, ix->cn, ix->tc_scale, labels32, labels64, dist);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
 }  // namespace at

@@ -10,10 +10,10 @@ struct at_index {
     int kcap = 0;   // allocation, in centroids
     float *c = nullptr;    // (kcap, d) fp32 centroids
     float *cn = nullptr;   // (kcap) canonical |c|^2
-    // tcgen05 operands (d == 64 only): per 128-centroid tile, two 128x64 fp16 K-major SWIZZLE_128B images
-    // (hi and lo halves of -2*16*c), see at_assign_tc.cu
-    __half *op = nullptr;  // (ktiles * 2 * 128 * 64) halves
-    float *cn_pad = nullptr;  // (ktiles*128) |c|^2, +inf for padding columns
+    // tcgen05 operands (d == 64 only): per 128-centroid tile one 36,864-byte image = hi | lo fp16 halves of
+    // -2*S*c as 128x64 K-major SWIZZLE_128B tiles + a 128x16 no-swizzle tile carrying |c|^2 (at_assign_tc.cu)
+    __half *op = nullptr;
+    float *tc_scale = nullptr;  // device: {S, S^2 / 4096}
     int ktiles = 0;
 };
 

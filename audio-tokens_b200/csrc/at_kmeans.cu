@@ -468,7 +468,7 @@ int at_index_destroy(at_index *ix) {
     cudaFree(ix->c);
     cudaFree(ix->cn);
     cudaFree(ix->op);
-    cudaFree(ix->cn_pad);
+    cudaFree(ix->tc_scale);
     delete ix;
     return AT_OK;
 }
@@ -478,16 +478,15 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
     cudaStream_t st = (cudaStream_t)stream;
     if (k > ix->kcap) {
         AT_CUDA_OK(cudaStreamSynchronize(st));
-        cudaFree(ix->c), cudaFree(ix->cn), cudaFree(ix->op), cudaFree(ix->cn_pad);
-        ix->c = ix->cn = ix->cn_pad = nullptr;
+        cudaFree(ix->c), cudaFree(ix->cn), cudaFree(ix->op);
+        ix->c = ix->cn = nullptr;
         ix->op = nullptr;
         ix->kcap = 0;
         int ktiles = (k + 127) / 128;
         AT_CUDA_OK(cudaMalloc(&ix->c, sizeof(float) * (size_t)k * ix->d));
         AT_CUDA_OK(cudaMalloc(&ix->cn, sizeof(float) * (size_t)k));
         if (ix->d == 64) {
-            AT_CUDA_OK(cudaMalloc(&ix->op, sizeof(__half) * (size_t)ktiles * 2 * 128 * 64));
-            AT_CUDA_OK(cudaMalloc(&ix->cn_pad, sizeof(float) * (size_t)ktiles * 128));
+            AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 36864));
         }
         ix->kcap = k;
     }

@@ -224,3 +224,72 @@ def test_bincount():
     counts = torch.empty(300, dtype=torch.int64, device="cuda")
     _lib.check(_lib.load().at_bincount(_lib.ptr(lab), lab.numel(), 300, _lib.ptr(counts), _lib.stream_ptr()))
     assert torch.equal(counts, torch.bincount(lab.long(), minlength=300))
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 path
+@pytest.mark.parametrize("k,n", [(256, 20000), (1024, 30011), (500, 4097), (16, 300), (2000, 12800)])
+def test_search_tensor_matches_exact_simt(k, n):
+    """The tcgen05 kernel re-checks its top-2 with the canonical fp32 formula, so labels AND distances must
+    equal the exact SIMT kernel's bit for bit (a 3-way tie within ~1e-7 is the only documented exception)."""
+    import torch
+    from at_b200 import FlatL2, _lib
+
+    spec, l2 = _frames(80)
+    assert l2.shape[0] >= n
+    x = l2[:n].contiguous()
+    g = torch.Generator().manual_seed(k)
+    c = l2[torch.randperm(l2.shape[0], generator=g)[:k].cuda()].contiguous()
+    ix = FlatL2(64)
+    ix.set_centroids(c)
+    ls, ds = ix.search(x, algo=_lib.ALGO_SIMT)
+    lt, dt = ix.search(x, algo=_lib.ALGO_TENSOR)
+    mism = (ls != lt)
+    print(f"tensor vs simt k={k} n={n}: label mismatches {int(mism.sum())}")
+    assert int(mism.sum()) <= max(1, n // 100000)
+    assert torch.equal(ds[~mism], dt[~mism])
+    # fused row normalisation
+    lt2, dt2 = ix.search(spec[:n].contiguous(), l2norm_rows=True, algo=_lib.ALGO_TENSOR)
+    ls2, ds2 = ix.search(spec[:n].contiguous(), l2norm_rows=True, algo=_lib.ALGO_SIMT)
+    assert int((lt2 != ls2).sum()) <= max(1, n // 100000)
+    assert torch.equal(ls2, ls)
+    # oracle parity gate
+    _check_labels(lt.cpu().numpy(), x.cpu().numpy(), c.cpu().numpy(), f"tensor k={k}")
+
+
+def test_search_tensor_random_and_out_of_range_rows():
+    import torch
+    from at_b200 import FlatL2, _lib
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(5000, 64, device="cuda", generator=g)
+    c = torch.randn(300, 64, device="cuda", generator=g)
+    x[17] *= 1e4    # beyond the fp16 operand range -> exact fallback inside the kernel
+    x[4000] *= 1e-6
+    x[123] = 0
+    ix = FlatL2(64)
+    ix.set_centroids(c)
+    ls, ds = ix.search(x, algo=_lib.ALGO_SIMT)
+    lt, dt = ix.search(x, algo=_lib.ALGO_TENSOR)
+    assert torch.equal(ls, lt) and torch.equal(ds, dt)
+    _check_labels(lt.cpu().numpy(), x.cpu().numpy(), c.cpu().numpy(), "tensor randn")
+
+
+def test_lloyd_tensor_vs_simt_bit_identical_centroids():
+    """Same labels + exact integer sums => the two search paths give bit-identical k-means trajectories."""
+    import torch
+    from at_b200 import LloydTrainer, _lib
+
+    _, l2 = _frames(60)
+    k = 128
+    init = l2[:: l2.shape[0] // k][:k].contiguous()
+    outs = []
+    for algo in (_lib.ALGO_SIMT, _lib.ALGO_TENSOR):
+        tr = LloydTrainer(64, k, algo=algo)
+        tr.begin(l2)
+        tr.set_centroids(init)
+        st = torch.zeros(5, 4, device="cuda")
+        for it in range(5):
+            tr.step(l2, st[it])
+        outs.append((tr.get_centroids(), st.clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
