@@ -21,6 +21,9 @@ PROTOTYPES = {
     "at_version": (c_int, []),
     "at_last_error": (ctypes.c_char_p, []),
     "at_device_info": (c_int, [c_ptr, c_ptr, c_ptr]),
+    "at_kernel_launches": (c_i64, []),
+    "at_profile_enable": (c_int, [c_int]),
+    "at_profile_summary": (c_int, [c_int, c_ptr, c_ptr]),
     "at_mel_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_ptr]),
     "at_mel_plan_set_constants_host": (c_int, [c_ptr, c_ptr, c_ptr]),
     "at_mel_plan_destroy": (c_int, [c_ptr]),

@@ -1,0 +1,141 @@
+"""The whole hot path on device-resident or host-resident waveforms:
+
+    waveforms -> MelPlan (mel dB + min-max + row-L2 copy) -> k-means (faiss::Clustering semantics, all rows)
+              -> nearest-centroid tokens
+
+This is what SpectrogramGenerator.run -> ClusterCreator.run -> SpecTokenizer.run do through .npy files in the
+reference (run_pipeline.py:11-13); here the intermediate stays in HBM.  Used by bench.py and by the drop-in
+processors when they are chained in one process.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from .index import FlatL2
+from .kmeans import LloydTrainer, rand_perm
+from .mel import MelPlan
+
+
+class HotPath:
+    def __init__(self, sample_rate=22050, n_fft=1024, hop_length=512, n_mels=64, normalize=True, vocab_size=1024,
+                 niter=20, group=False, seed=1234, algo=_lib.ALGO_AUTO):
+        self.plan = MelPlan(sample_rate, n_fft, hop_length, n_mels, normalize)
+        self.k, self.d, self.niter, self.group, self.seed = vocab_size, n_mels, niter, group, seed
+        self.trainer = LloydTrainer(n_mels, vocab_size, group=group, algo=algo)
+        self.index = FlatL2(n_mels)
+        self.algo = algo
+        self._init_rows = {}
+
+    # -- pieces ----------------------------------------------------------------------------------
+    def init_rows(self, n_total: int) -> np.ndarray:
+        """FAISS's random-point initialisation: rows rand_perm(n, seed + 1)[:k] of the training set. Depends only on
+        (n, seed), so it is computed once per size (host std::mt19937 Fisher-Yates) and cached."""
+        if n_total not in self._init_rows:
+            self._init_rows[n_total] = rand_perm(n_total, self.seed + 1)[: self.k].astype(np.int64)
+        return self._init_rows[n_total]
+
+    def mel(self, wave, spec=None, l2=None):
+        return self.plan.forward(wave, out=spec, out_l2=l2, want_l2=True)
+
+    def kmeans(self, l2_rows, row_offset=0, n_total=None, stats=None):
+        """Lloyd iterations over this rank's L2-normalised rows (n_local, d). Returns device centroids (k, d)."""
+        import torch
+        import torch.distributed as dist
+
+        n_local = l2_rows.shape[0]
+        n_total = n_local if n_total is None else n_total
+        rows = self.init_rows(n_total)
+        mine = (rows >= row_offset) & (rows < row_offset + n_local)
+        cent = torch.zeros((self.k, self.d), dtype=torch.float32, device=l2_rows.device)
+        idx = torch.from_numpy(np.nonzero(mine)[0]).to(l2_rows.device)
+        src = torch.from_numpy(rows[mine] - row_offset).to(l2_rows.device)
+        cent.index_copy_(0, idx, l2_rows.index_select(0, src))
+        if self.group is not False and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(cent, group=self.group or None)
+        self.trainer.begin(l2_rows, n_total)
+        self.trainer.set_centroids(cent)
+        for it in range(self.niter):
+            self.trainer.step(l2_rows, None if stats is None else stats[it])
+        return self.trainer.get_centroids()
+
+    def tokenize(self, spec_rows, centroids, tokens=None):
+        import torch
+
+        self.index.set_centroids(centroids)
+        lab, _ = self.index.search(spec_rows, l2norm_rows=True, algo=self.algo, want_dist=False,
+                                   labels_dtype=torch.int64, labels=tokens)
+        return lab
+
+    # -- whole path ------------------------------------------------------------------------------
+    def cluster_and_tokenize(self, spec, l2, row_offset=0, n_total=None, stats=None, tokens=None):
+        """spec / l2: (B, T, d) device tensors from mel().  Returns (tokens int64 (B*T,), unit-norm centroids)."""
+        from . import row_l2norm
+
+        cents = self.kmeans(l2.reshape(-1, self.d), row_offset, n_total, stats)
+        cents = row_l2norm(cents)  # ClusterCreator saves normalize_vectors(kmeans.centroids) (cluster_creator.py:58-61)
+        tok = self.tokenize(spec.reshape(-1, self.d), cents, tokens)
+        return tok, cents
+
+    def run_device(self, wave, bufs=None, row_offset=0, n_total=None, stats=None):
+        """wave (B, L) fp32 CUDA.  Returns (tokens int64 (B*T,), centroids (k, d), bad (B,))."""
+        bufs = bufs or {}
+        spec, bad, l2 = self.mel(wave, bufs.get("spec"), bufs.get("l2"))
+        tok, cents = self.cluster_and_tokenize(spec, l2, row_offset, n_total, stats, bufs.get("tokens"))
+        return tok, cents, bad
+
+    def run_host(self, wave_host, bufs, chunk_clips=296, row_offset=0, n_total=None):
+        """End to end from HOST memory: wave_host (B, L) pinned fp32 tensor.  Chunks are copied H2D on a copy stream
+        while the mel kernel works on the previous chunk; tokens (int64) and centroids are copied back into the
+        pinned host tensors bufs["tokens_host"], bufs["centroids_host"].  Blocks until they are there."""
+        import torch
+
+        B, L = wave_host.shape
+        T = self.plan.num_frames(L)
+        spec, l2 = bufs["spec"], bufs["l2"]
+        stage = bufs["stage"]  # (2, chunk_clips, L) device
+        main = torch.cuda.current_stream()
+        copy = bufs["copy_stream"]
+        bad = torch.zeros(B, dtype=torch.int32, device="cuda")
+        copy.wait_stream(main)
+        ev_free = [None, None]
+        for ci, b0 in enumerate(range(0, B, chunk_clips)):
+            nb = min(chunk_clips, B - b0)
+            sb = ci & 1
+            with torch.cuda.stream(copy):
+                if ev_free[sb] is not None:
+                    copy.wait_event(ev_free[sb])
+                stage[sb, :nb].copy_(wave_host[b0:b0 + nb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            main.wait_event(ev)
+            _lib.check(self.plan.lib.at_mel_forward(self.plan.h, _lib.ptr(stage[sb]), None, None, L, nb,
+                                                    _lib.ptr(spec[b0:]), _lib.ptr(l2[b0:]), _lib.ptr(bad[b0:]),
+                                                    _lib.stream_ptr()))
+            ev_free[sb] = torch.cuda.Event()
+            ev_free[sb].record(main)
+        tok, cents = self.cluster_and_tokenize(spec, l2, row_offset, n_total, None, bufs.get("tokens"))
+        bufs["tokens_host"].copy_(tok, non_blocking=True)
+        bufs["centroids_host"].copy_(cents, non_blocking=True)
+        bufs["bad_host"].copy_(bad, non_blocking=True)
+        main.synchronize()
+        return bufs["tokens_host"], bufs["centroids_host"], bufs["bad_host"]
+
+    def alloc_bufs(self, B, L, host=False, chunk_clips=296):
+        import torch
+
+        T = self.plan.num_frames(L)
+        bufs = dict(
+            spec=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
+            l2=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
+            tokens=torch.empty(B * T, dtype=torch.int64, device="cuda"),
+        )
+        if host:
+            bufs.update(
+                stage=torch.empty((2, chunk_clips, L), dtype=torch.float32, device="cuda"),
+                copy_stream=torch.cuda.Stream(),
+                tokens_host=torch.empty(B * T, dtype=torch.int64, pin_memory=True),
+                centroids_host=torch.empty((self.k, self.d), dtype=torch.float32, pin_memory=True),
+                bad_host=torch.empty(B, dtype=torch.int32, pin_memory=True),
+            )
+        return bufs

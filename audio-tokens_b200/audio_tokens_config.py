@@ -1,0 +1,58 @@
+"""Configuration object of the hot-path stages.
+
+The drop-in processors read a config by attribute name, so the reference's own ``AudioTokensConfig``
+(audio_tokens_config.py:14-81 of danavery/audio-tokens) can be passed unchanged.  This class carries the same
+field names and defaults for the three preprocessing stages, so tests and benchmarks run without the reference
+checkout, plus the knobs that only exist here (all defaulting to the reference's behaviour and always read with
+``getattr(config, name, default)``).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import List, Optional
+
+_BASE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _here(*parts) -> str:
+    return os.path.join(_BASE, *parts)
+
+
+@dataclass
+class AudioTokensConfig:
+    # shared
+    random_seed: int = 4242
+
+    # stage 1: SpectrogramGenerator
+    split_file: str = _here("output", "bal_train_data_split.json")
+    audio_source_path: str = "/media/davery/audioset"
+    audio_source_sets: List[str] = field(default_factory=lambda: ["bal_train"])
+    dest_spec_path: Path = Path(_here("spectrograms"))
+    common_sr: int = 22050
+    normalize: bool = False
+    n_mels: int = 64
+    n_fft: int = 512
+    hop_length: int = 128
+    spectrogram_batch_size: int = 5000
+
+    # stage 2: ClusterCreator
+    vocab_size: int = 500
+    niter: int = 20
+    use_convolution: bool = False
+    num_kernels: int = 10
+    kernel_size: int = 3
+    clustering_batch_size: int = 10000
+    centroids_path: Path = Path(_here("output", "centroids.npy"))
+    source_spec_path: Path = Path(_here("spectrograms"))
+
+    # stage 3: SpecTokenizer
+    dest_tokenized_path: str = _here("tokenized_audio")
+    tokenizer_batch_size: int = 10000
+
+    # ---- knobs that exist only in the B200 implementation (reference behaviour by default) ----
+    # faiss.ClusteringParameters.max_points_per_centroid; None keeps FAISS's 256 (subsample to 256*K rows)
+    max_points_per_centroid: Optional[int] = None
+    # sort the globbed .npy lists (the reference does not: its result depends on directory order)
+    sort_files: bool = False

@@ -31,6 +31,7 @@ void set_error(const char *fmt, ...);
 
 #define AT_LAUNCH_OK()                                                                         \
     do {                                                                                       \
+        at::g_launches++;                                                                      \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess) {                                                               \
             at::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),          \
@@ -40,6 +41,19 @@ void set_error(const char *fmt, ...);
     } while (0)
 
 int sm_count();  // cached; 0 when no device
+extern int64_t g_launches;
+
+// Event-pair profiling (at_profile_*): ProfScope brackets the launches issued while it is alive.
+enum { PROF_SEARCH = 0, PROF_MEL = 1, PROF_UPDATE = 2, PROF_FINALIZE = 3, PROF_TAGS = 4 };
+extern bool g_prof_on;
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
+struct ProfScope {
+    int tag;
+    cudaStream_t st;
+    ProfScope(int t, cudaStream_t s) : tag(t), st(s) { if (g_prof_on) prof_begin(tag, st); }
+    ~ProfScope() { if (g_prof_on) prof_end(tag, st); }
+};
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

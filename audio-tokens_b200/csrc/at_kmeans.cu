@@ -432,6 +432,7 @@ static int index_search(at_index *ix, const float *x, int64_t n, int l2norm, int
     } else if (algo == AT_ALGO_AUTO) {
         tc = assign_tc_supported(ix) && ix->k >= 64;
     }
+    ProfScope prof(PROF_SEARCH, st);
     if (tc) return assign_tc_search(ix, x, n, l2norm, l32, l64, dist, st);
     return launch_simt(ix, x, n, l2norm, l32, l64, dist, st);
 }
@@ -611,6 +612,7 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     rc = index_search(km->index, x, n_local, 0, algo, labels, nullptr, km->dist, st);
     if (rc != AT_OK) return rc;
     unsigned long long *acc = (unsigned long long *)accum;
+    ProfScope prof(PROF_UPDATE, st);
     int blocks = sm_count() * 8;
     k_counts<<<blocks, 256, 0, st>>>(labels, n_local, acc + kd);
     AT_LAUNCH_OK();
@@ -637,6 +639,7 @@ int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, flo
     AT_REQUIRE(km && accum && n_total > 0, "at_kmeans_finalize: bad arguments");
     AT_REQUIRE(km->begun, "at_kmeans_finalize: call at_kmeans_begin first");
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_FINALIZE, st);
     k_finalize<<<1, 1024, 0, st>>>((const long long *)accum, km->k, km->d, n_total, ldexp(1.0, -km->e_sum),
                                    ldexp(1.0, -km->e_obj), km->newc, km->hassign, stats);
     AT_LAUNCH_OK();

@@ -427,6 +427,7 @@ static int launch_mel(at_mel_plan *p, const float *wave, const int64_t *so, cons
     int grid = sm_count();
     if (grid > B) grid = B;
     if (grid < 1) grid = 1;
+    ProfScope prof(PROF_MEL, st);
     k_mel<LOG2NF><<<grid, MEL_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->win,
                                                      p->tw, p->fstart, p->fcnt, p->woff, p->wt, out, out_l2, bad);
     AT_LAUNCH_OK();

@@ -3,10 +3,29 @@
 
 #include <string.h>
 #include <random>
+#include <vector>
 
 namespace at {
 
 static thread_local char g_err[512] = "";
+int64_t g_launches = 0;
+bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof[PROF_TAGS];
+static cudaEvent_t g_prof_open[PROF_TAGS];
+
+void prof_begin(int tag, cudaStream_t st) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof_open[tag] = e;
+}
+void prof_end(int tag, cudaStream_t st) {
+    cudaEvent_t e;
+    if (!g_prof_open[tag] || cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof[tag].push_back({g_prof_open[tag], e});
+    g_prof_open[tag] = nullptr;
+}
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -125,6 +144,29 @@ extern "C" {
 int at_version(void) { return AT_B200_VERSION; }
 
 const char *at_last_error(void) { return g_err; }
+
+int64_t at_kernel_launches(void) { return g_launches; }
+
+int at_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return AT_OK;
+}
+
+int at_profile_summary(int tag, int64_t *launches, double *total_ms) {
+    AT_REQUIRE(tag >= 0 && tag < PROF_TAGS && launches && total_ms, "at_profile_summary: bad arguments");
+    double tot = 0;
+    for (auto &p : g_prof[tag]) {
+        AT_CUDA_OK(cudaEventSynchronize(p.second));
+        float ms = 0;
+        AT_CUDA_OK(cudaEventElapsedTime(&ms, p.first, p.second));
+        tot += ms;
+        cudaEventDestroy(p.first), cudaEventDestroy(p.second);
+    }
+    *launches = (int64_t)g_prof[tag].size();
+    *total_ms = tot;
+    g_prof[tag].clear();
+    return AT_OK;
+}
 
 int at_device_info(int *sm, int *major, int *minor) {
     int dev = 0;

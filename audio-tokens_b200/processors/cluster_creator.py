@@ -1,0 +1,92 @@
+"""Stage 2 drop-in: same class and outputs as the reference's processors/cluster_creator.py; faiss.Kmeans is
+replaced by at_b200.Kmeans (faiss::Clustering semantics on sm_100a kernels)."""
+import logging
+from pathlib import Path
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+import at_b200
+import at_b200.faiss_compat as faiss
+
+
+def _set_seed(seed=42):
+    """utils/set_seed.py of the reference (FAISS itself ignores it: its seeds stay 1234 / 1235)."""
+    import random
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+
+class ClusterCreator:
+    def __init__(self, config):
+        self.logger = logging.getLogger(__name__)
+        self.config = config
+        _set_seed(self.config.random_seed)
+        self.gpu = faiss.get_num_gpus() > 0
+        if not self.gpu:
+            raise RuntimeError("ClusterCreator (B200 build) needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device("cuda")
+        if self.config.use_convolution:
+            raise NotImplementedError("use_convolution is outside the accelerated hot path (SURVEY.md section 8f)")
+
+    def run(self):
+        n_freq_bins = self.config.n_mels
+        self.logger.info("starting clustering")
+        extra = {}
+        mppc = getattr(self.config, "max_points_per_centroid", None)
+        if mppc is not None:
+            extra["max_points_per_centroid"] = int(mppc)
+        kmeans = faiss.Kmeans(n_freq_bins, self.config.vocab_size, niter=self.config.niter, verbose=True,
+                              gpu=self.gpu, **extra)
+        for i, batch in enumerate(self._batch_generator(self.config.clustering_batch_size)):
+            batch = at_b200.row_l2norm(torch.from_numpy(batch).to(self.device))  # normalize_vectors on the device
+            if i == 0:
+                kmeans.train(batch)
+            else:
+                kmeans.train(batch, init_centroids=kmeans.centroids)
+        centroids = self.normalize_vectors(kmeans.centroids)
+        self.logger.info(f"Centroids shape: {centroids.shape}")
+        np.save(self.config.centroids_path, centroids)
+        self.visualize_centroids(centroids)
+
+    def normalize_vectors(self, vectors):
+        """v / (||v|| + 1e-10) per row (reference :64-66), computed by at_row_l2norm."""
+        v = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(self.device)
+        return at_b200.row_l2norm(v).cpu().numpy()
+
+    def _files(self):
+        spec_dir = Path(self.config.source_spec_path) / "train"
+        files = list(spec_dir.glob("*.npy"))
+        return sorted(files) if getattr(self.config, "sort_files", False) else files
+
+    def _batch_generator(self, batch_size):
+        files = self._files()
+        for i in tqdm(range(0, len(files), batch_size)):
+            batch_data = [np.load(f).T for f in files[i:i + batch_size]]
+            yield np.concatenate(batch_data, axis=0).astype(np.float32)
+
+    def visualize_centroids(self, centroids):
+        """PCA scatter plot (cosmetic): produced only when matplotlib and scikit-learn are importable."""
+        try:
+            import matplotlib.pyplot as plt
+            from sklearn.decomposition import PCA
+        except ImportError:
+            self.logger.info("Centroids visualization skipped (matplotlib / scikit-learn not installed)")
+            return
+        centroids_2d = PCA(n_components=2).fit_transform(centroids)
+        plt.figure(figsize=(10, 8))
+        plt.scatter(centroids_2d[:, 0], centroids_2d[:, 1])
+        plt.title("2D PCA of Centroids")
+        plt.savefig("output/centroids_visualization.png")
+        plt.close()
+        self.logger.info("Centroids visualization saved")
+
+
+if __name__ == "__main__":
+    from audio_tokens_config import AudioTokensConfig
+
+    ClusterCreator(AudioTokensConfig()).run()

@@ -49,6 +49,16 @@ const char *at_last_error(void);
 /* sm_count / compute capability of the current device; AT_ERR_CUDA when there is none. */
 int at_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Number of kernels this library has launched so far in this process (monotonic). */
+int64_t at_kernel_launches(void);
+/* Optional kernel timing with CUDA events on the launching stream (bench.py's roofline figures).
+ * at_profile_enable(1) starts recording an event pair around every launch of the kernels tagged below;
+ * at_profile_summary synchronises the recorded events and returns the launch count and summed device
+ * milliseconds of one tag, then forgets them. Tags: 0 search (distance-argmin), 1 mel, 2 k-means update
+ * (counts, objective, scan, place, gather-sum), 3 k-means finalize. */
+int at_profile_enable(int on);
+int at_profile_summary(int tag, int64_t *launches, double *total_ms);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1: waveform -> mel dB spectrogram (+ optional per-clip min-max, + optional row L2 norm)
  * ---------------------------------------------------------------------------------------------- */
