@@ -308,33 +308,38 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
         if (normalize || out_l2) {
             // half-warp per frame row; chunk class g handles elements 4g..4g+3 (+64, +128, ...)
             const float range = __fsub_rn(mx, mn);
-            const int g = tid & 15;
-            for (int64_t r = tid >> 4; r < T; r += MEL_THREADS / 16) {
-                float *row = dst + r * n_mels;
+            const int g = tid & 15, hw = (tid >> 4) & 1;
+            // warp-uniform trip count (both half-warps iterate together: the shuffles below need all 32 lanes)
+            for (int64_t r0 = (int64_t)(tid >> 5) * 2; r0 < T; r0 += MEL_THREADS / 16) {
+                const int64_t r = r0 + hw;
+                const bool live = r < T;
+                float *row = dst + (live ? r : 0) * n_mels;
                 float q = 0.f;
-                for (int base = 4 * g; base < n_mels; base += 64) {
+                if (live) {
+                    for (int base = 4 * g; base < n_mels; base += 64) {
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        if (base + e < n_mels) {
-                            float v = __ldcg(row + base + e);
-                            if (normalize) {
-                                v = __fdiv_rn(__fsub_rn(v, mn), range);
-                                nonfinite |= !isfinite(v);
-                                row[base + e] = v;
+                        for (int e = 0; e < 4; e++) {
+                            if (base + e < n_mels) {
+                                float v = __ldcg(row + base + e);
+                                if (normalize) {
+                                    v = __fdiv_rn(__fsub_rn(v, mn), range);
+                                    nonfinite |= !isfinite(v);
+                                    row[base + e] = v;
+                                }
+                                q = fmaf(v, v, q);
                             }
-                            q = fmaf(v, v, q);
                         }
                     }
                 }
                 if (out_l2) {
                     const float den = l2_denominator(half16_sum(q));
-                    float *orow = out_l2 + (f0 + r) * n_mels;
-                    for (int base = 4 * g; base < n_mels; base += 64) {
+                    if (live) {
+                        float *orow = out_l2 + (f0 + r) * n_mels;
+                        for (int base = 4 * g; base < n_mels; base += 64) {
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            if (base + e < n_mels) {
+                            for (int e = 0; e < 4; e++) {
                                 // final value of the row (this thread wrote it just above when normalising)
-                                orow[base + e] = __fdiv_rn(__ldcg(row + base + e), den);
+                                if (base + e < n_mels) orow[base + e] = __fdiv_rn(__ldcg(row + base + e), den);
                             }
                         }
                     }
