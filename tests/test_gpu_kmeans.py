@@ -107,7 +107,7 @@ def test_faiss_like_index_api():
     from at_b200 import IndexFlatL2
     from oracle import faiss_ref
 
-    _, l2 = _frames(10)
+    _, l2 = _frames(60)
     x = l2[:5000].cpu().numpy()
     c = x[::50].copy()
     a = IndexFlatL2(64)
@@ -234,7 +234,7 @@ def test_search_tensor_matches_exact_simt(k, n):
     import torch
     from at_b200 import FlatL2, _lib
 
-    spec, l2 = _frames(80)
+    spec, l2 = _frames(80, 220500)
     assert l2.shape[0] >= n
     x = l2[:n].contiguous()
     g = torch.Generator().manual_seed(k)
