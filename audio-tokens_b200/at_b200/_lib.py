@@ -35,6 +35,7 @@ PROTOTYPES = {
     "at_index_destroy": (c_int, [c_ptr]),
     "at_index_set_centroids": (c_int, [c_ptr, c_ptr, c_int, c_ptr]),
     "at_index_ntotal": (c_int, [c_ptr]),
+    "at_index_set_tc_mode": (c_int, [c_ptr, c_int]),
     "at_index_centroids": (c_ptr, [c_ptr]),
     "at_index_search": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "at_kmeans_create": (c_int, [c_int, c_int, c_ptr]),

@@ -29,6 +29,10 @@ class FlatL2:
         except Exception:
             pass
 
+    def set_tc_mode(self, mode: int):
+        """0 auto, 1 stream centroid tiles, 2 resident / K-sliced (at_index_set_tc_mode)."""
+        _lib.check(self.lib.at_index_set_tc_mode(self.h, int(mode)))
+
     def set_centroids(self, c):
         import torch
 

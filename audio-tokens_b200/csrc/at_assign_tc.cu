@@ -8,22 +8,29 @@
 // in ONE chain of 13 tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
 //     x_hi * c_hi  +  x_hi * c_lo  +  x_lo * c_hi          (fp16 hi/lo split of S*x and -2*S*c: ~22 mantissa bits)
 //   + [xn pieces | 2^12 2^12 2^12] * [2^12 2^12 2^12 | cn pieces]   (one extra K=16 step carrying both norms)
-// so the epilogue only has to keep a per-row top-2.  The two candidates are then re-evaluated with the library's
-// canonical fp32 formula (at_index.cuh), the very one the exact SIMT kernel uses, and the smaller wins (lowest
-// index on exact ties).  Token ids therefore agree with the fp32 path except when three or more centroids lie
-// within ~1e-7 (absolute, unit-norm data) of the minimum.
+// so the epilogue only has to find, per row, the two best GROUPS of four adjacent centroids (a group minimum costs
+// half an ALU op per score with FMNMX3; the group id rides in the low 5 mantissa bits).  The two best groups always
+// contain the two best centroids, so their 8 members are re-evaluated with the library's canonical fp32 formula
+// (at_index.cuh) -- the very one the exact SIMT kernel uses -- and the smallest wins (lowest index on exact ties).
+// Token ids therefore agree with the fp32 path except when a third group lies within ~1e-7 (absolute, unit-norm
+// data) of the minimum.
 //
 // Roofline note: 2*N*K*64 algorithmic flops are executed as 3.25x that many fp16 MMA flops.
 //
+// Two modes share one kernel:
+//   RESIDENT  (K <= 512 per CTA): the CTA's centroid operand tiles (36 KB each, pre-swizzled by k_tc_prep) are loaded
+//             into shared memory once and stay there; for K <= 2048 the centroids are cut into S = ceil(tiles/4)
+//             slices, CTA b serves slice b % S, and a small merge kernel takes the minimum over slices.  No operand
+//             re-streaming from L2 (at K = 1024 the streaming mode moved 22 GB per launch through L2).
+//   STREAM    (any K): operand tiles are streamed through a 4-slot ring with cp.async.bulk.
+//
 // Structure: persistent CTAs (one per SM), 12 warps:
-//   warp 0  lane 0   bulk-copies (cp.async.bulk, TMA engine) the fp32 row tile (128 x 64, contiguous 32 KB)
 //   warp 1  lane 0   issues tcgen05.mma, commits to mbarriers
 //   warp 2           TMEM allocation / deallocation
-//   warp 3  lane 0   bulk-copies centroid operand tiles (36 KB each, pre-swizzled in HBM/L2) into a 3-stage ring
-//   warps 4-7        convert the fp32 tile: optional row L2 normalisation, |x|^2, fp16 hi/lo split written
-//                    straight into the SWIZZLE_128B K-major layout the MMA descriptors expect
-//   warps 8-11       epilogue: tcgen05.ld the accumulator, packed (distance | column) top-2 with FMNMX3,
-//                    fp32 re-check, labels / distances out
+//   warp 3  lane 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into shared memory
+//   warps 4-7        read the fp32 row tile (coalesced 128-bit loads), optional row L2 normalisation, |x|^2, fp16 hi/lo
+//                    split written straight into the SWIZZLE_128B K-major layout the MMA descriptors expect
+//   warps 8-11       epilogue: tcgen05.ld the accumulator, group minima + packed top-2, fp32 re-check, outputs
 #include "at_index.cuh"
 
 namespace at {
@@ -31,28 +38,26 @@ namespace at {
 constexpr int TC_THREADS = 384;
 constexpr int TM = 128;          // rows per tile (UMMA M)
 constexpr int TN = 128;          // centroids per tile (UMMA N)
-constexpr int B_STAGES = 3;
+constexpr int B_SLOTS = 4;       // operand tiles resident per CTA / ring depth
 constexpr uint32_t A_MAIN_BYTES = TM * 128;              // 128 rows x 64 fp16
 constexpr uint32_t AUG_BYTES = TM * 32;                  // 128 rows x 16 fp16, no-swizzle core matrices
 constexpr uint32_t A_BUF_BYTES = 2 * A_MAIN_BYTES + AUG_BYTES;   // hi | lo | aug = 36,864
 constexpr uint32_t B_TILE_BYTES = 2 * TN * 128 + TN * 32;        // hi | lo | aug = 36,864
-constexpr uint32_t XF_BYTES = TM * 64 * 4;                       // 32,768
 
 // shared memory map (dynamic, 1024-B aligned base)
-constexpr uint32_t OFF_XF = 0;
-constexpr uint32_t OFF_A = OFF_XF + XF_BYTES;                    // 2 buffers
-constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 3 stages  (OFF_A, OFF_B multiples of 1024)
-constexpr uint32_t OFF_BAR = OFF_B + B_STAGES * B_TILE_BYTES;    // mbarriers
+constexpr uint32_t OFF_A = 0;                                    // 2 buffers
+constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 4 slots
+constexpr uint32_t OFF_BAR = OFF_B + B_SLOTS * B_TILE_BYTES;     // mbarriers
 constexpr uint32_t OFF_FLAGS = OFF_BAR + 256;                    // row fallback flags 2 x 128 bytes
 constexpr uint32_t TC_SMEM = OFF_FLAGS + 256 + 1024;             // + slack for manual 1024-B alignment
 static_assert(OFF_A % 1024 == 0 && OFF_B % 1024 == 0 && A_BUF_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "align");
+static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 enum {
-    BAR_XF_FULL = 0, BAR_XF_EMPTY = 1,
-    BAR_A_FULL = 2,   // +2
-    BAR_A_EMPTY = 4,  // +2
-    BAR_B_FULL = 6,   // +3
-    BAR_B_EMPTY = 9,  // +3
+    BAR_A_FULL = 0,    // +2
+    BAR_A_EMPTY = 2,   // +2
+    BAR_B_FULL = 4,    // +4
+    BAR_B_EMPTY = 8,   // +4
     BAR_ACC_FULL = 12,   // +2
     BAR_ACC_EMPTY = 14,  // +2
     BAR_COUNT = 16
@@ -227,10 +232,30 @@ __device__ __forceinline__ float exact_dist(const float (&xr)[64], float xn, con
     return l2_expanded(xn, __ldg(cn + j), tree16(q));
 }
 
+// group minima of 32 accumulator columns (8 groups of 4) folded into the running packed top-2 (t1 <= t2)
+__device__ __forceinline__ void fold32(const uint32_t (&r)[32], int cb, float &t1, float &t2) {
+#pragma unroll
+    for (int gp = 0; gp < 4; gp++) {
+        const int e = 8 * gp;
+        const float a = fminf(fmin3(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2])),
+                              __uint_as_float(r[e + 3]));
+        const float b = fminf(fmin3(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]), __uint_as_float(r[e + 6])),
+                              __uint_as_float(r[e + 7]));
+        const float ka = __uint_as_float((__float_as_uint(a) & 0xFFFFFFE0u) | (uint32_t)(cb / 4 + 2 * gp));
+        const float kb = __uint_as_float((__float_as_uint(b) & 0xFFFFFFE0u) | (uint32_t)(cb / 4 + 2 * gp + 1));
+        const float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
+        t2 = fmin3(t2, hi, fmaxf(t1, lo));
+        t1 = fminf(t1, lo);
+    }
+}
+
+// RESIDENT: blockIdx.x % nslices selects the centroid slice [tile0, tile0 + ntl), kept in shared memory.
+template <bool RESIDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned char *__restrict__ op, int ktiles,
-            int k, const float *__restrict__ c, const float *__restrict__ cn, const float *__restrict__ scale,
-            int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist) {
+            int nslices, int k, const float *__restrict__ c, const float *__restrict__ cn,
+            const float *__restrict__ scale, int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
+            float *__restrict__ dist, float *__restrict__ part_dist, int32_t *__restrict__ part_lab) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ uint32_t s_tmem_base;
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -240,19 +265,22 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
     unsigned char *flags = sm + OFF_FLAGS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slice = RESIDENT ? (int)(blockIdx.x % nslices) : 0;
+    const int worker = RESIDENT ? (int)(blockIdx.x / nslices) : (int)blockIdx.x;
+    const int workers = RESIDENT ? (int)(gridDim.x / nslices) : (int)gridDim.x;
+    const int tile0 = RESIDENT ? slice * B_SLOTS : 0;                       // first centroid tile of this CTA
+    const int ntl = RESIDENT ? min(B_SLOTS, ktiles - tile0) : ktiles;       // centroid tiles this CTA visits per row tile
     const int64_t ntiles = (n + TM - 1) / TM;
-    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t my_tiles = worker < ntiles ? (ntiles - worker + workers - 1) / workers : 0;
 
     if (tid == 0) {
-        mbar_init(BAR(BAR_XF_FULL), 1);
-        mbar_init(BAR(BAR_XF_EMPTY), 4);
         for (int i = 0; i < 2; i++) {
             mbar_init(BAR(BAR_A_FULL + i), 4);
             mbar_init(BAR(BAR_A_EMPTY + i), 1);
             mbar_init(BAR(BAR_ACC_FULL + i), 1);
             mbar_init(BAR(BAR_ACC_EMPTY + i), 4);
         }
-        for (int i = 0; i < B_STAGES; i++) {
+        for (int i = 0; i < B_SLOTS; i++) {
             mbar_init(BAR(BAR_B_FULL + i), 1);
             mbar_init(BAR(BAR_B_EMPTY + i), 1);
         }
@@ -267,29 +295,25 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
 
-    if (warp == 0) {
-        // ================================================================== row-tile producer
-        if (lane == 0) {
-            for (int64_t i = 0; i < my_tiles; i++) {
-                const int64_t tile = blockIdx.x + i * gridDim.x;
-                const int64_t r0 = tile * TM;
-                const uint32_t rows = (uint32_t)min((int64_t)TM, n - r0);
-                mbar_wait(BAR(BAR_XF_EMPTY), (uint32_t)((i & 1) ^ 1));
-                mbar_expect_tx(BAR(BAR_XF_FULL), rows * 256u);
-                bulk_g2s(base + OFF_XF, x + r0 * 64, rows * 256u, BAR(BAR_XF_FULL));
-            }
-        }
-    } else if (warp == 3) {
+    if (warp == 3) {
         // ================================================================== centroid-tile producer
-        if (lane == 0) {
-            uint32_t s = 0;
-            for (int64_t i = 0; i < my_tiles; i++) {
-                for (int jt = 0; jt < ktiles; jt++, s++) {
-                    const uint32_t st = s % B_STAGES, ph = (s / B_STAGES) & 1;
-                    mbar_wait(BAR(BAR_B_EMPTY + st), ph ^ 1);
-                    mbar_expect_tx(BAR(BAR_B_FULL + st), B_TILE_BYTES);
-                    bulk_g2s(base + OFF_B + st * B_TILE_BYTES, op + (size_t)jt * B_TILE_BYTES, B_TILE_BYTES,
-                             BAR(BAR_B_FULL + st));
+        if (lane == 0 && my_tiles > 0) {
+            if (RESIDENT) {
+                for (int jt = 0; jt < ntl; jt++) {
+                    mbar_expect_tx(BAR(BAR_B_FULL + jt), B_TILE_BYTES);
+                    bulk_g2s(base + OFF_B + jt * B_TILE_BYTES, op + (size_t)(tile0 + jt) * B_TILE_BYTES, B_TILE_BYTES,
+                             BAR(BAR_B_FULL + jt));
+                }
+            } else {
+                uint32_t s = 0;
+                for (int64_t i = 0; i < my_tiles; i++) {
+                    for (int jt = 0; jt < ktiles; jt++, s++) {
+                        const uint32_t st = s % B_SLOTS, ph = (s / B_SLOTS) & 1;
+                        mbar_wait(BAR(BAR_B_EMPTY + st), ph ^ 1);
+                        mbar_expect_tx(BAR(BAR_B_FULL + st), B_TILE_BYTES);
+                        bulk_g2s(base + OFF_B + st * B_TILE_BYTES, op + (size_t)jt * B_TILE_BYTES, B_TILE_BYTES,
+                                 BAR(BAR_B_FULL + st));
+                    }
                 }
             }
         }
@@ -301,10 +325,11 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                 const uint32_t ab = (uint32_t)(i & 1);
                 mbar_wait(BAR(BAR_A_FULL + ab), (uint32_t)((i >> 1) & 1));
                 const uint32_t a_hi = base + OFF_A + ab * A_BUF_BYTES, a_lo = a_hi + A_MAIN_BYTES, a_aug = a_lo + A_MAIN_BYTES;
-                for (int jt = 0; jt < ktiles; jt++, s++, u++) {
-                    const uint32_t st = s % B_STAGES, bph = (s / B_STAGES) & 1;
+                for (int jt = 0; jt < ntl; jt++, s++, u++) {
+                    const uint32_t st = RESIDENT ? (uint32_t)jt : s % B_SLOTS;
+                    const uint32_t bph = RESIDENT ? 0u : (s / B_SLOTS) & 1;
                     const uint32_t buf = u & 1, aph = (u >> 1) & 1;
-                    mbar_wait(BAR(BAR_B_FULL + st), bph);
+                    if (!RESIDENT || i == 0) mbar_wait(BAR(BAR_B_FULL + st), bph);
                     mbar_wait(BAR(BAR_ACC_EMPTY + buf), aph ^ 1);
                     tc_fence_after();
                     const uint32_t b_hi = base + OFF_B + st * B_TILE_BYTES, b_lo = b_hi + TN * 128, b_aug = b_lo + TN * 128;
@@ -316,7 +341,7 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) umma_f16(d, desc_sw128(a_lo + kk * 32), desc_sw128(b_hi + kk * 32), IDESC, 1);
                     umma_f16(d, desc_nosw(a_aug), desc_nosw(b_aug), IDESC, 1);
-                    umma_commit(BAR(BAR_B_EMPTY + st));
+                    if (!RESIDENT) umma_commit(BAR(BAR_B_EMPTY + st));
                     umma_commit(BAR(BAR_ACC_FULL + buf));
                 }
                 umma_commit(BAR(BAR_A_EMPTY + ab));
@@ -328,17 +353,23 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
         const int half = lane >> 4, g = lane & 15;
         const float S = scale[0], S2A = scale[1];
         for (int64_t i = 0; i < my_tiles; i++) {
-            const int64_t tile = blockIdx.x + i * gridDim.x;
+            const int64_t tile = worker + i * workers;
             const int rows = (int)min((int64_t)TM, n - tile * TM);
             const uint32_t ab = (uint32_t)(i & 1);
-            mbar_wait(BAR(BAR_XF_FULL), (uint32_t)(i & 1));
-            mbar_wait(BAR(BAR_A_EMPTY + ab), (uint32_t)(((i >> 1) & 1) ^ 1));
-            unsigned char *a_hi = sm + OFF_A + ab * A_BUF_BYTES, *a_lo = a_hi + A_MAIN_BYTES, *a_aug = a_lo + A_MAIN_BYTES;
-            const float4 *xf = reinterpret_cast<const float4 *>(sm + OFF_XF);
-#pragma unroll 4
+            const float4 *xg = reinterpret_cast<const float4 *>(x + tile * TM * 64);
+            // issue the global loads before waiting for the buffer: they do not depend on it
+            float4 vv[16];
+#pragma unroll
             for (int it = 0; it < 16; it++) {
                 const int r = cw * 32 + it * 2 + half;
-                float4 v = r < rows ? xf[r * 16 + g] : make_float4(0.f, 0.f, 0.f, 0.f);
+                vv[it] = r < rows ? __ldg(xg + r * 16 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_wait(BAR(BAR_A_EMPTY + ab), (uint32_t)(((i >> 1) & 1) ^ 1));
+            unsigned char *a_hi = sm + OFF_A + ab * A_BUF_BYTES, *a_lo = a_hi + A_MAIN_BYTES, *a_aug = a_lo + A_MAIN_BYTES;
+#pragma unroll
+            for (int it = 0; it < 16; it++) {
+                const int r = cw * 32 + it * 2 + half;
+                float4 v = vv[it];
                 if (l2norm) {
                     float q = v.x * v.x;
                     q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
@@ -375,10 +406,7 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
             }
             fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(BAR(BAR_XF_EMPTY));
-                mbar_arrive(BAR(BAR_A_FULL + ab));
-            }
+            if (lane == 0) mbar_arrive(BAR(BAR_A_FULL + ab));
         }
     } else if (warp >= 8) {
         // ================================================================== epilogue
@@ -388,34 +416,32 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
         constexpr float BIG = 3.0e38f;
         uint32_t u = 0;
         for (int64_t i = 0; i < my_tiles; i++) {
-            const int64_t tile = blockIdx.x + i * gridDim.x;
+            const int64_t tile = worker + i * workers;
             const int64_t row = tile * TM + row_in_tile;
             float g1 = BIG, g2 = BIG;
             int j1 = 0, j2 = 0;
             int fallback = 0;
-            for (int jt = 0; jt < ktiles; jt++, u++) {
+            for (int jt = 0; jt < ntl; jt++, u++) {
                 const uint32_t buf = u & 1, ph = (u >> 1) & 1;
                 mbar_wait(BAR(BAR_ACC_FULL + buf), ph);
                 tc_fence_after();
                 if (jt == 0) fallback = flags[(i & 1) * 128 + row_in_tile];
                 float t1 = BIG, t2 = BIG;
-#pragma unroll
-                for (int cb = 0; cb < TN; cb += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem + lane_addr + buf * TN + cb, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        const float ka = __uint_as_float((r[e] & 0xFFFFFF80u) | (uint32_t)(cb + e));
-                        const float kb = __uint_as_float((r[e + 1] & 0xFFFFFF80u) | (uint32_t)(cb + e + 1));
-                        const float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
-                        t2 = fmin3(t2, hi, fmaxf(t1, lo));
-                        t1 = fminf(t1, lo);
-                    }
-                }
+                const uint32_t ta = tmem + lane_addr + buf * TN;
+                uint32_t ra[32], rb[32];
+                tmem_ld32(ta, ra);
+                tmem_ld32(ta + 32, rb);
+                tmem_ld_wait();
+                fold32(ra, 0, t1, t2);
+                tmem_ld32(ta + 64, ra);
+                fold32(rb, 32, t1, t2);
+                tmem_ld32(ta + 96, rb);
+                tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + buf));
+                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + buf));  // accumulator is in registers: free it early
+                fold32(ra, 64, t1, t2);
+                fold32(rb, 96, t1, t2);
                 if (t1 < g1) {
                     if (t2 < g1) g2 = t2, j2 = jt; else g2 = g1, j2 = j1;
                     g1 = t1, j1 = jt;
@@ -424,7 +450,7 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                 }
             }
             if (row < n) {
-                // fp32 re-check of the two candidates with the canonical formula
+                // fp32 re-check of the members of the two best groups with the canonical formula
                 float xr[64];
                 const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
 #pragma unroll
@@ -451,28 +477,40 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                     q[l] = s;
                 }
                 const float xn = tree16(q);
-                int best;
-                float bd;
+                int best = 0;
+                float bd = INFINITY;
                 if (!fallback) {
-                    int ca = j1 * TN + (int)(__float_as_uint(g1) & 127u);
-                    int cbb = j2 * TN + (int)(__float_as_uint(g2) & 127u);
-                    if (ca >= k) ca = 0;      // cannot happen for finite data; keeps the loads in bounds
-                    if (cbb >= k) cbb = ca;
-                    const float da = exact_dist(xr, xn, c, cn, ca);
-                    const float db = exact_dist(xr, xn, c, cn, cbb);
-                    const bool take_b = db < da || (db == da && cbb < ca);
-                    best = take_b ? cbb : ca;
-                    bd = take_b ? db : da;
-                } else {  // out-of-range row: exact scan (rare)
-                    best = 0, bd = INFINITY;
-                    for (int j = 0; j < k; j++) {
+                    int ca = (tile0 + j1) * TN + 4 * (int)(__float_as_uint(g1) & 31u);
+                    int cb = (tile0 + j2) * TN + 4 * (int)(__float_as_uint(g2) & 31u);
+                    if (cb < ca) { const int t = ca; ca = cb; cb = t; }  // ascending columns: strict '<' keeps the lowest index
+#pragma unroll 1
+                    for (int gsel = 0; gsel < 2; gsel++) {
+                        const int c0 = gsel ? cb : ca;
+                        if (gsel && cb == ca) break;
+#pragma unroll 1
+                        for (int e = 0; e < 4; e++) {
+                            const int j = c0 + e;
+                            if (j < k) {
+                                const float dj = exact_dist(xr, xn, c, cn, j);
+                                if (dj < bd) bd = dj, best = j;
+                            }
+                        }
+                    }
+                } else {  // out-of-range row: exact scan of this CTA's centroid range (rare)
+                    const int jend = min(k, (tile0 + ntl) * TN);
+                    for (int j = tile0 * TN; j < jend; j++) {
                         const float dj = exact_dist(xr, xn, c, cn, j);
                         if (dj < bd) bd = dj, best = j;
                     }
                 }
-                if (labels32) labels32[row] = best;
-                if (labels64) labels64[row] = best;
-                if (dist) dist[row] = bd;
+                if (RESIDENT && nslices > 1) {
+                    part_dist[(size_t)slice * n + row] = bd;
+                    part_lab[(size_t)slice * n + row] = best;
+                } else {
+                    if (labels32) labels32[row] = best;
+                    if (labels64) labels64[row] = best;
+                    if (dist) dist[row] = bd;
+                }
             }
         }
     }
@@ -484,8 +522,24 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
     }
 }
 
-// ------------------------------------------------------------------------------------------ host side
+// minimum over centroid slices (slices are in ascending label order: strict '<' keeps the lowest index on ties)
+__global__ void k_tc_merge(const float *__restrict__ part_dist, const int32_t *__restrict__ part_lab, int64_t n,
+                           int nslices, int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
+                           float *__restrict__ dist) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float bd = part_dist[i];
+    int best = part_lab[i];
+    for (int s = 1; s < nslices; s++) {
+        const float d = part_dist[(size_t)s * n + i];
+        if (d < bd) bd = d, best = part_lab[(size_t)s * n + i];
+    }
+    if (labels32) labels32[i] = best;
+    if (labels64) labels64[i] = best;
+    if (dist) dist[i] = bd;
+}
 
+// ------------------------------------------------------------------------------------------ host side
 bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16 && ix->op != nullptr; }
 
 int assign_tc_prepare(at_index *ix, cudaStream_t st) {
@@ -507,15 +561,44 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     }
     static bool configured = false;
     if (!configured) {
-        AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         configured = true;
     }
     const int64_t ntiles = (n + TM - 1) / TM;
-    int grid = sm_count();
+    const int sms = sm_count() > 0 ? sm_count() : 1;
+    const unsigned char *op = reinterpret_cast<const unsigned char *>(ix->op);
+    const int nslices = (ix->ktiles + B_SLOTS - 1) / B_SLOTS;
+    const int mode = ix->tc_mode;  // 0 auto, 1 force stream, 2 force resident
+    const bool resident = mode == 2 ? nslices <= sms : (mode == 1 ? false : nslices <= 4);
+    if (resident) {
+        int workers = sms / nslices;
+        if (workers > ntiles) workers = (int)ntiles;
+        if (workers < 1) workers = 1;
+        if (nslices > 1 && (int64_t)nslices * n > ix->part_cap) {
+            AT_CUDA_OK(cudaStreamSynchronize(st));
+            cudaFree(ix->part_dist), cudaFree(ix->part_lab);
+            ix->part_dist = nullptr, ix->part_lab = nullptr, ix->part_cap = 0;
+            AT_CUDA_OK(cudaMalloc(&ix->part_dist, sizeof(float) * (size_t)nslices * n));
+            AT_CUDA_OK(cudaMalloc(&ix->part_lab, sizeof(int32_t) * (size_t)nslices * n));
+            ix->part_cap = (int64_t)nslices * n;
+        }
+        k_assign_tc<true><<<workers * nslices, TC_THREADS, TC_SMEM, st>>>(x, n, l2norm_rows, op, ix->ktiles, nslices, ix->k,
+                                                                         ix->c, ix->cn, ix->tc_scale, labels32, labels64,
+                                                                         dist, ix->part_dist, ix->part_lab);
+        AT_LAUNCH_OK();
+        if (nslices > 1) {
+            k_tc_merge<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ix->part_dist, ix->part_lab, n, nslices, labels32,
+                                                                    labels64, dist);
+            AT_LAUNCH_OK();
+        }
+        return AT_OK;
+    }
+    int grid = sms;
     if (grid > ntiles) grid = (int)ntiles;
     if (grid < 1) grid = 1;
-    k_assign_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(x, n, l2norm_rows, reinterpret_cast<const unsigned char *>(ix->op),
-                                                  ix->ktiles, ix->k, ix->c, ix->cn, ix->tc_scale, labels32, labels64, dist);
+    k_assign_tc<false><<<grid, TC_THREADS, TC_SMEM, st>>>(x, n, l2norm_rows, op, ix->ktiles, 1, ix->k, ix->c, ix->cn,
+                                                         ix->tc_scale, labels32, labels64, dist, nullptr, nullptr);
     AT_LAUNCH_OK();
     return AT_OK;
 }

@@ -14,6 +14,10 @@ struct at_index {
     // -2*S*c as 128x64 K-major SWIZZLE_128B tiles + a 128x16 no-swizzle tile carrying |c|^2 (at_assign_tc.cu)
     __half *op = nullptr;
     float *tc_scale = nullptr;  // device: {S, S^2 / 4096}
+    int tc_mode = 0;            // 0 auto, 1 stream operand tiles, 2 keep them resident (K-sliced)
+    float *part_dist = nullptr; // (nslices, n) per-slice results of the K-sliced resident mode
+    int32_t *part_lab = nullptr;
+    int64_t part_cap = 0;
     int ktiles = 0;
 };
 

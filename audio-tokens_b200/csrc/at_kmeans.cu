@@ -470,6 +470,7 @@ int at_index_destroy(at_index *ix) {
     cudaFree(ix->cn);
     cudaFree(ix->op);
     cudaFree(ix->tc_scale);
+    cudaFree(ix->part_dist), cudaFree(ix->part_lab);
     delete ix;
     return AT_OK;
 }
@@ -502,6 +503,12 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
 }
 
 int at_index_ntotal(const at_index *ix) { return ix ? ix->k : 0; }
+
+int at_index_set_tc_mode(at_index *ix, int mode) {
+    AT_REQUIRE(ix && mode >= 0 && mode <= 2, "at_index_set_tc_mode: bad arguments");
+    ix->tc_mode = mode;
+    return AT_OK;
+}
 const float *at_index_centroids(const at_index *ix) { return ix ? ix->c : nullptr; }
 
 int at_index_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int algo, int32_t *labels32,

@@ -111,6 +111,9 @@ int at_index_destroy(at_index *index);
  * (norms; for the tcgen05 path the split-fp16 tiles). */
 int at_index_set_centroids(at_index *index, const float *centroids, int k, void *stream);
 int at_index_ntotal(const at_index *index);
+/* Operand policy of the tcgen05 kernel: 0 auto (default), 1 stream centroid tiles through a ring for every row tile,
+ * 2 keep up to 512 centroids per CTA resident in shared memory and split larger vocabularies into slices. */
+int at_index_set_tc_mode(at_index *index, int mode);
 /* fp32 (k, d) centroids currently held (device pointer, valid until the next set / destroy). */
 const float *at_index_centroids(const at_index *index);
 /* search(x, 1).  l2norm_rows != 0 applies normalize_vectors to each row while loading.

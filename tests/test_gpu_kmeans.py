@@ -227,8 +227,9 @@ def test_bincount():
 
 
 # ------------------------------------------------------------------------------------------------ tcgen05 path
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("k,n", [(256, 20000), (1024, 30011), (500, 4097), (16, 300), (2000, 12800)])
-def test_search_tensor_matches_exact_simt(k, n):
+def test_search_tensor_matches_exact_simt(k, n, mode):
     """The tcgen05 kernel re-checks its top-2 with the canonical fp32 formula, so labels AND distances must
     equal the exact SIMT kernel's bit for bit (a 3-way tie within ~1e-7 is the only documented exception)."""
     import torch
@@ -240,11 +241,12 @@ def test_search_tensor_matches_exact_simt(k, n):
     g = torch.Generator().manual_seed(k)
     c = l2[torch.randperm(l2.shape[0], generator=g)[:k].cuda()].contiguous()
     ix = FlatL2(64)
+    ix.set_tc_mode(mode)  # 1: streamed operand tiles, 2: resident / K-sliced
     ix.set_centroids(c)
     ls, ds = ix.search(x, algo=_lib.ALGO_SIMT)
     lt, dt = ix.search(x, algo=_lib.ALGO_TENSOR)
     mism = (ls != lt)
-    print(f"tensor vs simt k={k} n={n}: label mismatches {int(mism.sum())}")
+    print(f"tensor vs simt k={k} n={n} mode={mode}: label mismatches {int(mism.sum())}")
     assert int(mism.sum()) <= max(1, n // 100000)
     assert torch.equal(ds[~mism], dt[~mism])
     # fused row normalisation
