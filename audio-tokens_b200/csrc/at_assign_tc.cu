@@ -8,12 +8,10 @@
 // in ONE chain of 13 tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
 //     x_hi * c_hi  +  x_hi * c_lo  +  x_lo * c_hi          (fp16 hi/lo split of S*x and -2*S*c: ~22 mantissa bits)
 //   + [xn pieces | 2^12 2^12 2^12] * [2^12 2^12 2^12 | cn pieces]   (one extra K=16 step carrying both norms)
-// so the epilogue only has to find, per row, the two best GROUPS of four adjacent centroids (a group minimum costs
-// half an ALU op per score with FMNMX3; the group id rides in the low 5 mantissa bits).  The two best groups always
-// contain the two best centroids, so their 8 members are re-evaluated with the library's canonical fp32 formula
-// (at_index.cuh) -- the very one the exact SIMT kernel uses -- and the smallest wins (lowest index on exact ties).
-// Token ids therefore agree with the fp32 path except when a third group lies within ~1e-7 (absolute, unit-norm
-// data) of the minimum.
+// so the epilogue only has to keep a per-row top-2 of packed (distance | column) keys (FMNMX / FMNMX3, four independent
+// chains).  The two candidates are re-evaluated with the library's canonical fp32 formula (at_index.cuh) -- the very
+// one the exact SIMT kernel uses -- and the smaller wins (lowest index on exact ties).  Token ids therefore agree
+// with the fp32 path except when three or more centroids lie within ~1e-7 (absolute, unit-norm data) of the minimum.
 //
 // Roofline note: 2*N*K*64 algorithmic flops are executed as 3.25x that many fp16 MMA flops.
 //
@@ -232,21 +230,24 @@ __device__ __forceinline__ float exact_dist(const float (&xr)[64], float xn, con
     return l2_expanded(xn, __ldg(cn + j), tree16(q));
 }
 
-// group minima of 32 accumulator columns (8 groups of 4) folded into the running packed top-2 (t1 <= t2)
-__device__ __forceinline__ void fold32(const uint32_t (&r)[32], int cb, float &t1, float &t2) {
+// 32 accumulator columns folded into four independent packed (distance | column) top-2 chains (t1[c] <= t2[c]);
+// four chains so that one warp per scheduler has enough independent FMNMX work to keep the ALU pipe issuing.
+__device__ __forceinline__ void fold32(const uint32_t (&r)[32], int cb, float (&t1)[4], float (&t2)[4]) {
 #pragma unroll
-    for (int gp = 0; gp < 4; gp++) {
-        const int e = 8 * gp;
-        const float a = fminf(fmin3(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), __uint_as_float(r[e + 2])),
-                              __uint_as_float(r[e + 3]));
-        const float b = fminf(fmin3(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]), __uint_as_float(r[e + 6])),
-                              __uint_as_float(r[e + 7]));
-        const float ka = __uint_as_float((__float_as_uint(a) & 0xFFFFFFE0u) | (uint32_t)(cb / 4 + 2 * gp));
-        const float kb = __uint_as_float((__float_as_uint(b) & 0xFFFFFFE0u) | (uint32_t)(cb / 4 + 2 * gp + 1));
+    for (int p = 0; p < 16; p++) {
+        const int e = 2 * p, ch = p & 3;
+        const float ka = __uint_as_float((r[e] & 0xFFFFFF80u) | (uint32_t)(cb + e));
+        const float kb = __uint_as_float((r[e + 1] & 0xFFFFFF80u) | (uint32_t)(cb + e + 1));
         const float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
-        t2 = fmin3(t2, hi, fmaxf(t1, lo));
-        t1 = fminf(t1, lo);
+        t2[ch] = fmin3(t2[ch], hi, fmaxf(t1[ch], lo));
+        t1[ch] = fminf(t1[ch], lo);
     }
+}
+// merge chain b into chain a
+__device__ __forceinline__ void merge_top2(float &a1, float &a2, float b1, float b2) {
+    const float lo = fminf(a1, b1), hi = fmaxf(a1, b1);
+    a2 = fmin3(hi, a2, b2);
+    a1 = lo;
 }
 
 // RESIDENT: blockIdx.x % nslices selects the centroid slice [tile0, tile0 + ntl), kept in shared memory.
@@ -426,22 +427,26 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                 mbar_wait(BAR(BAR_ACC_FULL + buf), ph);
                 tc_fence_after();
                 if (jt == 0) fallback = flags[(i & 1) * 128 + row_in_tile];
-                float t1 = BIG, t2 = BIG;
+                float c1[4] = {BIG, BIG, BIG, BIG}, c2[4] = {BIG, BIG, BIG, BIG};
                 const uint32_t ta = tmem + lane_addr + buf * TN;
                 uint32_t ra[32], rb[32];
                 tmem_ld32(ta, ra);
                 tmem_ld32(ta + 32, rb);
                 tmem_ld_wait();
-                fold32(ra, 0, t1, t2);
+                fold32(ra, 0, c1, c2);
                 tmem_ld32(ta + 64, ra);
-                fold32(rb, 32, t1, t2);
+                fold32(rb, 32, c1, c2);
                 tmem_ld32(ta + 96, rb);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + buf));  // accumulator is in registers: free it early
-                fold32(ra, 64, t1, t2);
-                fold32(rb, 96, t1, t2);
+                fold32(ra, 64, c1, c2);
+                fold32(rb, 96, c1, c2);
+                merge_top2(c1[0], c2[0], c1[1], c2[1]);
+                merge_top2(c1[2], c2[2], c1[3], c2[3]);
+                merge_top2(c1[0], c2[0], c1[2], c2[2]);
+                const float t1 = c1[0], t2 = c2[0];
                 if (t1 < g1) {
                     if (t2 < g1) g2 = t2, j2 = jt; else g2 = g1, j2 = j1;
                     g1 = t1, j1 = jt;
@@ -450,7 +455,7 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                 }
             }
             if (row < n) {
-                // fp32 re-check of the members of the two best groups with the canonical formula
+                // fp32 re-check of the two candidates with the canonical formula
                 float xr[64];
                 const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
 #pragma unroll
@@ -480,22 +485,15 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                 int best = 0;
                 float bd = INFINITY;
                 if (!fallback) {
-                    int ca = (tile0 + j1) * TN + 4 * (int)(__float_as_uint(g1) & 31u);
-                    int cb = (tile0 + j2) * TN + 4 * (int)(__float_as_uint(g2) & 31u);
-                    if (cb < ca) { const int t = ca; ca = cb; cb = t; }  // ascending columns: strict '<' keeps the lowest index
-#pragma unroll 1
-                    for (int gsel = 0; gsel < 2; gsel++) {
-                        const int c0 = gsel ? cb : ca;
-                        if (gsel && cb == ca) break;
-#pragma unroll 1
-                        for (int e = 0; e < 4; e++) {
-                            const int j = c0 + e;
-                            if (j < k) {
-                                const float dj = exact_dist(xr, xn, c, cn, j);
-                                if (dj < bd) bd = dj, best = j;
-                            }
-                        }
-                    }
+                    int ca = (tile0 + j1) * TN + (int)(__float_as_uint(g1) & 127u);
+                    int cb = (tile0 + j2) * TN + (int)(__float_as_uint(g2) & 127u);
+                    if (ca >= k) ca = tile0 * TN;  // cannot happen for finite data; keeps the loads in bounds
+                    if (cb >= k) cb = ca;
+                    const float da = exact_dist(xr, xn, c, cn, ca);
+                    const float db = exact_dist(xr, xn, c, cn, cb);
+                    const bool take_b = db < da || (db == da && cb < ca);
+                    best = take_b ? cb : ca;
+                    bd = take_b ? db : da;
                 } else {  // out-of-range row: exact scan of this CTA's centroid range (rare)
                     const int jend = min(k, (tile0 + ntl) * TN);
                     for (int j = tile0 * TN; j < jend; j++) {
