@@ -8,10 +8,14 @@
 // in ONE chain of 13 tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
 //     x_hi * c_hi  +  x_hi * c_lo  +  x_lo * c_hi          (fp16 hi/lo split of S*x and -2*S*c: ~22 mantissa bits)
 //   + [xn pieces | 2^12 2^12 2^12] * [2^12 2^12 2^12 | cn pieces]   (one extra K=16 step carrying both norms)
-// so the epilogue only has to keep a per-row top-2 of packed (distance | column) keys (FMNMX / FMNMX3, four independent
-// chains).  The two candidates are re-evaluated with the library's canonical fp32 formula (at_index.cuh) -- the very
-// one the exact SIMT kernel uses -- and the smaller wins (lowest index on exact ties).  Token ids therefore agree
-// with the fp32 path except when three or more centroids lie within ~1e-7 (absolute, unit-norm data) of the minimum.
+// so the epilogue only scans packed (distance | column) keys.  The ALU pipe (FMNMX, LOP3: one warp instruction per two
+// cycles per scheduler) bounds that scan, so it keeps the top-2 over minima of groups of four adjacent columns
+// (1.8 ALU ops per score) instead of an exact per-column top-2 (3.5, measured ALU-bound at 2.1x the MMA time).  The
+// two candidates are re-evaluated by separate warps with the library's canonical fp32 formula (at_index.cuh) -- the
+// one the exact SIMT kernel uses -- and the smaller wins (lowest index on exact ties).
+// Tie note: token ids agree with the fp32 path except when (a) three or more centroids lie within ~1e-7 (absolute,
+// unit-norm data) of the minimum, or (b) the runner-up shares the winner's group of four AND lies within ~1e-7 of it
+// (the group hides it from the re-check); both are ties below what the fp32 formula itself resolves.
 //
 // Roofline note: 2*N*K*64 algorithmic flops are executed as 3.25x that many fp16 MMA flops.
 //
@@ -22,18 +26,19 @@
 //             re-streaming from L2 (at K = 1024 the streaming mode moved 22 GB per launch through L2).
 //   STREAM    (any K): operand tiles are streamed through a 4-slot ring with cp.async.bulk.
 //
-// Structure: persistent CTAs (one per SM), 12 warps:
+// Structure: persistent CTAs (one per SM), 16 warps:
 //   warp 1  lane 0   issues tcgen05.mma, commits to mbarriers
 //   warp 2           TMEM allocation / deallocation
 //   warp 3  lane 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into shared memory
 //   warps 4-7        read the fp32 row tile (coalesced 128-bit loads), optional row L2 normalisation, |x|^2, fp16 hi/lo
 //                    split written straight into the SWIZZLE_128B K-major layout the MMA descriptors expect
-//   warps 8-11       epilogue: tcgen05.ld the accumulator, group minima + packed top-2, fp32 re-check, outputs
+//   warps 8-11       epilogue: tcgen05.ld the accumulator, packed keys, group minima, top-2 -> two candidate columns
+//   warps 12-15      fp32 re-check of the candidates (off the MMA critical path), labels / distances out
 #include "at_index.cuh"
 
 namespace at {
 
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 512;
 constexpr int TM = 128;          // rows per tile (UMMA M)
 constexpr int TN = 128;          // centroids per tile (UMMA N)
 constexpr int B_SLOTS = 4;       // operand tiles resident per CTA / ring depth
@@ -47,7 +52,8 @@ constexpr uint32_t OFF_A = 0;                                    // 2 buffers
 constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 4 slots
 constexpr uint32_t OFF_BAR = OFF_B + B_SLOTS * B_TILE_BYTES;     // mbarriers
 constexpr uint32_t OFF_FLAGS = OFF_BAR + 256;                    // row fallback flags 2 x 128 bytes
-constexpr uint32_t TC_SMEM = OFF_FLAGS + 256 + 1024;             // + slack for manual 1024-B alignment
+constexpr uint32_t OFF_CAND = OFF_FLAGS + 256;                   // candidate pairs 2 x 128 x int2
+constexpr uint32_t TC_SMEM = OFF_CAND + 2048 + 1024;             // + slack for manual 1024-B alignment
 static_assert(OFF_A % 1024 == 0 && OFF_B % 1024 == 0 && A_BUF_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "align");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
 
@@ -58,7 +64,9 @@ enum {
     BAR_B_EMPTY = 8,   // +4
     BAR_ACC_FULL = 12,   // +2
     BAR_ACC_EMPTY = 14,  // +2
-    BAR_COUNT = 16
+    BAR_CAND_FULL = 16,  // +2
+    BAR_CAND_EMPTY = 18, // +2
+    BAR_COUNT = 20
 };
 
 constexpr float AUG_ONE = 4096.0f;            // 2^12, exact in fp16
@@ -230,15 +238,21 @@ __device__ __forceinline__ float exact_dist(const float (&xr)[64], float xn, con
     return l2_expanded(xn, __ldg(cn + j), tree16(q));
 }
 
-// 32 accumulator columns folded into four independent packed (distance | column) top-2 chains (t1[c] <= t2[c]);
-// four chains so that one warp per scheduler has enough independent FMNMX work to keep the ALU pipe issuing.
-__device__ __forceinline__ void fold32(const uint32_t (&r)[32], int cb, float (&t1)[4], float (&t2)[4]) {
+// 32 accumulator columns -> packed (distance | column) keys -> minima of groups of four adjacent columns (FMNMX3 +
+// FMNMX: half an ALU op per score) -> running top-2 over GROUP minima, two independent chains.
+// ALU-pipe budget: 1 LOP3 + 0.5 + 0.31 ops per score (the exact per-column top-2 needs 3.5 and is ALU-bound).
+// The best column overall is always the minimum of the best group; the runner-up is the minimum of the second-best
+// group unless it sits in the best group itself (3 of K-1 positions) -- see the tie note in the file header.
+__device__ __forceinline__ void fold32(const uint32_t (&r)[32], int cb, float (&t1)[2], float (&t2)[2]) {
 #pragma unroll
-    for (int p = 0; p < 16; p++) {
-        const int e = 2 * p, ch = p & 3;
-        const float ka = __uint_as_float((r[e] & 0xFFFFFF80u) | (uint32_t)(cb + e));
-        const float kb = __uint_as_float((r[e + 1] & 0xFFFFFF80u) | (uint32_t)(cb + e + 1));
-        const float lo = fminf(ka, kb), hi = fmaxf(ka, kb);
+    for (int gp = 0; gp < 4; gp++) {
+        const int e = 8 * gp, ch = gp & 1;
+        float kx[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) kx[i] = __uint_as_float((r[e + i] & 0xFFFFFF80u) | (uint32_t)(cb + e + i));
+        const float a = fminf(fmin3(kx[0], kx[1], kx[2]), kx[3]);
+        const float b = fminf(fmin3(kx[4], kx[5], kx[6]), kx[7]);
+        const float lo = fminf(a, b), hi = fmaxf(a, b);
         t2[ch] = fmin3(t2[ch], hi, fmaxf(t1[ch], lo));
         t1[ch] = fminf(t1[ch], lo);
     }
@@ -280,6 +294,8 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
             mbar_init(BAR(BAR_A_EMPTY + i), 1);
             mbar_init(BAR(BAR_ACC_FULL + i), 1);
             mbar_init(BAR(BAR_ACC_EMPTY + i), 4);
+            mbar_init(BAR(BAR_CAND_FULL + i), 4);
+            mbar_init(BAR(BAR_CAND_EMPTY + i), 4);
         }
         for (int i = 0; i < B_SLOTS; i++) {
             mbar_init(BAR(BAR_B_FULL + i), 1);
@@ -409,16 +425,15 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(BAR_A_FULL + ab));
         }
-    } else if (warp >= 8) {
-        // ================================================================== epilogue
+    } else if (warp >= 8 && warp < 12) {
+        // ================================================================== epilogue: accumulator scan
         const int ew = warp - 8;  // == warp % 4: the TMEM lane quadrant this warp may read
         const int row_in_tile = ew * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         constexpr float BIG = 3.0e38f;
+        int2 *cand = reinterpret_cast<int2 *>(sm + OFF_CAND);
         uint32_t u = 0;
         for (int64_t i = 0; i < my_tiles; i++) {
-            const int64_t tile = worker + i * workers;
-            const int64_t row = tile * TM + row_in_tile;
             float g1 = BIG, g2 = BIG;
             int j1 = 0, j2 = 0;
             int fallback = 0;
@@ -426,8 +441,9 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                 const uint32_t buf = u & 1, ph = (u >> 1) & 1;
                 mbar_wait(BAR(BAR_ACC_FULL + buf), ph);
                 tc_fence_after();
+                // the converters may rewrite this flag slot as soon as MMA(i) retires: read it now
                 if (jt == 0) fallback = flags[(i & 1) * 128 + row_in_tile];
-                float c1[4] = {BIG, BIG, BIG, BIG}, c2[4] = {BIG, BIG, BIG, BIG};
+                float c1[2] = {BIG, BIG}, c2[2] = {BIG, BIG};
                 const uint32_t ta = tmem + lane_addr + buf * TN;
                 uint32_t ra[32], rb[32];
                 tmem_ld32(ta, ra);
@@ -444,8 +460,6 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                 fold32(ra, 64, c1, c2);
                 fold32(rb, 96, c1, c2);
                 merge_top2(c1[0], c2[0], c1[1], c2[1]);
-                merge_top2(c1[2], c2[2], c1[3], c2[3]);
-                merge_top2(c1[0], c2[0], c1[2], c2[2]);
                 const float t1 = c1[0], t2 = c2[0];
                 if (t1 < g1) {
                     if (t2 < g1) g2 = t2, j2 = jt; else g2 = g1, j2 = j1;
@@ -454,39 +468,61 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                     g2 = t1, j2 = jt;
                 }
             }
-            if (row < n) {
-                // fp32 re-check of the two candidates with the canonical formula
-                float xr[64];
-                const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
+            // hand the two candidate columns to the re-check warps
+            const uint32_t cbuf = (uint32_t)(i & 1);
+            mbar_wait(BAR(BAR_CAND_EMPTY + cbuf), (uint32_t)(((i >> 1) & 1) ^ 1));
+            cand[cbuf * 128 + row_in_tile] = make_int2(((tile0 + j1) * TN + (int)(__float_as_uint(g1) & 127u)) | (fallback << 30),
+                                                       (tile0 + j2) * TN + (int)(__float_as_uint(g2) & 127u));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_CAND_FULL + cbuf));
+        }
+    } else if (warp >= 12) {
+        // ================================================================== fp32 re-check + outputs
+        const int row_in_tile = (warp - 12) * 32 + lane;
+        const int2 *cand = reinterpret_cast<const int2 *>(sm + OFF_CAND);
+        for (int64_t i = 0; i < my_tiles; i++) {
+            const int64_t tile = worker + i * workers;
+            const int64_t row = tile * TM + row_in_tile;
+            const bool live = row < n;
+            // the row itself does not depend on the scan: fetch and normalise it first
+            float xr[64];
+            const float4 *xp = reinterpret_cast<const float4 *>(x + (live ? row : 0) * 64);
 #pragma unroll
-                for (int l = 0; l < 16; l++) {
-                    float4 v = __ldg(xp + l);
-                    xr[4 * l] = v.x, xr[4 * l + 1] = v.y, xr[4 * l + 2] = v.z, xr[4 * l + 3] = v.w;
-                }
-                float q[16];
-                if (l2norm) {
-#pragma unroll
-                    for (int l = 0; l < 16; l++) {
-                        float s = xr[4 * l] * xr[4 * l];
-                        s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
-                        q[l] = s;
-                    }
-                    const float den = l2_denominator(tree16(q));
-#pragma unroll
-                    for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
-                }
+            for (int l = 0; l < 16; l++) {
+                float4 v = __ldg(xp + l);
+                xr[4 * l] = v.x, xr[4 * l + 1] = v.y, xr[4 * l + 2] = v.z, xr[4 * l + 3] = v.w;
+            }
+            float q[16];
+            if (l2norm) {
 #pragma unroll
                 for (int l = 0; l < 16; l++) {
                     float s = xr[4 * l] * xr[4 * l];
                     s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
                     q[l] = s;
                 }
-                const float xn = tree16(q);
+                const float den = l2_denominator(tree16(q));
+#pragma unroll
+                for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
+            }
+#pragma unroll
+            for (int l = 0; l < 16; l++) {
+                float s = xr[4 * l] * xr[4 * l];
+                s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
+                q[l] = s;
+            }
+            const float xn = tree16(q);
+            const uint32_t cbuf = (uint32_t)(i & 1);
+            mbar_wait(BAR(BAR_CAND_FULL + cbuf), (uint32_t)((i >> 1) & 1));
+            int2 cc = cand[cbuf * 128 + row_in_tile];
+            const int fallback = (cc.x >> 30) & 1;
+            cc.x &= 0x3FFFFFFF;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_CAND_EMPTY + cbuf));
+            if (live) {
                 int best = 0;
                 float bd = INFINITY;
                 if (!fallback) {
-                    int ca = (tile0 + j1) * TN + (int)(__float_as_uint(g1) & 127u);
-                    int cb = (tile0 + j2) * TN + (int)(__float_as_uint(g2) & 127u);
+                    int ca = cc.x, cb = cc.y;
                     if (ca >= k) ca = tile0 * TN;  // cannot happen for finite data; keeps the loads in bounds
                     if (cb >= k) cb = ca;
                     const float da = exact_dist(xr, xn, c, cn, ca);
