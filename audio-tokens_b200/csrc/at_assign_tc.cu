@@ -13,6 +13,9 @@
 // (1.8 ALU ops per score) instead of an exact per-column top-2 (3.5, measured ALU-bound at 2.1x the MMA time).  The
 // two candidates are re-evaluated by separate warps with the library's canonical fp32 formula (at_index.cuh) -- the
 // one the exact SIMT kernel uses -- and the smaller wins (lowest index on exact ties).
+// A row whose runner-up is safely behind the winner (gap above a bound on the split-fp16 error) skips the re-check: its
+// label is final and its distance is the accumulator value / S^2 (agrees with the canonical fp32 value to ~2e-5
+// relative, 1e-6 absolute for unit-norm data).  All other rows get the exact canonical distance.
 // Tie note: token ids agree with the fp32 path except when (a) three or more centroids lie within ~1e-7 (absolute,
 // unit-norm data) of the minimum, or (b) the runner-up shares the winner's group of four AND lies within ~1e-7 of it
 // (the group hides it from the re-check); both are ties below what the fp32 formula itself resolves.
@@ -182,6 +185,11 @@ __global__ void k_tc_scale(const float *__restrict__ c, int n, float *__restrict
         float S = ldexpf(1.0f, e);
         scale[0] = S;
         scale[1] = S * S * AUG_INV;
+        scale[2] = 1.0f / (S * S);
+        // absolute part of the "is the runner-up safely behind?" threshold, in accumulator units: 2^-18 * S^2 * 64 m^2
+        // bounds 2^-18 S^2 |c|^2 (m = max |c_ij|); split-fp16 products carry ~2^-21 of |x||c| S^2, fp32 accumulation
+        // a few 2^-24 of the same, so this leaves a factor ~4 of head-room
+        scale[3] = ldexpf(S * S * 64.0f * m * m, -18);
     }
 }
 
@@ -432,6 +440,7 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         constexpr float BIG = 3.0e38f;
         int2 *cand = reinterpret_cast<int2 *>(sm + OFF_CAND);
+        const float inv_s2 = scale[2], tau_abs = scale[3];
         uint32_t u = 0;
         for (int64_t i = 0; i < my_tiles; i++) {
             float g1 = BIG, g2 = BIG;
@@ -468,11 +477,24 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
                     g2 = t1, j2 = jt;
                 }
             }
-            // hand the two candidate columns to the re-check warps
+            // Runner-up safely behind the winner (beyond what the split-fp16 product can get wrong)?  Then the winner
+            // is final and its distance is read off the accumulator; otherwise the re-check warps decide in fp32.
+            const int64_t tile = worker + i * workers;
+            const int64_t row = tile * TM + row_in_tile;
+            const float v1 = __uint_as_float(__float_as_uint(g1) & 0xFFFFFF80u);
+            const float v2 = __uint_as_float(__float_as_uint(g2) & 0xFFFFFF80u);
+            const int ca = (tile0 + j1) * TN + (int)(__float_as_uint(g1) & 127u);
+            const int cb = (tile0 + j2) * TN + (int)(__float_as_uint(g2) & 127u);
+            const bool sliced = RESIDENT && nslices > 1;  // slices are merged on exact distances
+            const bool safe = !fallback && !sliced && (v2 - v1 > fmaf(fabsf(v1), 1.52587890625e-5f, tau_abs)) && ca < k;
+            if (safe && row < n) {
+                if (labels32) labels32[row] = ca;
+                if (labels64) labels64[row] = ca;
+                if (dist) dist[row] = fmaxf(v1, 0.f) * inv_s2;
+            }
             const uint32_t cbuf = (uint32_t)(i & 1);
             mbar_wait(BAR(BAR_CAND_EMPTY + cbuf), (uint32_t)(((i >> 1) & 1) ^ 1));
-            cand[cbuf * 128 + row_in_tile] = make_int2(((tile0 + j1) * TN + (int)(__float_as_uint(g1) & 127u)) | (fallback << 30),
-                                                       (tile0 + j2) * TN + (int)(__float_as_uint(g2) & 127u));
+            cand[cbuf * 128 + row_in_tile] = make_int2(safe ? -1 : (ca | (fallback << 30)), cb);
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(BAR_CAND_FULL + cbuf));
         }
@@ -483,41 +505,44 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
         for (int64_t i = 0; i < my_tiles; i++) {
             const int64_t tile = worker + i * workers;
             const int64_t row = tile * TM + row_in_tile;
-            const bool live = row < n;
-            // the row itself does not depend on the scan: fetch and normalise it first
+            const uint32_t cbuf = (uint32_t)(i & 1);
+            mbar_wait(BAR(BAR_CAND_FULL + cbuf), (uint32_t)((i >> 1) & 1));
+            int2 cc = cand[cbuf * 128 + row_in_tile];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(BAR_CAND_EMPTY + cbuf));
+            const bool live = row < n && cc.x >= 0;   // cc.x < 0: the scan already wrote this row
+            if (!__any_sync(0xffffffffu, live)) continue;
+            const int fallback = (cc.x >> 30) & 1;
+            cc.x &= 0x3FFFFFFF;
             float xr[64];
-            const float4 *xp = reinterpret_cast<const float4 *>(x + (live ? row : 0) * 64);
+            float xn = 0.f;
+            if (live) {
+                const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
 #pragma unroll
-            for (int l = 0; l < 16; l++) {
-                float4 v = __ldg(xp + l);
-                xr[4 * l] = v.x, xr[4 * l + 1] = v.y, xr[4 * l + 2] = v.z, xr[4 * l + 3] = v.w;
-            }
-            float q[16];
-            if (l2norm) {
+                for (int l = 0; l < 16; l++) {
+                    float4 v = __ldg(xp + l);
+                    xr[4 * l] = v.x, xr[4 * l + 1] = v.y, xr[4 * l + 2] = v.z, xr[4 * l + 3] = v.w;
+                }
+                float q[16];
+                if (l2norm) {
+#pragma unroll
+                    for (int l = 0; l < 16; l++) {
+                        float s = xr[4 * l] * xr[4 * l];
+                        s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
+                        q[l] = s;
+                    }
+                    const float den = l2_denominator(tree16(q));
+#pragma unroll
+                    for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
+                }
 #pragma unroll
                 for (int l = 0; l < 16; l++) {
                     float s = xr[4 * l] * xr[4 * l];
                     s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
                     q[l] = s;
                 }
-                const float den = l2_denominator(tree16(q));
-#pragma unroll
-                for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
+                xn = tree16(q);
             }
-#pragma unroll
-            for (int l = 0; l < 16; l++) {
-                float s = xr[4 * l] * xr[4 * l];
-                s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
-                q[l] = s;
-            }
-            const float xn = tree16(q);
-            const uint32_t cbuf = (uint32_t)(i & 1);
-            mbar_wait(BAR(BAR_CAND_FULL + cbuf), (uint32_t)((i >> 1) & 1));
-            int2 cc = cand[cbuf * 128 + row_in_tile];
-            const int fallback = (cc.x >> 30) & 1;
-            cc.x &= 0x3FFFFFFF;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_CAND_EMPTY + cbuf));
             if (live) {
                 int best = 0;
                 float bd = INFINITY;
@@ -577,7 +602,7 @@ __global__ void k_tc_merge(const float *__restrict__ part_dist, const int32_t *_
 bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16 && ix->op != nullptr; }
 
 int assign_tc_prepare(at_index *ix, cudaStream_t st) {
-    if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, 2 * sizeof(float)));
+    if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, 4 * sizeof(float)));
     k_tc_scale<<<1, 1024, 0, st>>>(ix->c, ix->k * 64, ix->tc_scale);
     AT_LAUNCH_OK();
     const int total = ix->ktiles * TN * 9;
@@ -604,7 +629,7 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     const unsigned char *op = reinterpret_cast<const unsigned char *>(ix->op);
     const int nslices = (ix->ktiles + B_SLOTS - 1) / B_SLOTS;
     const int mode = ix->tc_mode;  // 0 auto, 1 force stream, 2 force resident
-    const bool resident = mode == 2 ? nslices <= sms : (mode == 1 ? false : nslices <= 4);
+    const bool resident = mode == 2 ? nslices <= sms : (mode == 1 ? false : nslices <= 1);
     if (resident) {
         int workers = sms / nslices;
         if (workers > ntiles) workers = (int)ntiles;

@@ -230,8 +230,8 @@ def test_bincount():
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("k,n", [(256, 20000), (1024, 30011), (500, 4097), (16, 300), (2000, 12800)])
 def test_search_tensor_matches_exact_simt(k, n, mode):
-    """The tcgen05 kernel re-checks its top-2 with the canonical fp32 formula, so labels AND distances must
-    equal the exact SIMT kernel's bit for bit (a 3-way tie within ~1e-7 is the only documented exception)."""
+    """The tcgen05 kernel re-checks near-tied top-2 candidates with the canonical fp32 formula, so labels must equal
+    the exact SIMT kernel's (ties below fp32 resolution are the documented exception); distances agree to ~2e-5."""
     import torch
     from at_b200 import FlatL2, _lib
 
@@ -248,7 +248,8 @@ def test_search_tensor_matches_exact_simt(k, n, mode):
     mism = (ls != lt)
     print(f"tensor vs simt k={k} n={n} mode={mode}: label mismatches {int(mism.sum())}")
     assert int(mism.sum()) <= max(1, n // 100000)
-    assert torch.equal(ds[~mism], dt[~mism])
+    # rows whose runner-up is safely behind skip the fp32 re-check: distance read off the accumulator
+    torch.testing.assert_close(dt[~mism], ds[~mism], rtol=1e-4, atol=2e-6)
     # fused row normalisation
     lt2, dt2 = ix.search(spec[:n].contiguous(), l2norm_rows=True, algo=_lib.ALGO_TENSOR)
     ls2, ds2 = ix.search(spec[:n].contiguous(), l2norm_rows=True, algo=_lib.ALGO_SIMT)
@@ -272,7 +273,8 @@ def test_search_tensor_random_and_out_of_range_rows():
     ix.set_centroids(c)
     ls, ds = ix.search(x, algo=_lib.ALGO_SIMT)
     lt, dt = ix.search(x, algo=_lib.ALGO_TENSOR)
-    assert torch.equal(ls, lt) and torch.equal(ds, dt)
+    assert torch.equal(ls, lt)
+    torch.testing.assert_close(dt, ds, rtol=1e-4, atol=1e-4)
     _check_labels(lt.cpu().numpy(), x.cpu().numpy(), c.cpu().numpy(), "tensor randn")
 
 
@@ -293,5 +295,6 @@ def test_lloyd_tensor_vs_simt_bit_identical_centroids():
         for it in range(5):
             tr.step(l2, st[it])
         outs.append((tr.get_centroids(), st.clone()))
-    assert torch.equal(outs[0][0], outs[1][0])
-    assert torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[1][0])           # centroids: bit-identical
+    assert torch.equal(outs[0][1][:, 1:], outs[1][1][:, 1:])  # nsplit, imbalance, empties
+    torch.testing.assert_close(outs[0][1][:, 0], outs[1][1][:, 0], rtol=1e-4, atol=0)  # objective
