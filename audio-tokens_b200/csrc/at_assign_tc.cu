@@ -186,10 +186,10 @@ __global__ void k_tc_scale(const float *__restrict__ c, int n, float *__restrict
         scale[0] = S;
         scale[1] = S * S * AUG_INV;
         scale[2] = 1.0f / (S * S);
-        // absolute part of the "is the runner-up safely behind?" threshold, in accumulator units: 2^-18 * S^2 * 64 m^2
-        // bounds 2^-18 S^2 |c|^2 (m = max |c_ij|); split-fp16 products carry ~2^-21 of |x||c| S^2, fp32 accumulation
+        // absolute part of the "is the runner-up safely behind?" threshold, in accumulator units: 2^-19 * S^2 * 64 m^2
+        // bounds 2^-19 S^2 |c|^2 (m = max |c_ij|); split-fp16 products carry ~2^-21 of |x||c| S^2, fp32 accumulation
         // a few 2^-24 of the same, so this leaves a factor ~4 of head-room
-        scale[3] = ldexpf(S * S * 64.0f * m * m, -18);
+        scale[3] = ldexpf(S * S * 64.0f * m * m, -19);
     }
 }
 

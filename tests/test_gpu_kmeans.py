@@ -249,7 +249,7 @@ def test_search_tensor_matches_exact_simt(k, n, mode):
     print(f"tensor vs simt k={k} n={n} mode={mode}: label mismatches {int(mism.sum())}")
     assert int(mism.sum()) <= max(1, n // 100000)
     # rows whose runner-up is safely behind skip the fp32 re-check: distance read off the accumulator
-    torch.testing.assert_close(dt[~mism], ds[~mism], rtol=1e-4, atol=2e-6)
+    torch.testing.assert_close(dt[~mism], ds[~mism], rtol=1e-4, atol=5e-6)
     # fused row normalisation
     lt2, dt2 = ix.search(spec[:n].contiguous(), l2norm_rows=True, algo=_lib.ALGO_TENSOR)
     ls2, ds2 = ix.search(spec[:n].contiguous(), l2norm_rows=True, algo=_lib.ALGO_SIMT)
