@@ -8,6 +8,9 @@
 //   check_for_nan_inf       -> bad flag
 //
 // Kernel shape (one persistent CTA of 16 warps per SM, clips dealt round-robin):
+//   * the sample window of the next batch of frames (31 hops + n_fft samples, <= 67.6 KB) is fetched into shared memory
+//     by one cp.async.bulk (TMA engine) while the current batch is in its mel / write-out phases, so overlapping
+//     frames are read from HBM once and no warp ever waits on DRAM (reflected edge frames read global memory);
 //   * a warp owns one "job": 1024 complex points = G complex FFTs of n_fft points, each packing TWO real
 //     frames (frame a -> real part, frame b -> imaginary part), so no arithmetic is spent on the redundant
 //     half of a real-input transform;
@@ -21,6 +24,7 @@
 //   * after the clip's last frame the CTA normalises the clip's tile in place (it is still in L2).
 #include "at_common.cuh"
 #include "at_index.cuh"
+#include "at_ptx.cuh"
 
 #include <math.h>
 #include <new>
@@ -129,9 +133,10 @@ __device__ __forceinline__ int64_t reflect_index(int64_t s, int64_t L) {
 
 constexpr int MEL_WARPS = 16;
 constexpr int MEL_THREADS = MEL_WARPS * 32;
-constexpr int XCH_STRIDE = 33;                          // float2 per exchange row (32 + 1 pad)
-constexpr int XCH_WARP_F2 = 32 * XCH_STRIDE;            // float2 per warp
-constexpr int XCH_BYTES = MEL_WARPS * XCH_WARP_F2 * 8;  // 135,168
+constexpr int XCH_STRIDE = 33;                          // floats per exchange row (32 + 1 pad)
+constexpr int XCH_WARP_F = 32 * XCH_STRIDE;             // floats per warp (real and imaginary parts go through in turn)
+constexpr int XCH_BYTES = MEL_WARPS * XCH_WARP_F * 4;   // 67,584
+constexpr int STAGE_FLOATS = 16896;                     // staged sample window: 31 * 512 + 1024 samples (67,584 B)
 
 template <int LOG2NF>
 struct MelCfg {
@@ -143,7 +148,22 @@ struct MelCfg {
     static constexpr int BF = MEL_WARPS * FR;  // frames per batch
     static constexpr int NB = NF / 2 + 1;    // bins
     static constexpr int P_FLOATS = BF * NB;
-    static constexpr size_t SMEM = (size_t)XCH_BYTES + (size_t)P_FLOATS * 4 + (size_t)N2 * 32 * 8 + (size_t)NF * 4;
+    // [exchange | power tile | twiddles | window | staged samples]; the dB tile aliases exchange + power-tile space
+    static constexpr size_t OFF_P = XCH_BYTES;
+    static constexpr size_t OFF_TW = OFF_P + (size_t)P_FLOATS * 4;
+    static constexpr size_t OFF_WIN = OFF_TW + (size_t)N2 * 32 * 8;
+    static constexpr size_t OFF_STAGE = (OFF_WIN + (size_t)NF * 4 + 127) & ~(size_t)127;
+    static constexpr size_t SMEM = OFF_STAGE + (size_t)STAGE_FLOATS * 4;
+};
+
+// One unit of CTA work: a batch of BF consecutive frames of one clip.
+struct MelItem {
+    int clip;
+    int64_t t0;     // first frame of the batch
+    int64_t s0, L, T, f0;
+    bool staged;    // the sample window of this batch comes through the bulk-copy stage
+    int64_t lo;     // first staged sample (clip-relative)
+    uint32_t bytes; // staged bytes
 };
 
 template <int LOG2NF>
@@ -156,200 +176,274 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
       int32_t *__restrict__ bad_flags) {
     using C = MelCfg<LOG2NF>;
     constexpr int NF = C::NF, N2 = C::N2, G = C::G, FR = C::FR, BF = C::BF, NB = C::NB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *xch_all = reinterpret_cast<float2 *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *xch_all = reinterpret_cast<float *>(smem_raw);
     float *dtile = reinterpret_cast<float *>(smem_raw);  // aliases the exchange region (mel stage only)
-    float *ptile = reinterpret_cast<float *>(smem_raw + XCH_BYTES);
-    float2 *s_tw = reinterpret_cast<float2 *>(smem_raw + XCH_BYTES + (size_t)C::P_FLOATS * 4);
-    float *s_win = reinterpret_cast<float *>(smem_raw + XCH_BYTES + (size_t)C::P_FLOATS * 4 + (size_t)N2 * 32 * 8);
+    float *ptile = reinterpret_cast<float *>(smem_raw + C::OFF_P);
+    float2 *s_tw = reinterpret_cast<float2 *>(smem_raw + C::OFF_TW);
+    float *s_win = reinterpret_cast<float *>(smem_raw + C::OFF_WIN);
+    float *s_stage = reinterpret_cast<float *>(smem_raw + C::OFF_STAGE);
     __shared__ float s_red[2][MEL_WARPS];
     __shared__ int s_flag;
+    __shared__ __align__(8) unsigned long long s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < N2 * 32; i += MEL_THREADS) s_tw[i] = g_tw[i];
     for (int i = tid; i < NF; i += MEL_THREADS) s_win[i] = g_win[i];
+    const uint32_t bar = smem_u32(&s_bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    float2 *xch = xch_all + warp * XCH_WARP_F2;
+    float *xch = xch_all + warp * XCH_WARP_F;
     const int dstride = n_mels + 1;
     // pass-2 role of this lane: complex FFT g2, residue k2
     const int g2 = lane / N2, k2 = lane % N2;
     const int partner = g2 * N2 + ((N2 - k2) & (N2 - 1));
+    // staging needs 16-byte aligned windows: base pointer, clip offsets, lengths and hop all multiples of 4 samples
+    const int64_t win_samples = (int64_t)(BF - 1) * hop + NF;
+    const bool can_stage = win_samples <= STAGE_FLOATS && (hop & 3) == 0 && ((uintptr_t)wave & 15) == 0;
 
-    for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
-        const int64_t s0 = sample_offsets ? sample_offsets[clip] : (int64_t)clip * uniform_samples;
-        const int64_t L = sample_offsets ? sample_offsets[clip + 1] - s0 : uniform_samples;
-        const int64_t T = 1 + L / hop;
-        const int64_t f0 = frame_offsets ? frame_offsets[clip] : (int64_t)clip * (1 + uniform_samples / hop);
-        const float *x = wave + s0;
-        float *dst = out + f0 * n_mels;
-        if (L <= NF / 2) {  // torch's reflect pad raises: pad must be smaller than the input
-            if (tid == 0 && bad_flags) bad_flags[clip] = 2;
-            continue;
+    // ---- work-item iterator (every thread evaluates it identically) -------------------------------------------
+    auto load_clip = [&](MelItem &it) -> bool {  // fills the clip fields; false when the grid-stride range is exhausted
+        while (it.clip < B) {
+            it.s0 = sample_offsets ? sample_offsets[it.clip] : (int64_t)it.clip * uniform_samples;
+            it.L = sample_offsets ? sample_offsets[it.clip + 1] - it.s0 : uniform_samples;
+            it.T = 1 + it.L / hop;
+            it.f0 = frame_offsets ? frame_offsets[it.clip] : (int64_t)it.clip * (1 + uniform_samples / hop);
+            if (it.L > NF / 2) return true;
+            // torch's reflect pad raises when the pad is not smaller than the input: flag 2, no output
+            if (tid == 0 && bad_flags) bad_flags[it.clip] = 2;
+            it.clip += gridDim.x;
         }
-        float vmin = INFINITY, vmax = -INFINITY;
-        int nonfinite = 0;
+        return false;
+    };
+    auto set_window = [&](MelItem &it) {
+        const int64_t start = it.t0 * hop - NF / 2;
+        it.lo = start < 0 ? 0 : start;
+        int64_t hi = start + win_samples;
+        if (hi > it.L) hi = it.L;
+        it.staged = can_stage && ((it.s0 | it.L) & 3) == 0 && hi > it.lo;
+        it.bytes = it.staged ? (uint32_t)((hi - it.lo) * 4) : 0u;
+    };
+    auto next_item = [&](const MelItem &cur, MelItem &nx) -> bool {
+        nx = cur;
+        if (cur.t0 + BF < cur.T) {
+            nx.t0 = cur.t0 + BF;
+        } else {
+            nx.clip = cur.clip + gridDim.x;
+            nx.t0 = 0;
+            if (!load_clip(nx)) return false;
+        }
+        set_window(nx);
+        return true;
+    };
+    auto issue_stage = [&](const MelItem &it) {  // one thread: arm the barrier and start the bulk copy
+        if (it.staged) {
+            mbar_expect_tx(bar, it.bytes);
+            bulk_g2s(smem_u32(s_stage), wave + it.s0 + it.lo, it.bytes, bar);
+        }
+    };
 
-        for (int64_t t0 = 0; t0 < T; t0 += BF) {
-            // ------------------------------------------------------------ phase A: FFT -> power tile
-            {
-                float zr[32], zi[32];
-                const int64_t tj = t0 + (int64_t)warp * FR;
+    MelItem cur;
+    cur.clip = blockIdx.x;
+    cur.t0 = 0;
+    bool have = load_clip(cur);
+    if (have) {
+        set_window(cur);
+        if (tid == 0) issue_stage(cur);
+    }
+    uint32_t stage_phase = 0;
+    float vmin = INFINITY, vmax = -INFINITY;
+    int nonfinite = 0;
+
+    while (have) {
+        const float *x = wave + cur.s0;
+        float *dst = out + cur.f0 * n_mels;
+        const int64_t L = cur.L, T = cur.T, t0 = cur.t0;
+        MelItem nxt;
+        const bool have_next = next_item(cur, nxt);
+        if (cur.staged) {
+            mbar_wait(bar, stage_phase);
+            stage_phase ^= 1;
+        }
+        // ------------------------------------------------------------ phase A: FFT -> power tile
+        {
+            float zr[32], zi[32];
+            const int64_t tj = t0 + (int64_t)warp * FR;
 #pragma unroll
-                for (int g = 0; g < G; g++) {
+            for (int g = 0; g < G; g++) {
 #pragma unroll
-                    for (int half = 0; half < 2; half++) {
-                        const int64_t f = tj + 2 * g + half;
-                        float *dstv = half ? zi : zr;
-                        const int64_t start = f * hop - NF / 2;
-                        if (f < T && start >= 0 && start + NF <= L) {
+                for (int half = 0; half < 2; half++) {
+                    const int64_t f = tj + 2 * g + half;
+                    float *dstv = half ? zi : zr;
+                    const int64_t start = f * hop - NF / 2;
+                    if (f < T && start >= 0 && start + NF <= L) {
+                        if (cur.staged) {
+                            const float *sp = s_stage + (start - cur.lo) + lane;
+#pragma unroll
+                            for (int n2 = 0; n2 < N2; n2++) dstv[g * N2 + n2] = sp[32 * n2] * s_win[lane + 32 * n2];
+                        } else {
 #pragma unroll
                             for (int n2 = 0; n2 < N2; n2++)
                                 dstv[g * N2 + n2] = __ldg(x + start + lane + 32 * n2) * s_win[lane + 32 * n2];
-                        } else if (f < T) {
-#pragma unroll
-                            for (int n2 = 0; n2 < N2; n2++)
-                                dstv[g * N2 + n2] =
-                                    __ldg(x + reflect_index(start + lane + 32 * n2, L)) * s_win[lane + 32 * n2];
-                        } else {
-#pragma unroll
-                            for (int n2 = 0; n2 < N2; n2++) dstv[g * N2 + n2] = 0.f;
                         }
+                    } else if (f < T) {
+#pragma unroll
+                        for (int n2 = 0; n2 < N2; n2++)
+                            dstv[g * N2 + n2] =
+                                __ldg(x + reflect_index(start + lane + 32 * n2, L)) * s_win[lane + 32 * n2];
+                    } else {
+#pragma unroll
+                        for (int n2 = 0; n2 < N2; n2++) dstv[g * N2 + n2] = 0.f;
                     }
                 }
-                // pass 1: N2-point FFTs over n2, then twiddle W_NF^(n1*k2), then transpose
+            }
+            // pass 1: N2-point FFTs over n2, then twiddle W_NF^(n1*k2)
 #pragma unroll
-                for (int g = 0; g < G; g++) fft_dif<N2>(zr + g * N2, zi + g * N2);
+            for (int g = 0; g < G; g++) fft_dif<N2>(zr + g * N2, zi + g * N2);
 #pragma unroll
-                for (int g = 0; g < G; g++) {
+            for (int g = 0; g < G; g++) {
 #pragma unroll
-                    for (int p = 0; p < N2; p++) {
-                        const int kk = brev(p, C::LOG2N2);
-                        const float2 w = s_tw[kk * 32 + lane];
-                        const float a = zr[g * N2 + p], b = zi[g * N2 + p];
-                        float2 v;
-                        v.x = fmaf(a, w.x, -(b * w.y));
-                        v.y = fmaf(a, w.y, b * w.x);
-                        xch[(g * N2 + kk) * XCH_STRIDE + lane] = v;
-                    }
+                for (int p = 0; p < N2; p++) {
+                    const int kk = brev(p, C::LOG2N2);
+                    const float2 w = s_tw[kk * 32 + lane];
+                    const float a = zr[g * N2 + p], b = zi[g * N2 + p];
+                    zr[g * N2 + p] = fmaf(a, w.x, -(b * w.y));
+                    zi[g * N2 + p] = fmaf(a, w.y, b * w.x);
                 }
+            }
+            // 32x32 transpose through the warp's exchange tile, real parts then imaginary parts
+#pragma unroll
+            for (int part = 0; part < 2; part++) {
+                float *z = part ? zi : zr;
+#pragma unroll
+                for (int g = 0; g < G; g++)
+#pragma unroll
+                    for (int p = 0; p < N2; p++) xch[(g * N2 + brev(p, C::LOG2N2)) * XCH_STRIDE + lane] = z[g * N2 + p];
                 __syncwarp();
 #pragma unroll
-                for (int n1 = 0; n1 < 32; n1++) {
-                    const float2 v = xch[lane * XCH_STRIDE + n1];
-                    zr[n1] = v.x;
-                    zi[n1] = v.y;
-                }
+                for (int n1 = 0; n1 < 32; n1++) z[n1] = xch[lane * XCH_STRIDE + n1];
                 __syncwarp();
-                // pass 2: 32-point FFT over n1; position p holds k1 = brev5(p); Z[N2*k1 + k2]
-                fft_dif<32>(zr, zi);
-                // separate the two real frames and store |.|^2 (the 1/4 lives in the mel weights)
-                float *pa = ptile + (size_t)(warp * FR + 2 * g2) * NB;
-                float *pb = pa + NB;
+            }
+            // pass 2: 32-point FFT over n1; position p holds k1 = brev5(p); Z[N2*k1 + k2]
+            fft_dif<32>(zr, zi);
+            // separate the two real frames and store |.|^2 (the 1/4 lives in the mel weights)
+            float *pa = ptile + (size_t)(warp * FR + 2 * g2) * NB;
+            float *pb = pa + NB;
 #pragma unroll
-                for (int k1 = 0; k1 < 16; k1++) {
-                    const float Zr = zr[brev(k1, 5)], Zi = zi[brev(k1, 5)];
-                    const float qr = k2 == 0 ? zr[brev((32 - k1) & 31, 5)] : zr[brev(31 - k1, 5)];
-                    const float qi = k2 == 0 ? zi[brev((32 - k1) & 31, 5)] : zi[brev(31 - k1, 5)];
-                    const float pr = __shfl_sync(0xffffffffu, qr, partner);
-                    const float pi = __shfl_sync(0xffffffffu, qi, partner);
-                    const float ar = Zr + pr, ai = Zi - pi, br = Zi + pi, bi = pr - Zr;
-                    pa[N2 * k1 + k2] = fmaf(ar, ar, ai * ai);
-                    pb[N2 * k1 + k2] = fmaf(br, br, bi * bi);
-                }
-                if (k2 == 0) {  // Nyquist bin: Z[NF/2] is its own partner
-                    const float Zr = zr[brev(16, 5)], Zi = zi[brev(16, 5)];
-                    pa[NF / 2] = 4.f * Zr * Zr;
-                    pb[NF / 2] = 4.f * Zi * Zi;
-                }
+            for (int k1 = 0; k1 < 16; k1++) {
+                const float Zr = zr[brev(k1, 5)], Zi = zi[brev(k1, 5)];
+                const float qr = k2 == 0 ? zr[brev((32 - k1) & 31, 5)] : zr[brev(31 - k1, 5)];
+                const float qi = k2 == 0 ? zi[brev((32 - k1) & 31, 5)] : zi[brev(31 - k1, 5)];
+                const float pr = __shfl_sync(0xffffffffu, qr, partner);
+                const float pi = __shfl_sync(0xffffffffu, qi, partner);
+                const float ar = Zr + pr, ai = Zi - pi, br = Zi + pi, bi = pr - Zr;
+                pa[N2 * k1 + k2] = fmaf(ar, ar, ai * ai);
+                pb[N2 * k1 + k2] = fmaf(br, br, bi * bi);
             }
-            __syncthreads();
-            // ------------------------------------------------------------ phase C: sparse mel + dB
-            {
-                constexpr int FG = BF / 32;  // frame groups of 32
-                for (int item = warp; item < FG * n_mels; item += MEL_WARPS) {
-                    const int fg = item % FG, m = item / FG;
-                    const int f = fg * 32 + lane;
-                    const float *prow = ptile + (size_t)f * NB;
-                    const int k0 = fstart[m], cnt = fcnt[m];
-                    const float *w = wt + woff[m];
-                    float acc = 0.f;
-                    for (int i = 0; i < cnt; i++) acc = fmaf(__ldg(w + i), prow[k0 + i], acc);
-                    dtile[f * dstride + m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
-                }
+            if (k2 == 0) {  // Nyquist bin: Z[NF/2] is its own partner
+                const float Zr = zr[brev(16, 5)], Zi = zi[brev(16, 5)];
+                pa[NF / 2] = 4.f * Zr * Zr;
+                pb[NF / 2] = 4.f * Zi * Zi;
             }
-            __syncthreads();
-            // ------------------------------------------------------------ phase D: coalesced write-out
-            {
-                const int64_t nf = min((int64_t)BF, T - t0);
-                const int total = (int)nf * n_mels;
-                float *o = dst + t0 * n_mels;
-                for (int i = tid; i < total; i += MEL_THREADS) {
-                    const int f = i / n_mels, m = i - f * n_mels;
-                    const float v = dtile[f * dstride + m];
-                    vmin = fminf(vmin, v);
-                    vmax = fmaxf(vmax, v);
-                    nonfinite |= !isfinite(v);
-                    o[i] = v;
-                }
-            }
-            __syncthreads();
         }
-
-        // ---------------------------------------------------------------- clip epilogue
-        vmin = warp_min(vmin);
-        vmax = warp_max(vmax);
-        if (lane == 0) s_red[0][warp] = vmin, s_red[1][warp] = vmax;
-        if (tid == 0) s_flag = 0;
         __syncthreads();
-        float mn = s_red[0][0], mx = s_red[1][0];
+        // the staged window has been consumed by every warp: start fetching the next batch's window now, it lands
+        // while this batch goes through the mel projection and the write-out
+        if (tid == 0 && have_next) issue_stage(nxt);
+        // ------------------------------------------------------------ phase C: sparse mel + dB
+        {
+            constexpr int FG = BF / 32;  // frame groups of 32
+            for (int item = warp; item < FG * n_mels; item += MEL_WARPS) {
+                const int fg = item % FG, m = item / FG;
+                const int f = fg * 32 + lane;
+                const float *prow = ptile + (size_t)f * NB;
+                const int k0 = fstart[m], cnt = fcnt[m];
+                const float *w = wt + woff[m];
+                float acc = 0.f;
+                for (int i = 0; i < cnt; i++) acc = fmaf(__ldg(w + i), prow[k0 + i], acc);
+                dtile[f * dstride + m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------------------ phase D: coalesced write-out
+        {
+            const int64_t nf = min((int64_t)BF, T - t0);
+            const int total = (int)nf * n_mels;
+            float *o = dst + t0 * n_mels;
+            for (int i = tid; i < total; i += MEL_THREADS) {
+                const int f = i / n_mels, m = i - f * n_mels;
+                const float v = dtile[f * dstride + m];
+                vmin = fminf(vmin, v);
+                vmax = fmaxf(vmax, v);
+                nonfinite |= !isfinite(v);
+                o[i] = v;
+            }
+        }
+        __syncthreads();
+
+        if (t0 + BF >= T) {
+            // ---------------------------------------------------------------- clip epilogue
+            vmin = warp_min(vmin);
+            vmax = warp_max(vmax);
+            if (lane == 0) s_red[0][warp] = vmin, s_red[1][warp] = vmax;
+            if (tid == 0) s_flag = 0;
+            __syncthreads();
+            float mn = s_red[0][0], mx = s_red[1][0];
 #pragma unroll
-        for (int w = 1; w < MEL_WARPS; w++) mn = fminf(mn, s_red[0][w]), mx = fmaxf(mx, s_red[1][w]);
-        if (normalize || out_l2) {
-            // half-warp per frame row; chunk class g handles elements 4g..4g+3 (+64, +128, ...)
-            const float range = __fsub_rn(mx, mn);
-            const int g = tid & 15, hw = (tid >> 4) & 1;
-            // warp-uniform trip count (both half-warps iterate together: the shuffles below need all 32 lanes)
-            for (int64_t r0 = (int64_t)(tid >> 5) * 2; r0 < T; r0 += MEL_THREADS / 16) {
-                const int64_t r = r0 + hw;
-                const bool live = r < T;
-                float *row = dst + (live ? r : 0) * n_mels;
-                float q = 0.f;
-                if (live) {
-                    for (int base = 4 * g; base < n_mels; base += 64) {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            if (base + e < n_mels) {
-                                float v = __ldcg(row + base + e);
-                                if (normalize) {
-                                    v = __fdiv_rn(__fsub_rn(v, mn), range);
-                                    nonfinite |= !isfinite(v);
-                                    row[base + e] = v;
-                                }
-                                q = fmaf(v, v, q);
-                            }
-                        }
-                    }
-                }
-                if (out_l2) {
-                    const float den = l2_denominator(half16_sum(q));
+            for (int w = 1; w < MEL_WARPS; w++) mn = fminf(mn, s_red[0][w]), mx = fmaxf(mx, s_red[1][w]);
+            if (normalize || out_l2) {
+                // half-warp per frame row; chunk class g handles elements 4g..4g+3 (+64, +128, ...)
+                const float range = __fsub_rn(mx, mn);
+                const int g = tid & 15, hw = (tid >> 4) & 1;
+                // warp-uniform trip count (both half-warps iterate together: the shuffles below need all 32 lanes)
+                for (int64_t r0 = (int64_t)(tid >> 5) * 2; r0 < T; r0 += MEL_THREADS / 16) {
+                    const int64_t r = r0 + hw;
+                    const bool live = r < T;
+                    float *row = dst + (live ? r : 0) * n_mels;
+                    float q = 0.f;
                     if (live) {
-                        float *orow = out_l2 + (f0 + r) * n_mels;
                         for (int base = 4 * g; base < n_mels; base += 64) {
 #pragma unroll
                             for (int e = 0; e < 4; e++) {
-                                // final value of the row (this thread wrote it just above when normalising)
-                                if (base + e < n_mels) orow[base + e] = __fdiv_rn(__ldcg(row + base + e), den);
+                                if (base + e < n_mels) {
+                                    float v = __ldcg(row + base + e);
+                                    if (normalize) {
+                                        v = __fdiv_rn(__fsub_rn(v, mn), range);
+                                        nonfinite |= !isfinite(v);
+                                        row[base + e] = v;
+                                    }
+                                    q = fmaf(v, v, q);
+                                }
+                            }
+                        }
+                    }
+                    if (out_l2) {
+                        const float den = l2_denominator(half16_sum(q));
+                        if (live) {
+                            float *orow = out_l2 + (cur.f0 + r) * n_mels;
+                            for (int base = 4 * g; base < n_mels; base += 64) {
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    // final value of the row (this thread wrote it just above when normalising)
+                                    if (base + e < n_mels) orow[base + e] = __fdiv_rn(__ldcg(row + base + e), den);
+                                }
                             }
                         }
                     }
                 }
             }
+            if (nonfinite) s_flag = 1;
+            __syncthreads();
+            if (tid == 0 && bad_flags) bad_flags[cur.clip] = s_flag;
+            __syncthreads();
+            vmin = INFINITY, vmax = -INFINITY, nonfinite = 0;
         }
-        if (nonfinite) s_flag = 1;
-        __syncthreads();
-        if (tid == 0 && bad_flags) bad_flags[clip] = s_flag;
-        __syncthreads();
+        cur = nxt;
+        have = have_next;
     }
 }
 
@@ -452,8 +546,10 @@ int at_mel_plan_create(int sample_rate, int n_fft, int hop_length, int n_mels, i
         set_error("at_mel_plan_create: n_fft=%d is not covered (256, 512, 1024 are)", n_fft);
         return AT_ERR_UNSUPPORTED;
     }
-    if (n_mels > 256) {
-        set_error("at_mel_plan_create: n_mels=%d > 256 is not covered", n_mels);
+    // the dB tile of one batch (16 * 2048 / n_fft frames x (n_mels + 1) floats) must fit the 67,584-byte exchange area
+    const int max_mels = 67584 / (4 * (16 * 2048 / n_fft)) - 1 < 256 ? 67584 / (4 * (16 * 2048 / n_fft)) - 1 : 256;
+    if (n_mels > max_mels) {
+        set_error("at_mel_plan_create: n_mels=%d > %d is not covered for n_fft=%d", n_mels, max_mels, n_fft);
         return AT_ERR_UNSUPPORTED;
     }
     int dev;
