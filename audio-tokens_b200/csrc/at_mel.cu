@@ -39,7 +39,9 @@ struct at_mel_plan {
     int *fstart = nullptr;    // n_mels: first bin of each filter's support
     int *fcnt = nullptr;      // n_mels: bins in the support
     int *woff = nullptr;      // n_mels: offset into wt
-    float *wt = nullptr;      // concatenated non-zero weights, pre-scaled by 1/4
+    float *wt = nullptr;      // concatenated weights of each filter's support, pre-scaled by 1/4, each filter padded
+                              // with zeros to a multiple of 4 entries (16-byte aligned segments)
+    int wt_count = 0;         // floats in wt
     // host copies
     std::vector<float> h_win, h_fb;
     // staging for the _host entry point
@@ -137,6 +139,7 @@ constexpr int XCH_STRIDE = 33;                          // floats per exchange r
 constexpr int XCH_WARP_F = 32 * XCH_STRIDE;             // floats per warp (real and imaginary parts go through in turn)
 constexpr int XCH_BYTES = MEL_WARPS * XCH_WARP_F * 4;   // 67,584
 constexpr int STAGE_FLOATS = 16896;                     // staged sample window: 31 * 512 + 1024 samples (67,584 B)
+constexpr int WT_SMEM_FLOATS = 2048;                    // filterbank weights kept in shared memory when they fit
 
 template <int LOG2NF>
 struct MelCfg {
@@ -153,7 +156,8 @@ struct MelCfg {
     static constexpr size_t OFF_TW = OFF_P + (size_t)P_FLOATS * 4;
     static constexpr size_t OFF_WIN = OFF_TW + (size_t)N2 * 32 * 8;
     static constexpr size_t OFF_STAGE = (OFF_WIN + (size_t)NF * 4 + 127) & ~(size_t)127;
-    static constexpr size_t SMEM = OFF_STAGE + (size_t)STAGE_FLOATS * 4;
+    static constexpr size_t OFF_WT = OFF_STAGE + (size_t)STAGE_FLOATS * 4;
+    static constexpr size_t SMEM = OFF_WT + (size_t)WT_SMEM_FLOATS * 4;
 };
 
 // One unit of CTA work: a batch of BF consecutive frames of one clip.
@@ -172,7 +176,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
       const int64_t *__restrict__ frame_offsets, int64_t uniform_samples, int B, int hop, int n_mels,
       int normalize, const float *__restrict__ g_win, const float2 *__restrict__ g_tw,
       const int *__restrict__ fstart, const int *__restrict__ fcnt, const int *__restrict__ woff,
-      const float *__restrict__ wt, float *__restrict__ out, float *__restrict__ out_l2,
+      const float *__restrict__ wt, int wt_count, float *__restrict__ out, float *__restrict__ out_l2,
       int32_t *__restrict__ bad_flags) {
     using C = MelCfg<LOG2NF>;
     constexpr int NF = C::NF, N2 = C::N2, G = C::G, FR = C::FR, BF = C::BF, NB = C::NB;
@@ -183,6 +187,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw + C::OFF_TW);
     float *s_win = reinterpret_cast<float *>(smem_raw + C::OFF_WIN);
     float *s_stage = reinterpret_cast<float *>(smem_raw + C::OFF_STAGE);
+    float *s_wt = reinterpret_cast<float *>(smem_raw + C::OFF_WT);
     __shared__ float s_red[2][MEL_WARPS];
     __shared__ int s_flag;
     __shared__ __align__(8) unsigned long long s_bar;
@@ -190,6 +195,9 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < N2 * 32; i += MEL_THREADS) s_tw[i] = g_tw[i];
     for (int i = tid; i < NF; i += MEL_THREADS) s_win[i] = g_win[i];
+    const bool wt_in_smem = wt_count <= WT_SMEM_FLOATS;
+    if (wt_in_smem)
+        for (int i = tid; i < wt_count; i += MEL_THREADS) s_wt[i] = wt[i];
     const uint32_t bar = smem_u32(&s_bar);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -198,7 +206,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
     __syncthreads();
 
     float *xch = xch_all + warp * XCH_WARP_F;
-    const int dstride = n_mels + 1;
+    const int dstride = n_mels + 4;  // rows stay 16-byte aligned for the vector write-out
     // pass-2 role of this lane: complex FFT g2, residue k2
     const int g2 = lane / N2, k2 = lane % N2;
     const int partner = g2 * N2 + ((N2 - k2) & (N2 - 1));
@@ -360,27 +368,52 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
             for (int item = warp; item < FG * n_mels; item += MEL_WARPS) {
                 const int fg = item % FG, m = item / FG;
                 const int f = fg * 32 + lane;
-                const float *prow = ptile + (size_t)f * NB;
-                const int k0 = fstart[m], cnt = fcnt[m];
-                const float *w = wt + woff[m];
+                const float *prow = ptile + (size_t)f * NB + fstart[m];
+                const int cnt4 = fcnt[m];
                 float acc = 0.f;
-                for (int i = 0; i < cnt; i++) acc = fmaf(__ldg(w + i), prow[k0 + i], acc);
+                if (wt_in_smem) {
+                    const float4 *w4 = reinterpret_cast<const float4 *>(s_wt + woff[m]);
+#pragma unroll 2
+                    for (int i = 0; i < cnt4; i++) {
+                        const float4 w = w4[i];  // broadcast: every lane reads the same filter segment
+                        acc = fmaf(w.x, prow[4 * i], acc);
+                        acc = fmaf(w.y, prow[4 * i + 1], acc);
+                        acc = fmaf(w.z, prow[4 * i + 2], acc);
+                        acc = fmaf(w.w, prow[4 * i + 3], acc);
+                    }
+                } else {
+                    const float *w = wt + woff[m];
+                    for (int i = 0; i < 4 * cnt4; i++) acc = fmaf(__ldg(w + i), prow[i], acc);
+                }
                 dtile[f * dstride + m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
             }
         }
         __syncthreads();
         // ------------------------------------------------------------ phase D: coalesced write-out
         {
-            const int64_t nf = min((int64_t)BF, T - t0);
-            const int total = (int)nf * n_mels;
+            const int nf = (int)min((int64_t)BF, T - t0);
             float *o = dst + t0 * n_mels;
-            for (int i = tid; i < total; i += MEL_THREADS) {
-                const int f = i / n_mels, m = i - f * n_mels;
-                const float v = dtile[f * dstride + m];
-                vmin = fminf(vmin, v);
-                vmax = fmaxf(vmax, v);
-                nonfinite |= !isfinite(v);
-                o[i] = v;
+            if ((n_mels & 3) == 0) {
+                const int q4 = n_mels >> 2;  // float4 per frame; a warp takes whole frames (no integer division)
+                for (int f = warp; f < nf; f += MEL_WARPS) {
+                    for (int j = lane; j < q4; j += 32) {
+                        const float4 v = *reinterpret_cast<const float4 *>(dtile + f * dstride + 4 * j);
+                        vmin = fminf(fminf(vmin, v.x), fminf(fminf(v.y, v.z), v.w));
+                        vmax = fmaxf(fmaxf(vmax, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+                        nonfinite |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+                        *reinterpret_cast<float4 *>(o + (size_t)f * n_mels + 4 * j) = v;
+                    }
+                }
+            } else {
+                for (int f = warp; f < nf; f += MEL_WARPS) {
+                    for (int m = lane; m < n_mels; m += 32) {
+                        const float v = dtile[f * dstride + m];
+                        vmin = fminf(vmin, v);
+                        vmax = fmaxf(vmax, v);
+                        nonfinite |= !isfinite(v);
+                        o[(size_t)f * n_mels + m] = v;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -398,13 +431,53 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
             if (normalize || out_l2) {
                 // half-warp per frame row; chunk class g handles elements 4g..4g+3 (+64, +128, ...)
                 const float range = __fsub_rn(mx, mn);
+                const float inv_range = __fdiv_rn(1.0f, range);  // range == 0 -> inf -> 0 * inf = NaN like the reference's 0/0
                 const int g = tid & 15, hw = (tid >> 4) & 1;
+                const bool vec = (n_mels & 3) == 0 && n_mels <= 256;
                 // warp-uniform trip count (both half-warps iterate together: the shuffles below need all 32 lanes)
                 for (int64_t r0 = (int64_t)(tid >> 5) * 2; r0 < T; r0 += MEL_THREADS / 16) {
                     const int64_t r = r0 + hw;
                     const bool live = r < T;
                     float *row = dst + (live ? r : 0) * n_mels;
                     float q = 0.f;
+                    if (vec) {
+                        float4 v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int base = 4 * g + 64 * j;
+                            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live && base < n_mels) v[j] = __ldcg(reinterpret_cast<const float4 *>(row + base));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int base = 4 * g + 64 * j;
+                            if (live && base < n_mels) {
+                                if (normalize) {
+                                    v[j].x = __fmul_rn(__fsub_rn(v[j].x, mn), inv_range);
+                                    v[j].y = __fmul_rn(__fsub_rn(v[j].y, mn), inv_range);
+                                    v[j].z = __fmul_rn(__fsub_rn(v[j].z, mn), inv_range);
+                                    v[j].w = __fmul_rn(__fsub_rn(v[j].w, mn), inv_range);
+                                    nonfinite |= !(isfinite(v[j].x) && isfinite(v[j].y) && isfinite(v[j].z) && isfinite(v[j].w));
+                                    *reinterpret_cast<float4 *>(row + base) = v[j];
+                                }
+                                q = fmaf(v[j].x, v[j].x, q), q = fmaf(v[j].y, v[j].y, q);
+                                q = fmaf(v[j].z, v[j].z, q), q = fmaf(v[j].w, v[j].w, q);
+                            }
+                        }
+                        if (out_l2) {
+                            const float den = l2_denominator(half16_sum(q));
+                            float *orow = out_l2 + (cur.f0 + (live ? r : 0)) * n_mels;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int base = 4 * g + 64 * j;
+                                if (live && base < n_mels)
+                                    *reinterpret_cast<float4 *>(orow + base) =
+                                        make_float4(__fdiv_rn(v[j].x, den), __fdiv_rn(v[j].y, den), __fdiv_rn(v[j].z, den),
+                                                    __fdiv_rn(v[j].w, den));
+                            }
+                        }
+                        continue;
+                    }
                     if (live) {
                         for (int base = 4 * g; base < n_mels; base += 64) {
 #pragma unroll
@@ -412,7 +485,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                                 if (base + e < n_mels) {
                                     float v = __ldcg(row + base + e);
                                     if (normalize) {
-                                        v = __fdiv_rn(__fsub_rn(v, mn), range);
+                                        v = __fmul_rn(__fsub_rn(v, mn), inv_range);
                                         nonfinite |= !isfinite(v);
                                         row[base + e] = v;
                                     }
@@ -487,8 +560,11 @@ static int upload_constants(at_mel_plan *p) {
         fcnt[m] = hi < 0 ? 0 : hi - lo + 1;
         woff[m] = (int)wt.size();
         for (int k = fstart[m]; k < fstart[m] + fcnt[m]; k++) wt.push_back(0.25f * p->h_fb[(size_t)k * nm + m]);
+        while (wt.size() % 4) wt.push_back(0.f);
+        fcnt[m] = (fcnt[m] + 3) / 4;  // in groups of four bins
     }
-    if (wt.empty()) wt.push_back(0.f);
+    if (wt.empty()) wt.assign(4, 0.f);
+    p->wt_count = (int)wt.size();
     std::vector<float2> tw((size_t)n2 * 32);
     for (int kk = 0; kk < n2; kk++)
         for (int n1 = 0; n1 < 32; n1++) {
@@ -528,7 +604,8 @@ static int launch_mel(at_mel_plan *p, const float *wave, const int64_t *so, cons
     if (grid < 1) grid = 1;
     ProfScope prof(PROF_MEL, st);
     k_mel<LOG2NF><<<grid, MEL_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->win,
-                                                     p->tw, p->fstart, p->fcnt, p->woff, p->wt, out, out_l2, bad);
+                                                     p->tw, p->fstart, p->fcnt, p->woff, p->wt, p->wt_count, out, out_l2,
+                                                     bad);
     AT_LAUNCH_OK();
     return AT_OK;
 }
@@ -547,7 +624,7 @@ int at_mel_plan_create(int sample_rate, int n_fft, int hop_length, int n_mels, i
         return AT_ERR_UNSUPPORTED;
     }
     // the dB tile of one batch (16 * 2048 / n_fft frames x (n_mels + 1) floats) must fit the 67,584-byte exchange area
-    const int max_mels = 67584 / (4 * (16 * 2048 / n_fft)) - 1 < 256 ? 67584 / (4 * (16 * 2048 / n_fft)) - 1 : 256;
+    const int max_mels = 67584 / (4 * (16 * 2048 / n_fft)) - 4 < 256 ? 67584 / (4 * (16 * 2048 / n_fft)) - 4 : 256;
     if (n_mels > max_mels) {
         set_error("at_mel_plan_create: n_mels=%d > %d is not covered for n_fft=%d", n_mels, max_mels, n_fft);
         return AT_ERR_UNSUPPORTED;

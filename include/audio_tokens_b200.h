@@ -66,7 +66,7 @@ typedef struct at_mel_plan at_mel_plan;
 
 /* MelSpectrogram(sample_rate, n_mels, n_fft, hop_length) + AmplitudeToDB() with torchaudio defaults:
  * periodic Hann (win_length = n_fft), center + reflect pad, power 2, HTK filterbank, f_min 0,
- * f_max sample_rate/2, norm None, 10*log10(max(x,1e-10)).  n_fft in {256, 512, 1024}; n_mels <= 256 (<= 131 for
+ * f_max sample_rate/2, norm None, 10*log10(max(x,1e-10)).  n_fft in {256, 512, 1024}; n_mels <= 256 (<= 128 for
  * n_fft 256).
  * normalize != 0 applies (s - min s) / (max s - min s) over each clip (normalize_spectrogram). */
 int at_mel_plan_create(int sample_rate, int n_fft, int hop_length, int n_mels, int normalize, at_mel_plan **plan);
