@@ -1,0 +1,142 @@
+"""The drop-in stage classes on a small synthetic tree: run() x 3 with the reference's file contract, compared with the
+oracle (reference torchaudio calls + FAISS restatement) stage by stage."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SR, L = 22050, 22050 * 3
+
+
+def _config(tmp_path, **over):
+    from audio_tokens_config import AudioTokensConfig
+
+    cfg = AudioTokensConfig()
+    cfg.split_file = str(tmp_path / "split.json")
+    cfg.dest_spec_path = tmp_path / "spectrograms"
+    cfg.source_spec_path = tmp_path / "spectrograms"
+    cfg.centroids_path = tmp_path / "output" / "centroids.npy"
+    cfg.dest_tokenized_path = str(tmp_path / "tokenized_audio")
+    cfg.n_fft, cfg.hop_length, cfg.normalize = 1024, 512, True
+    cfg.vocab_size, cfg.niter = 32, 6
+    cfg.spectrogram_batch_size = 7   # several batches
+    cfg.clustering_batch_size = 10000
+    cfg.tokenizer_batch_size = 9
+    cfg.sort_files = True            # deterministic file order for the comparison (the reference globs unsorted)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    (tmp_path / "output").mkdir(exist_ok=True)
+    ytids = [f"clip{i:04d}" for i in range(24)]
+    json.dump({"train": ytids[:20], "validation": ytids[20:]}, open(cfg.split_file, "w"))
+    return cfg, ytids
+
+
+def _wave(ytid):
+    import torch
+    from oracle import synth_ref
+
+    idx = int(ytid[4:])
+    if idx == 3:
+        return torch.zeros(1, L)          # silent clip: NaN after min-max -> dropped like the reference does
+    return torch.from_numpy(synth_ref.make_clip(4242, idx, L if idx % 5 else L - 777)).reshape(1, -1)
+
+
+def test_three_stages_run_with_the_reference_file_contract(tmp_path, monkeypatch):
+    import torch
+    from oracle import faiss_ref, mel_ref
+    from processors.cluster_creator import ClusterCreator
+    from processors.spec_tokenizer import SpecTokenizer
+    from processors.spectrogram_generator import SpectrogramGenerator
+
+    cfg, ytids = _config(tmp_path)
+    gen = SpectrogramGenerator(cfg)
+    monkeypatch.setattr(gen, "find_audio_file", lambda y: None if y == "clip0005" else f"/audio/{y}.flac")
+    monkeypatch.setattr(gen, "preprocess_waveform", lambda p: _wave(os.path.basename(p)[:-5]).cuda())
+    gen.run()
+
+    # ---- stage 1 files
+    train_files = sorted((tmp_path / "spectrograms" / "train").glob("*.npy"))
+    names = [f.stem for f in train_files]
+    assert "clip0003" not in names and "clip0005" not in names and len(names) == 18   # silent + missing are skipped
+    assert len(list((tmp_path / "spectrograms" / "validation").glob("*.npy"))) == 4
+    for f in train_files[:6]:
+        with open(f, "rb") as fh:
+            header = fh.read(128)
+        assert b"'fortran_order': True" in header and b"'descr': '<f4'" in header
+        s = np.load(f)
+        w = _wave(f.stem)[0].numpy()
+        assert s.shape == (64, 1 + len(w) // 512) and s.dtype == np.float32
+        ref = mel_ref.mel_db_torchaudio(w, SR, 1024, 512, 64, True)
+        assert np.abs(s - ref).max() <= 1e-4
+    # public helpers keep their meaning
+    one = gen.generate_mel_spectrogram(_wave("clip0001").cuda())
+    ref_db = mel_ref.mel_db_torchaudio(_wave("clip0001")[0].numpy(), SR, 1024, 512, 64, False)
+    assert tuple(one.shape) == ref_db.shape
+    assert np.abs(one.cpu().numpy() - ref_db).max() <= 1e-4 * (ref_db.max() - ref_db.min())
+    assert gen.check_for_nan_inf(gen.normalize_spectrogram(gen.generate_mel_spectrogram(torch.zeros(1, 4096).cuda())))
+
+    # ---- stage 2
+    ClusterCreator(cfg).run()
+    cents = np.load(cfg.centroids_path)
+    assert cents.shape == (32, 64) and cents.dtype == np.float32 and not np.isfortran(cents)
+    np.testing.assert_allclose(np.linalg.norm(cents, axis=1), 1.0, rtol=1e-5)
+    x = np.concatenate([np.load(f).T for f in train_files], axis=0).astype(np.float32)
+    km = faiss_ref.Kmeans(64, 32, niter=6)
+    km.exact_search = True
+    km.train(mel_ref.normalize_rows(x))
+    ref_c = mel_ref.normalize_rows(km.centroids)
+    rel = np.linalg.norm(cents - ref_c, axis=1) / np.linalg.norm(ref_c, axis=1)
+    print("centroids within 1e-4 of the oracle's:", float((rel <= 1e-4).mean()))
+    assert (rel <= 1e-4).mean() >= 0.9
+
+    # ---- stage 3
+    tok = SpecTokenizer(cfg)
+    tok.run()
+    ix = faiss_ref.IndexFlatL2(64)
+    ix.add(cents)
+    total = 0
+    for split in ("train", "validation"):
+        for f in sorted((tmp_path / "spectrograms" / split).glob("*.npy")):
+            t = np.load(tmp_path / "tokenized_audio" / split / f"{f.stem}.npy")
+            s = np.load(f).T.astype(np.float32)
+            assert t.dtype == np.int64 and t.shape == (s.shape[0],)
+            xn = mel_ref.normalize_rows(s)
+            lab, d1, d2 = faiss_ref.assign_l2_scalar(xn, cents)
+            mism = t != lab
+            gap = (d2 - d1) / np.maximum(d1, 1e-30)
+            assert (gap[mism] < 1e-4).all()
+            total += len(t)
+    assert tok.token_counts is not None and int(tok.token_counts.sum()) == sum(
+        len(np.load(f)) for f in (tmp_path / "tokenized_audio" / "train").glob("*.npy"))
+    assert total > 0
+
+
+def test_hot_path_in_hbm_matches_the_staged_classes(tmp_path):
+    """HotPath (no files) == mel -> Kmeans(all rows) -> tokens computed piecewise with the same operators."""
+    import torch
+    from at_b200 import FlatL2, Kmeans, MelPlan, row_l2norm, synth_clips
+    from at_b200.pipeline import HotPath
+
+    B, K = 30, 64
+    wave = synth_clips(4242, 0, B, L)
+    hp = HotPath(SR, 1024, 512, 64, True, vocab_size=K, niter=5)
+    tok, cents, bad = hp.run_device(wave)
+    assert int(bad.sum()) == 0 and tok.dtype == torch.int64
+    spec, _, l2 = MelPlan(SR, 1024, 512, 64, True).forward(wave, want_l2=True)
+    km = Kmeans(64, K, niter=5, max_points_per_centroid=10 ** 9)
+    km.train(l2.reshape(-1, 64))
+    c2 = row_l2norm(km.centroids_device())
+    assert torch.equal(c2, cents)
+    ix = FlatL2(64)
+    ix.set_centroids(c2)
+    t2, _ = ix.search(spec.reshape(-1, 64), l2norm_rows=True, labels_dtype=torch.int64)
+    assert torch.equal(t2, tok)
+    # host entry point gives the same tokens
+    hb = hp.alloc_bufs(B, L, host=True, chunk_clips=8)
+    wh = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+    wh.copy_(wave)
+    th, ch, bh = hp.run_host(wh, hb, chunk_clips=8)
+    assert torch.equal(th.cuda(), tok) and torch.equal(ch.cuda(), cents)
