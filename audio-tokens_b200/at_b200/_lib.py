@@ -37,6 +37,7 @@ PROTOTYPES = {
     "at_index_ntotal": (c_int, [c_ptr]),
     "at_index_set_tc_mode": (c_int, [c_ptr, c_int]),
     "at_index_centroids": (c_ptr, [c_ptr]),
+    "at_index_tc_stats": (c_int, [c_ptr, c_ptr]),
     "at_index_search": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "at_kmeans_create": (c_int, [c_int, c_int, c_ptr]),
     "at_kmeans_destroy": (c_int, [c_ptr]),

@@ -30,8 +30,14 @@ class FlatL2:
             pass
 
     def set_tc_mode(self, mode: int):
-        """0 auto, 1 stream centroid tiles, 2 resident / K-sliced (at_index_set_tc_mode)."""
+        """0 auto (resident when the tiles fit), 1 always stream centroid tiles (at_index_set_tc_mode)."""
         _lib.check(self.lib.at_index_set_tc_mode(self.h, int(mode)))
+
+    def tc_stats(self):
+        """(rows decided by the fp32 re-check, rows scanned exactly) of the tcgen05 kernel so far (at_index_tc_stats)."""
+        out = (ctypes.c_uint64 * 2)()
+        _lib.check(self.lib.at_index_tc_stats(self.h, out))
+        return int(out[0]), int(out[1])
 
     def set_centroids(self, c):
         import torch

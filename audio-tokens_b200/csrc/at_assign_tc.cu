@@ -3,96 +3,140 @@
 // Replaces the blocked sgemm + top-1 scan of faiss::exhaustive_L2sqr_blas (reached from
 // processors/spec_tokenizer.py:77 and, inside faiss.Kmeans.train, processors/cluster_creator.py:54-56).
 //
-// Arithmetic.  The tensor core evaluates, for a tile of 128 rows x 128 centroids,
-//     acc = S^2 * ( |x|^2 + |c|^2 - 2 <x, c> )
-// in ONE chain of 13 tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
-//     x_hi * c_hi  +  x_hi * c_lo  +  x_lo * c_hi          (fp16 hi/lo split of S*x and -2*S*c: ~22 mantissa bits)
-//   + [xn pieces | 2^12 2^12 2^12] * [2^12 2^12 2^12 | cn pieces]   (one extra K=16 step carrying both norms)
-// so the epilogue only scans packed (distance | column) keys.  The ALU pipe (FMNMX, LOP3: one warp instruction per two
-// cycles per scheduler) bounds that scan, so it keeps the top-2 over minima of groups of four adjacent columns
-// (1.8 ALU ops per score) instead of an exact per-column top-2 (3.5, measured ALU-bound at 2.1x the MMA time).  The
-// two candidates are re-evaluated by separate warps with the library's canonical fp32 formula (at_index.cuh) -- the
-// one the exact SIMT kernel uses -- and the smaller wins (lowest index on exact ties).
-// A row whose runner-up is safely behind the winner (gap above a bound on the split-fp16 error) skips the re-check: its
-// label is final and its distance is the accumulator value / S^2 (agrees with the canonical fp32 value to ~2e-5
-// relative, 1e-6 absolute for unit-norm data).  All other rows get the exact canonical distance.
-// Tie note: token ids agree with the fp32 path except when (a) three or more centroids lie within ~1e-7 (absolute,
-// unit-norm data) of the minimum, or (b) the runner-up shares the winner's group of four AND lies within ~1e-7 of it
-// (the group hides it from the re-check); both are ties below what the fp32 formula itself resolves.
+// Three kernels:
+//   k_tc_rows    rows (fp32) -> optional L2 normalisation -> the fp16 operand image of the rows, laid out exactly as the
+//                tensor core reads it (128-row tiles: 128x64 K-major SWIZZLE_128B + a 128x16 tile carrying |x|^2), plus
+//                per row the norm of the fp16 rounding error |delta| and |x|^2.  K-means builds it ONCE per training set
+//                and re-uses it for every Lloyd iteration (the rows do not change); a one-off search builds it per call.
+//   k_assign_tc  distances + scan (below).  Certifies almost every row from the accumulators.
+//   k_tc_tail    the uncertified rows (a compacted list, ~1-2 %): canonical fp32 re-evaluation of the candidate
+//                columns -- or of every centroid -- by one warp per row.
 //
-// Roofline note: 2*N*K*64 algorithmic flops are executed as 3.25x that many fp16 MMA flops.
+// Arithmetic.  For a tile of 128 rows x 128 centroids the tensor core evaluates, in ONE chain of 9 tcgen05.mma
+// (kind::f16, fp32 accumulate in TMEM),
+//     acc = BIAS + P * ( |x|^2 + |c|^2 - 2 <x~, c> )          P = S^2 a power of two chosen from max |c|
+//   = x~ * c_hi  +  x~ * c_lo                       (x~ = fp16(Sx x); c_hi + c_lo = fp16 hi/lo split of -2 (P/Sx) c, ~22 bits)
+//   + [xn pieces | 2^12 2^12 2^12] * [w w w | cn pieces]              (one extra K=16 step: both norms and the bias)
+// The only first-order error is the rounding of the ROW: acc_j - P d_j = 2 P <x - x~/Sx, c_j>, the same vector
+// delta = x - x~/Sx for every centroid, so for two candidates j, j' the error of the DIFFERENCE is bounded by
+// 2 |delta| |c_j - c_j'| <= 2 |delta| (sqrt d_j + sqrt d_j') -- small exactly when the two are close competitors.
 //
-// Two modes share one kernel:
-//   RESIDENT  (K <= 512 per CTA): the CTA's centroid operand tiles (36 KB each, pre-swizzled by k_tc_prep) are loaded
-//             into shared memory once and stay there; for K <= 2048 the centroids are cut into S = ceil(tiles/4)
-//             slices, CTA b serves slice b % S, and a small merge kernel takes the minimum over slices.  No operand
-//             re-streaming from L2 (at K = 1024 the streaming mode moved 22 GB per launch through L2).
-//   STREAM    (any K): operand tiles are streamed through a 4-slot ring with cp.async.bulk.
+// BIAS = 2^14 puts every accumulator into the binades [2^13, 2^17): the low 25 bits of its fp32 pattern are then a
+// monotone fixed-point image of the distance, and  key = pattern * 128 + column  (ONE IMAD, fma pipe) is an unsigned
+// integer whose order is the order of the distances with the column riding in the low 7 bits.  Measured pipe rates
+// (tools/ubench_pipes.cu): VIMNMX / VIMNMX3 / LOP3 one warp instruction per 2 cycles per scheduler (alu pipe), IMAD
+// one per 2 cycles on the fma pipe, concurrently.  The scan keeps TWO orthogonal groupings of a tile's 128 columns:
+//     A: 16 groups of 8 adjacent columns   -> exact running top-3 over the group minima
+//     B: 8 groups of 16 columns = position mod 8  -> exact running top-2 over the group minima
+// = 1.0 fma-pipe + 1.66 alu-pipe instructions per score.  Two columns never share both an A and a B group, so the
+// second smallest COLUMN of a row is exactly min(second A minimum, second B minimum): a runner-up can hide behind the
+// winner in one grouping, never in both.
 //
-// Structure: persistent CTAs (one per SM), 16 warps:
-//   warp 1  lane 0   issues tcgen05.mma, commits to mbarriers
-//   warp 2           TMEM allocation / deallocation
-//   warp 3  lane 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into shared memory
-//   warps 4-7        read the fp32 row tile (coalesced 128-bit loads), optional row L2 normalisation, |x|^2, fp16 hi/lo
-//                    split written straight into the SWIZZLE_128B K-major layout the MMA descriptors expect
-//   warps 8-11       epilogue: tcgen05.ld the accumulator, packed keys, group minima, top-2 -> two candidate columns
-//   warps 12-15      fp32 re-check of the candidates (off the MMA critical path), labels / distances out
+// Certification (per row, accumulator units; tau from the measured |delta|):
+//   second smallest column further than tau from the best -> the best column is the argmin: label final.
+// Otherwise the row goes to the tail list with the columns of the best and second-best A group minima; the tail kernel
+// re-evaluates those two groups (16 columns) with the library's canonical fp32 formula (at_index.cuh, the one the exact
+// SIMT kernel uses) -- every other column is at least the third A minimum, which must be further than tau; if it is
+// not, or the row is outside the fp16 / accumulator range, the tail kernel scans all centroids exactly.
+// Labels therefore equal the exact fp32 kernel's except ties below what the fp32 formula itself resolves.
+// Distances: canonical fp32 for tail rows, accumulator read-out (|error| <= 2 |delta| |c|) for certified rows;
+// at_index_search re-evaluates them exactly in a second pass when the caller asks for distances.
+//
+// Roofline note: 2*N*K*64 algorithmic flops are executed as 2.25x that many fp16 MMA flops.
+//
+// k_assign_tc: persistent CTAs (one per SM), 12 warps; the unit of work is a SUPER TILE of 256 rows (two 128-row MMA
+// tiles) so every centroid operand tile fetched from L2 is used twice:
+//   warp 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into a 3-slot ring (or once, when all
+//            tiles fit: RESIDENT)
+//   warp 1   issues tcgen05.mma, commits to mbarriers
+//   warp 2   TMEM allocation / deallocation (all 512 columns: 2 row tiles x 2 accumulator stages)
+//   warp 3   bulk-copies the row operand image, one 40 KB super tile at a time, double-buffered
+//   warps 4-11  epilogue: warps 4-7 scan row tile 0, warps 8-11 row tile 1 (tcgen05.ld -> keys -> top-3 / top-2)
+// Producer, MMA and row-image warps run their loops converged and issue from one elected lane (uniform operands).
 #include "at_index.cuh"
 #include "at_ptx.cuh"
 
 namespace at {
 
-constexpr int TC_THREADS = 512;
-constexpr int TM = 128;          // rows per tile (UMMA M)
+constexpr int TC_THREADS = 384;
+constexpr int TM = 128;          // rows per MMA tile (UMMA M)
 constexpr int TN = 128;          // centroids per tile (UMMA N)
-constexpr int B_SLOTS = 4;       // operand tiles resident per CTA / ring depth
+constexpr int RT = 2;            // row tiles per super tile
+constexpr int SROWS = RT * TM;   // 256
+constexpr int B_SLOTS = 3;       // operand tiles resident per CTA / ring depth
 constexpr uint32_t A_MAIN_BYTES = TM * 128;              // 128 rows x 64 fp16
 constexpr uint32_t AUG_BYTES = TM * 32;                  // 128 rows x 16 fp16, no-swizzle core matrices
-constexpr uint32_t A_BUF_BYTES = 2 * A_MAIN_BYTES + AUG_BYTES;   // hi | lo | aug = 36,864
+constexpr uint32_t A_TILE_BYTES = A_MAIN_BYTES + AUG_BYTES;      // 20,480
+constexpr uint32_t A_BUF_BYTES = RT * A_TILE_BYTES;              // 40,960
 constexpr uint32_t B_TILE_BYTES = 2 * TN * 128 + TN * 32;        // hi | lo | aug = 36,864
 
 // shared memory map (dynamic, 1024-B aligned base)
 constexpr uint32_t OFF_A = 0;                                    // 2 buffers
-constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 4 slots
+constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 3 slots
 constexpr uint32_t OFF_BAR = OFF_B + B_SLOTS * B_TILE_BYTES;     // mbarriers
-constexpr uint32_t OFF_FLAGS = OFF_BAR + 256;                    // row fallback flags 2 x 128 bytes
-constexpr uint32_t OFF_CAND = OFF_FLAGS + 256;                   // candidate pairs 2 x 128 x int2
-constexpr uint32_t TC_SMEM = OFF_CAND + 2048 + 1024;             // + slack for manual 1024-B alignment
-static_assert(OFF_A % 1024 == 0 && OFF_B % 1024 == 0 && A_BUF_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "align");
+constexpr uint32_t TC_SMEM = OFF_BAR + 256 + 1024;               // + slack for manual 1024-B alignment
+static_assert(OFF_A % 1024 == 0 && OFF_B % 1024 == 0 && A_TILE_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "align");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
 
 enum {
-    BAR_A_FULL = 0,    // +2
-    BAR_A_EMPTY = 2,   // +2
-    BAR_B_FULL = 4,    // +4
-    BAR_B_EMPTY = 8,   // +4
-    BAR_ACC_FULL = 12,   // +2
-    BAR_ACC_EMPTY = 14,  // +2
-    BAR_CAND_FULL = 16,  // +2
-    BAR_CAND_EMPTY = 18, // +2
-    BAR_COUNT = 20
+    BAR_A_FULL = 0,      // +2   (bulk copy tx)
+    BAR_A_EMPTY = 2,     // +2   (MMA commit)
+    BAR_B_FULL = 4,      // +3   (bulk copy tx)
+    BAR_B_EMPTY = 7,     // +3   (MMA commit)
+    BAR_ACC_FULL = 10,   // +4   [stage*2 + row tile]  (MMA commit)
+    BAR_ACC_EMPTY = 14,  // +4   (4 epilogue warps)
+    BAR_COUNT = 18
 };
+static_assert(BAR_COUNT * 8 <= 256, "barrier area");
 
 constexpr float AUG_ONE = 4096.0f;            // 2^12, exact in fp16
 constexpr float AUG_INV = 1.0f / 4096.0f;
-constexpr float PAD_NORM = 30000.0f;          // aug entry of padding columns: acc ~ 1.2e8, never selected
-constexpr float ROW_LIMIT = 1024.0f;          // |S*x| above this -> exact fallback for the row
+constexpr float BIAS = 16384.0f;              // 2^14: exponent field 141 == 1 (mod 4), see key_of / acc_of
+constexpr uint32_t BIAS_HI = 0x46000000u;     // the 7 pattern bits shared by [2^13, 2^17)
+constexpr float SC_LIMIT = 96.0f;             // S * max|c| <= 96
+constexpr float X_LIMIT = 192.0f;             // S |x| above this -> exact scan in the tail kernel
+constexpr float PAD_BUMP = 28672.0f;          // padding columns sit this far (accumulator units) behind centroid k-1:
+                                              // (192 + 96)^2 + PAD_BUMP + BIAS = 128,000 < 2^17, the end of the key range
+constexpr float TAU_SAFETY = 1.0625f;
+
+// scale[] layout (device floats written by k_tc_scale).  Sx is the scale of the row image (x~ = fp16(Sx x)): the
+// index's own S unless a prepared image with its own scale is attached (k-means), R = S / Sx.
+enum { SC_S = 0, SC_INV_S2 = 2, SC_TAU = 3, SC_CMAX = 4, SC_SX = 5, SC_RATIO = 6, SC_COUNT = 8 };
 
 // (mbarrier / bulk-copy wrappers: at_ptx.cuh)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// The MMA / commit / bulk-copy wrappers are executed by a whole converged warp with warp-uniform operands and issue
+// from one elected lane: the operands then live in uniform registers (a lane-0 branch instead makes the compiler move
+// every descriptor through R2UR inside a per-instruction election loop, ~100 cycles per MMA).
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
+        ".reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar) : "memory");
+}
+// expect_tx + bulk copy from one elected lane of a converged warp
+__device__ __forceinline__ void bulk_g2s_elect(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+        "}" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // K-major operand descriptors (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
@@ -119,13 +163,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float fmin3(float a, float b, float c) {
-    float r;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }  // VIMNMX3.U32
+// accumulator value of a key (exact): the 7 dropped pattern bits are the same for every binade in range
+__device__ __forceinline__ float acc_of(uint32_t key) { return __uint_as_float(BIAS_HI | (key >> 7)); }
 
 // value split into three fp16 pieces (p1 + p2 + p3 ~ v to ~33 bits)
 __device__ __forceinline__ void split3(float v, __half &p1, __half &p2, __half &p3) {
@@ -142,60 +203,81 @@ __device__ __host__ __forceinline__ uint32_t sw128_off(int r, int chunk) { retur
 __device__ __host__ __forceinline__ uint32_t aug_off(int r, int kc) { return (uint32_t)(r >> 3) * 256u + (uint32_t)kc * 128u + (uint32_t)(r & 7) * 16u; }
 
 // ------------------------------------------------------------------------------------------ operand prep
-__global__ void k_tc_scale(const float *__restrict__ c, int n, float *__restrict__ scale) {
-    __shared__ float red[32];
-    float m = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(c[i]));
-    m = warp_max(m);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+// S = 2^s, the largest power of two with S * max|c_j| <= SC_LIMIT (so P d + BIAS stays inside [2^13, 2^17) for every
+// row with S |x| <= X_LIMIT); tau = absolute part of the certification threshold in accumulator units.
+__global__ void k_tc_scale(const float *__restrict__ c, const float *__restrict__ cn, int k,
+                           const float *__restrict__ ext_sx, float *__restrict__ scale) {
+    __shared__ float red[2][32];
+    float m = 0.f, n2 = 0.f;
+    for (int i = threadIdx.x; i < k * 64; i += blockDim.x) m = fmaxf(m, fabsf(c[i]));
+    for (int i = threadIdx.x; i < k; i += blockDim.x) n2 = fmaxf(n2, cn[i]);
+    m = warp_max(m), n2 = warp_max(n2);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = m, red[1][threadIdx.x >> 5] = n2;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, red[w]);
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, red[0][w]), n2 = fmaxf(n2, red[1][w]);
+        const float cmax = sqrtf(n2) * 1.0009765625f;
         int e = 0;
-        if (m > 0.f && isfinite(m)) {
+        if (cmax > 0.f && isfinite(cmax)) {
             int ex;
-            frexpf(m, &ex);  // m < 2^ex
-            e = 7 - ex;      // m * 2^e in [64, 128)
+            frexpf(cmax, &ex);   // cmax = f * 2^ex, f in [0.5, 1)
+            e = 6 - ex;          // cmax * 2^e in [32, 64)
+            if (ldexpf(cmax, e + 1) <= SC_LIMIT) e++;   // up to (48, 96]
+            e = max(-40, min(40, e));
         }
         float S = ldexpf(1.0f, e);
-        scale[0] = S;
-        scale[1] = S * S * AUG_INV;
-        scale[2] = 1.0f / (S * S);
-        // absolute part of the "is the runner-up safely behind?" threshold, in accumulator units: 2^-19 * S^2 * 64 m^2
-        // bounds 2^-19 S^2 |c|^2 (m = max |c_ij|); split-fp16 products carry ~2^-21 of |x||c| S^2, fp32 accumulation
-        // a few 2^-24 of the same, so this leaves a factor ~4 of head-room
-        scale[3] = ldexpf(S * S * 64.0f * m * m, -19);
+        float Sx = S;
+        if (ext_sx) {
+            // an attached row image fixes Sx: the c-side norm weights 4096 R^2 must stay fp16 numbers, R = S / Sx <= 1
+            // keeps them exact; a smaller S only costs accumulator resolution
+            Sx = ext_sx[0];
+            if (!(Sx > 0.f) || !isfinite(Sx)) Sx = S;
+            if (S > Sx) S = Sx;
+            if (S < Sx * 0.0009765625f) S = Sx * 0.0009765625f;
+        }
+        scale[SC_S] = S;
+        scale[1] = 0.f;
+        scale[SC_INV_S2] = 1.0f / (S * S);
+        // split-fp16 centroid products carry ~2^-21 of |x||c| S^2, fp32 accumulation a few 2^-24 of the partial sums
+        // (|.| <= 2^17): 2^-19 S^2 64 m^2 (>= 2^-19 S^2 |c|^2) plus 8 ulps of the accumulator leaves a factor ~4
+        scale[SC_TAU] = ldexpf(S * S * 64.0f * m * m, -19) + 0.0625f;
+        scale[SC_CMAX] = S * cmax;
+        scale[SC_SX] = Sx;
+        scale[SC_RATIO] = S / Sx;
+        scale[7] = 0.f;
     }
 }
 
-// one thread per (padded centroid, 16-byte chunk): chunks 0..7 main columns, chunk 8 = aug
+// one thread per (padded centroid, 16-byte chunk): chunks 0..7 main columns, chunk 8 = aug.
+// Padding columns (j >= k) repeat centroid k-1 with PAD_BUMP added to the norm: always behind the real column by far
+// more than any threshold, inside the key range, skipped by the tail kernel.
 __global__ void k_tc_prep(const float *__restrict__ c, const float *__restrict__ cn, int k, int ktiles,
                           const float *__restrict__ scale, unsigned char *__restrict__ op) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int j = idx / 9, chunk = idx % 9;
     if (j >= ktiles * TN) return;
-    const float S = scale[0], S2A = scale[1];
+    const float S = scale[SC_S], R = scale[SC_RATIO];
+    const float Sc = S * R;   // x~ carries Sx: -2 Sc c with Sx Sc = S^2
     unsigned char *tile = op + (size_t)(j / TN) * B_TILE_BYTES;
     const int r = j % TN;
+    const int js = j < k ? j : k - 1;
     if (chunk < 8) {
         __align__(16) __half hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            float v = j < k ? -2.0f * S * c[(size_t)j * 64 + chunk * 8 + e] : 0.f;
+            float v = -2.0f * Sc * c[(size_t)js * 64 + chunk * 8 + e];
             hi[e] = __float2half_rn(v);
             lo[e] = __float2half_rn(v - __half2float(hi[e]));
         }
         *reinterpret_cast<uint4 *>(tile + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(hi);
         *reinterpret_cast<uint4 *>(tile + TN * 128 + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(lo);
     } else {
+        // row side: [pieces of xn Sx^2 / 4096 | 4096 4096 4096]; this side: [w w w | pieces of (cn S^2 + BIAS) / 4096],
+        // w = 4096 R^2 (a power of two <= 4096)
         __align__(16) __half a[8];
-        const __half one = __float2half_rn(AUG_ONE), zero = __float2half_rn(0.f);
-        a[0] = a[1] = a[2] = one;
-        if (j < k) {
-            split3(cn[j] * S2A, a[3], a[4], a[5]);
-        } else {
-            a[3] = __float2half_rn(PAD_NORM), a[4] = zero, a[5] = zero;
-        }
+        const __half w = __float2half_rn(AUG_ONE * R * R), zero = __float2half_rn(0.f);
+        a[0] = a[1] = a[2] = w;
+        split3(fmaf(cn[js], S * S * AUG_INV, (j < k ? BIAS : BIAS + PAD_BUMP) * AUG_INV), a[3], a[4], a[5]);
         a[6] = a[7] = zero;
         unsigned char *aug = tile + 2 * TN * 128;
         *reinterpret_cast<uint4 *>(aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
@@ -203,82 +285,140 @@ __global__ void k_tc_prep(const float *__restrict__ c, const float *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------ row image
+// 4 lanes per row (lane jq holds floats 16 jq .. 16 jq + 15), 8 rows per warp step.  Rows beyond n are zero.
+// The reductions here need not follow the canonical association: a row that differs from the canonically normalised
+// one in the last bit is inside the certification threshold (the 1e-6 |Sx x| term of erow).
+__global__ void __launch_bounds__(256) k_tc_rows(const float *__restrict__ x, int64_t n, int64_t n_pad, int l2norm,
+                                                 const float *__restrict__ sx_ptr, unsigned char *__restrict__ img,
+                                                 float *__restrict__ erow, float *__restrict__ xns) {
+    const int lane = threadIdx.x & 31, rsub = lane >> 2, jq = lane & 3;
+    const float Sx = sx_ptr[0];
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp * 8; r0 < n_pad; r0 += nwarps * 8) {   // warp-uniform trip count
+        const int64_t r = r0 + rsub;
+        float xs[16];
+        if (r < n) {
+            const float4 *xp = reinterpret_cast<const float4 *>(x + r * 64) + 4 * jq;
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float4 v = __ldg(xp + t);
+                xs[4 * t] = v.x, xs[4 * t + 1] = v.y, xs[4 * t + 2] = v.z, xs[4 * t + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 16; t++) xs[t] = 0.f;
+        }
+        float q = 0.f;
+#pragma unroll
+        for (int t = 0; t < 16; t++) q = fmaf(xs[t], xs[t], q);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        float xn = q;
+        if (l2norm) {
+            const float inv = 1.0f / l2_denominator(q);
+            float q2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; t++) xs[t] *= inv, q2 = fmaf(xs[t], xs[t], q2);
+            q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+            q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
+            xn = q2;
+        }
+        __align__(16) __half2 hh[8];
+        float e2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const float s0 = Sx * xs[2 * t], s1 = Sx * xs[2 * t + 1];
+            hh[t] = __floats2half2_rn(s0, s1);
+            const float2 f = __half22float2(hh[t]);
+            const float e0 = s0 - f.x, e1 = s1 - f.y;
+            e2 = fmaf(e0, e0, e2), e2 = fmaf(e1, e1, e2);
+        }
+        e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
+        e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
+        const int rr = (int)(r & (TM - 1));
+        unsigned char *a_tile = img + (size_t)(r >> 7) * A_TILE_BYTES;
+        // floats 16 jq .. 16 jq + 15 = fp16 chunks 2 jq, 2 jq + 1 of the row
+        *reinterpret_cast<uint4 *>(a_tile + sw128_off(rr, 2 * jq)) = *reinterpret_cast<uint4 *>(&hh[0]);
+        *reinterpret_cast<uint4 *>(a_tile + sw128_off(rr, 2 * jq + 1)) = *reinterpret_cast<uint4 *>(&hh[4]);
+        if (jq == 0) {
+            const float xnS = Sx * Sx * xn;   // inf / NaN for rows the fp16 image cannot hold: the epilogue sends them to the tail
+            __align__(16) __half a[8];
+            const __half one = __float2half_rn(AUG_ONE), zero = __float2half_rn(0.f);
+            split3(xnS * AUG_INV, a[0], a[1], a[2]);
+            a[3] = a[4] = a[5] = one;
+            a[6] = a[7] = zero;
+            unsigned char *a_aug = a_tile + A_MAIN_BYTES;
+            *reinterpret_cast<uint4 *>(a_aug + aug_off(rr, 0)) = *reinterpret_cast<uint4 *>(a);
+            *reinterpret_cast<uint4 *>(a_aug + aug_off(rr, 1)) = make_uint4(0, 0, 0, 0);
+            erow[r] = sqrtf(e2) * 1.001f + 1e-6f * sqrtf(xnS);
+            xns[r] = xnS;
+        }
+    }
+}
+
+// canonical fp32 distance of the row to a centroid, evaluated by a 16-lane group: lane l holds chunk l of the row
+// (xv) and of the centroid (v) -- 4-element FMA chain per chunk, xor butterfly over the group: bit-identical to
+// at_index.cuh's tree16 form.
+__device__ __forceinline__ float coop_dist(const float4 xv, float xn, const float4 v, float cnj) {
+    float s = xv.x * v.x;
+    s = fmaf(xv.y, v.y, s);
+    s = fmaf(xv.z, v.z, s);
+    s = fmaf(xv.w, v.w, s);
+    return l2_expanded(xn, cnj, half16_sum(s));
+}
+
+constexpr int GA = 8;   // columns per A group
+
+// 16 accumulator columns -> keys.  Two orthogonal groupings of the tile's 128 columns:
+//   A: 16 groups of 8 adjacent columns -> exact running top-3 over the group minima (keys carry the column);
+//   B: 8 groups of 16 columns with the same position mod 8 -> bp[h], the running minimum of group h over the tile.
+// Two columns never share both an A and a B group, so the second smallest COLUMN of a row is exactly
+// min(second smallest A-group minimum, second smallest B-group minimum): the runner-up can hide behind the winner in
+// one grouping, never in both.   alu: 8 (A minima) + 8 (A top-3) + 8 (B) per 16 columns; fma pipe: 16 IMAD.
+__device__ __forceinline__ void fold16(const uint32_t (&r)[16], const int cb, const uint32_t mul, uint32_t &t1,
+                                       uint32_t &t2, uint32_t &t3, uint32_t (&bp)[8]) {
+    uint32_t kx[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) kx[i] = r[i] * mul + (uint32_t)(cb + i);   // IMAD R, R, Rmul, imm
+    const uint32_t ga0 = min(umin3(umin3(kx[0], kx[1], kx[2]), kx[3], kx[4]), umin3(kx[5], kx[6], kx[7]));
+    const uint32_t ga1 = min(umin3(umin3(kx[8], kx[9], kx[10]), kx[11], kx[12]), umin3(kx[13], kx[14], kx[15]));
+    const uint32_t lo = min(ga0, ga1), hi = max(ga0, ga1);
+    t3 = umin3(t3, max(t2, lo), max(t1, hi));
+    t2 = umin3(t2, hi, max(t1, lo));
+    t1 = min(t1, lo);
+#pragma unroll
+    for (int h = 0; h < 8; h++) bp[h] = umin3(bp[h], kx[h], kx[h + 8]);
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
-// canonical fp32 distance of row x (registers, already normalised) to centroid j
-__device__ __forceinline__ float exact_dist(const float (&xr)[64], float xn, const float *__restrict__ c,
-                                            const float *__restrict__ cn, int j) {
-    const float4 *cj = reinterpret_cast<const float4 *>(c + (size_t)j * 64);
-    float q[16];
-#pragma unroll
-    for (int l = 0; l < 16; l++) {
-        float4 v = __ldg(cj + l);
-        float s = xr[4 * l] * v.x;
-        s = fmaf(xr[4 * l + 1], v.y, s);
-        s = fmaf(xr[4 * l + 2], v.z, s);
-        s = fmaf(xr[4 * l + 3], v.w, s);
-        q[l] = s;
-    }
-    return l2_expanded(xn, __ldg(cn + j), tree16(q));
-}
-
-// 32 accumulator columns -> packed (distance | column) keys -> minima of groups of four adjacent columns (FMNMX3 +
-// FMNMX: half an ALU op per score) -> running top-2 over GROUP minima, two independent chains.
-// ALU-pipe budget: 1 LOP3 + 0.5 + 0.31 ops per score (the exact per-column top-2 needs 3.5 and is ALU-bound).
-// The best column overall is always the minimum of the best group; the runner-up is the minimum of the second-best
-// group unless it sits in the best group itself (3 of K-1 positions) -- see the tie note in the file header.
-__device__ __forceinline__ void fold32(const uint32_t (&r)[32], int cb, float (&t1)[2], float (&t2)[2]) {
-#pragma unroll
-    for (int gp = 0; gp < 4; gp++) {
-        const int e = 8 * gp, ch = gp & 1;
-        float kx[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) kx[i] = __uint_as_float((r[e + i] & 0xFFFFFF80u) | (uint32_t)(cb + e + i));
-        const float a = fminf(fmin3(kx[0], kx[1], kx[2]), kx[3]);
-        const float b = fminf(fmin3(kx[4], kx[5], kx[6]), kx[7]);
-        const float lo = fminf(a, b), hi = fmaxf(a, b);
-        t2[ch] = fmin3(t2[ch], hi, fmaxf(t1[ch], lo));
-        t1[ch] = fminf(t1[ch], lo);
-    }
-}
-// merge chain b into chain a
-__device__ __forceinline__ void merge_top2(float &a1, float &a2, float b1, float b2) {
-    const float lo = fminf(a1, b1), hi = fmaxf(a1, b1);
-    a2 = fmin3(hi, a2, b2);
-    a1 = lo;
-}
-
-// RESIDENT: blockIdx.x % nslices selects the centroid slice [tile0, tile0 + ntl), kept in shared memory.
+// RESIDENT: all ktiles (<= B_SLOTS) operand tiles are loaded once and stay in shared memory.
 template <bool RESIDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned char *__restrict__ op, int ktiles,
-            int nslices, int k, const float *__restrict__ c, const float *__restrict__ cn,
-            const float *__restrict__ scale, int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
-            float *__restrict__ dist, float *__restrict__ part_dist, int32_t *__restrict__ part_lab) {
+k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ erow, const float *__restrict__ xns, int64_t n,
+            const unsigned char *__restrict__ op, int ktiles, int k, const float *__restrict__ scale, uint32_t key_mul,
+            int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist,
+            uint2 *__restrict__ tail, unsigned int *__restrict__ tail_count, unsigned int tail_cap) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ uint32_t s_tmem_base;
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    unsigned char *sm = smem_dyn + (base - smem_u32(smem_dyn));
     const uint32_t bar0 = base + OFF_BAR;
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    unsigned char *flags = sm + OFF_FLAGS;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int slice = RESIDENT ? (int)(blockIdx.x % nslices) : 0;
-    const int worker = RESIDENT ? (int)(blockIdx.x / nslices) : (int)blockIdx.x;
-    const int workers = RESIDENT ? (int)(gridDim.x / nslices) : (int)gridDim.x;
-    const int tile0 = RESIDENT ? slice * B_SLOTS : 0;                       // first centroid tile of this CTA
-    const int ntl = RESIDENT ? min(B_SLOTS, ktiles - tile0) : ktiles;       // centroid tiles this CTA visits per row tile
-    const int64_t ntiles = (n + TM - 1) / TM;
-    const int64_t my_tiles = worker < ntiles ? (ntiles - worker + workers - 1) / workers : 0;
+    const int worker = (int)blockIdx.x, workers = (int)gridDim.x;
+    const int64_t nsuper = (n + SROWS - 1) / SROWS;
+    const int64_t my_tiles = worker < nsuper ? (nsuper - worker + workers - 1) / workers : 0;
 
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
-            mbar_init(BAR(BAR_A_FULL + i), 4);
+            mbar_init(BAR(BAR_A_FULL + i), 1);
             mbar_init(BAR(BAR_A_EMPTY + i), 1);
+        }
+        for (int i = 0; i < 4; i++) {
             mbar_init(BAR(BAR_ACC_FULL + i), 1);
             mbar_init(BAR(BAR_ACC_EMPTY + i), 4);
-            mbar_init(BAR(BAR_CAND_FULL + i), 4);
-            mbar_init(BAR(BAR_CAND_EMPTY + i), 4);
         }
         for (int i = 0; i < B_SLOTS; i++) {
             mbar_init(BAR(BAR_B_FULL + i), 1);
@@ -287,7 +427,7 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -295,256 +435,199 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
 
-    if (warp == 3) {
-        // ================================================================== centroid-tile producer
-        if (lane == 0 && my_tiles > 0) {
+    if (warp == 0) {
+        // ================================================================== centroid-tile producer (whole warp, elected lane)
+        if (my_tiles > 0) {
             if (RESIDENT) {
-                for (int jt = 0; jt < ntl; jt++) {
-                    mbar_expect_tx(BAR(BAR_B_FULL + jt), B_TILE_BYTES);
-                    bulk_g2s(base + OFF_B + jt * B_TILE_BYTES, op + (size_t)(tile0 + jt) * B_TILE_BYTES, B_TILE_BYTES,
-                             BAR(BAR_B_FULL + jt));
-                }
+                for (int jt = 0; jt < ktiles; jt++)
+                    bulk_g2s_elect(base + OFF_B + jt * B_TILE_BYTES, op + (size_t)jt * B_TILE_BYTES, B_TILE_BYTES,
+                                   BAR(BAR_B_FULL + jt));
             } else {
-                uint32_t s = 0;
+                uint32_t st = 0, ph = 0;
                 for (int64_t i = 0; i < my_tiles; i++) {
-                    for (int jt = 0; jt < ktiles; jt++, s++) {
-                        const uint32_t st = s % B_SLOTS, ph = (s / B_SLOTS) & 1;
+                    for (int jt = 0; jt < ktiles; jt++) {
                         mbar_wait(BAR(BAR_B_EMPTY + st), ph ^ 1);
-                        mbar_expect_tx(BAR(BAR_B_FULL + st), B_TILE_BYTES);
-                        bulk_g2s(base + OFF_B + st * B_TILE_BYTES, op + (size_t)jt * B_TILE_BYTES, B_TILE_BYTES,
-                                 BAR(BAR_B_FULL + st));
+                        bulk_g2s_elect(base + OFF_B + st * B_TILE_BYTES, op + (size_t)jt * B_TILE_BYTES, B_TILE_BYTES,
+                                       BAR(BAR_B_FULL + st));
+                        if (++st == B_SLOTS) st = 0, ph ^= 1;
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================================================== MMA issuer
-        if (lane == 0) {
-            uint32_t s = 0, u = 0;
-            for (int64_t i = 0; i < my_tiles; i++) {
-                const uint32_t ab = (uint32_t)(i & 1);
-                mbar_wait(BAR(BAR_A_FULL + ab), (uint32_t)((i >> 1) & 1));
-                const uint32_t a_hi = base + OFF_A + ab * A_BUF_BYTES, a_lo = a_hi + A_MAIN_BYTES, a_aug = a_lo + A_MAIN_BYTES;
-                for (int jt = 0; jt < ntl; jt++, s++, u++) {
-                    const uint32_t st = RESIDENT ? (uint32_t)jt : s % B_SLOTS;
-                    const uint32_t bph = RESIDENT ? 0u : (s / B_SLOTS) & 1;
-                    const uint32_t buf = u & 1, aph = (u >> 1) & 1;
-                    if (!RESIDENT || i == 0) mbar_wait(BAR(BAR_B_FULL + st), bph);
-                    mbar_wait(BAR(BAR_ACC_EMPTY + buf), aph ^ 1);
-                    tc_fence_after();
-                    const uint32_t b_hi = base + OFF_B + st * B_TILE_BYTES, b_lo = b_hi + TN * 128, b_aug = b_lo + TN * 128;
-                    const uint32_t d = tmem + buf * TN;
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) umma_f16(d, desc_sw128(a_hi + kk * 32), desc_sw128(b_hi + kk * 32), IDESC, kk > 0);
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) umma_f16(d, desc_sw128(a_hi + kk * 32), desc_sw128(b_lo + kk * 32), IDESC, 1);
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) umma_f16(d, desc_sw128(a_lo + kk * 32), desc_sw128(b_hi + kk * 32), IDESC, 1);
-                    umma_f16(d, desc_nosw(a_aug), desc_nosw(b_aug), IDESC, 1);
-                    if (!RESIDENT) umma_commit(BAR(BAR_B_EMPTY + st));
-                    umma_commit(BAR(BAR_ACC_FULL + buf));
-                }
-                umma_commit(BAR(BAR_A_EMPTY + ab));
-            }
-        }
-    } else if (warp >= 4 && warp < 8) {
-        // ================================================================== converters
-        const int cw = warp - 4;
-        const int half = lane >> 4, g = lane & 15;
-        const float S = scale[0], S2A = scale[1];
+    } else if (warp == 3) {
+        // ================================================================== row-image producer
         for (int64_t i = 0; i < my_tiles; i++) {
-            const int64_t tile = worker + i * workers;
-            const int rows = (int)min((int64_t)TM, n - tile * TM);
             const uint32_t ab = (uint32_t)(i & 1);
-            const float4 *xg = reinterpret_cast<const float4 *>(x + tile * TM * 64);
-            // issue the global loads before waiting for the buffer: they do not depend on it
-            float4 vv[16];
-#pragma unroll
-            for (int it = 0; it < 16; it++) {
-                const int r = cw * 32 + it * 2 + half;
-                vv[it] = r < rows ? __ldg(xg + r * 16 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
             mbar_wait(BAR(BAR_A_EMPTY + ab), (uint32_t)(((i >> 1) & 1) ^ 1));
-            unsigned char *a_hi = sm + OFF_A + ab * A_BUF_BYTES, *a_lo = a_hi + A_MAIN_BYTES, *a_aug = a_lo + A_MAIN_BYTES;
+            bulk_g2s_elect(base + OFF_A + ab * A_BUF_BYTES, img + (size_t)(worker + i * workers) * A_BUF_BYTES, A_BUF_BYTES,
+                           BAR(BAR_A_FULL + ab));
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer (whole warp, elected lane)
+        uint32_t st = 0, bph = 0, u = 0;
+        for (int64_t i = 0; i < my_tiles; i++) {
+            const uint32_t ab = (uint32_t)(i & 1);
+            mbar_wait(BAR(BAR_A_FULL + ab), (uint32_t)((i >> 1) & 1));
+            const uint32_t a0 = base + OFF_A + ab * A_BUF_BYTES;
+            for (int jt = 0; jt < ktiles; jt++, u++) {
+                const uint32_t slot = RESIDENT ? (uint32_t)jt : st;
+                const uint32_t stage = u & 1, aph = (u >> 1) & 1;
+                if (!RESIDENT || i == 0) mbar_wait(BAR(BAR_B_FULL + slot), RESIDENT ? 0u : bph);
+                const uint32_t b_hi = base + OFF_B + slot * B_TILE_BYTES;
+                const uint64_t dB_hi = desc_sw128(b_hi), dB_lo = desc_sw128(b_hi + TN * 128), dB_aug = desc_nosw(b_hi + 2 * TN * 128);
 #pragma unroll
-            for (int it = 0; it < 16; it++) {
-                const int r = cw * 32 + it * 2 + half;
-                float4 v = vv[it];
-                if (l2norm) {
-                    float q = v.x * v.x;
-                    q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
-                    const float den = l2_denominator(half16_sum(q));
-                    v.x = __fdiv_rn(v.x, den), v.y = __fdiv_rn(v.y, den), v.z = __fdiv_rn(v.z, den), v.w = __fdiv_rn(v.w, den);
+                for (int rt = 0; rt < RT; rt++) {
+                    const uint32_t a_hi = a0 + rt * A_TILE_BYTES;
+                    const uint64_t dA = desc_sw128(a_hi), dA_aug = desc_nosw(a_hi + A_MAIN_BYTES);
+                    mbar_wait(BAR(BAR_ACC_EMPTY + stage * 2 + rt), aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d = tmem + (stage * 2 + rt) * TN;
+                    // descriptor start addresses are in 16-byte units: a K step of 16 fp16 = 32 bytes = +2
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_hi + 2 * kk, IDESC, kk > 0);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_lo + 2 * kk, IDESC, 1);
+                    umma_f16(d, dA_aug, dB_aug, IDESC, 1);
+                    umma_commit(BAR(BAR_ACC_FULL + stage * 2 + rt));
                 }
-                float q = v.x * v.x;
-                q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
-                const float xn = half16_sum(q);
-                float sx = S * v.x, sy = S * v.y, sz = S * v.z, sw = S * v.w;
-                float amax = fmaxf(fmaxf(fabsf(sx), fabsf(sy)), fmaxf(fabsf(sz), fabsf(sw)));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                const bool fallback = !(amax <= ROW_LIMIT);  // also catches NaN
-                if (fallback) sx = sy = sz = sw = 0.f;
-                __half2 h01 = __floats2half2_rn(sx, sy), h23 = __floats2half2_rn(sz, sw);
-                float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                __half2 l01 = __floats2half2_rn(sx - f01.x, sy - f01.y), l23 = __floats2half2_rn(sz - f23.x, sw - f23.y);
-                const uint32_t off = sw128_off(r, g >> 1) + (uint32_t)(g & 1) * 8u;
-                *reinterpret_cast<uint2 *>(a_hi + off) = make_uint2(*reinterpret_cast<uint32_t *>(&h01), *reinterpret_cast<uint32_t *>(&h23));
-                *reinterpret_cast<uint2 *>(a_lo + off) = make_uint2(*reinterpret_cast<uint32_t *>(&l01), *reinterpret_cast<uint32_t *>(&l23));
-                if (g == 0) {
-                    __align__(16) __half a[8];
-                    const __half one = __float2half_rn(AUG_ONE), zero = __float2half_rn(0.f);
-                    split3(fallback ? 0.f : xn * S2A, a[0], a[1], a[2]);
-                    a[3] = a[4] = a[5] = one;
-                    a[6] = a[7] = zero;
-                    *reinterpret_cast<uint4 *>(a_aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
-                    *reinterpret_cast<uint4 *>(a_aug + aug_off(r, 1)) = make_uint4(0, 0, 0, 0);
-                    flags[ab * 128 + r] = fallback ? 1 : 0;
+                if (!RESIDENT) {
+                    umma_commit(BAR(BAR_B_EMPTY + slot));
+                    if (++st == B_SLOTS) st = 0, bph ^= 1;
                 }
             }
-            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_A_FULL + ab));
+            umma_commit(BAR(BAR_A_EMPTY + ab));
         }
-    } else if (warp >= 8 && warp < 12) {
+    } else if (warp >= 4) {
         // ================================================================== epilogue: accumulator scan
-        const int ew = warp - 8;  // == warp % 4: the TMEM lane quadrant this warp may read
-        const int row_in_tile = ew * 32 + lane;
+        const int rt = (warp - 4) >> 2;   // row tile of the super tile
+        const int ew = warp & 3;          // the TMEM lane quadrant this warp may read
+        const int row_in_super = rt * TM + ew * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-        constexpr float BIG = 3.0e38f;
-        int2 *cand = reinterpret_cast<int2 *>(sm + OFF_CAND);
-        const float inv_s2 = scale[2], tau_abs = scale[3];
+        const float inv_s2 = scale[SC_INV_S2], tau_abs = scale[SC_TAU], cmax = scale[SC_CMAX], R = scale[SC_RATIO];
         uint32_t u = 0;
+        bool primed = false;
+        uint32_t c0[16], c1[16], c2[16], c3[16];
         for (int64_t i = 0; i < my_tiles; i++) {
-            float g1 = BIG, g2 = BIG;
+            uint32_t g1 = 0xFFFFFFFFu, g2 = 0xFFFFFFFFu, g3 = 0xFFFFFFFFu;   // A grouping: best three group minima of the row
+            uint32_t h1 = 0xFFFFFFFFu, h2 = 0xFFFFFFFFu;                     // B grouping: best two
             int j1 = 0, j2 = 0;
-            int fallback = 0;
-            for (int jt = 0; jt < ntl; jt++, u++) {
-                const uint32_t buf = u & 1, ph = (u >> 1) & 1;
-                mbar_wait(BAR(BAR_ACC_FULL + buf), ph);
+            const int64_t row = (worker + i * workers) * SROWS + row_in_super;
+            const float e = R * __ldg(erow + row);           // S |delta|
+            const float xnP = R * R * __ldg(xns + row);      // S^2 |x|^2
+            const bool fallback = !(xnP <= X_LIMIT * X_LIMIT);   // outside the accumulator range, Inf, NaN
+            // Accumulator read-out in eight 16-column loads through four register buffers: two loads are always in flight
+            // behind two folds, and the first two loads of the NEXT tile are issued before the last two folds of this one.
+            if (!primed) {   // very first tile of this warp
+                mbar_wait(BAR(BAR_ACC_FULL + (u & 1) * 2 + rt), (u >> 1) & 1);
                 tc_fence_after();
-                // the converters may rewrite this flag slot as soon as MMA(i) retires: read it now
-                if (jt == 0) fallback = flags[(i & 1) * 128 + row_in_tile];
-                float c1[2] = {BIG, BIG}, c2[2] = {BIG, BIG};
-                const uint32_t ta = tmem + lane_addr + buf * TN;
-                uint32_t ra[32], rb[32];
-                tmem_ld32(ta, ra);
-                tmem_ld32(ta + 32, rb);
+                const uint32_t ta = tmem + lane_addr + ((u & 1) * 2 + rt) * TN;
+                tmem_ld16(ta, c0);
+                tmem_ld16(ta + 16, c1);
+                primed = true;
+            }
+            for (int jt = 0; jt < ktiles; jt++, u++) {
+                const uint32_t stage = u & 1;
+                const uint32_t ta = tmem + lane_addr + (stage * 2 + rt) * TN;
+                uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;
+                uint32_t bp[8];
+#pragma unroll
+                for (int h = 0; h < 8; h++) bp[h] = 0xFFFFFFFFu;
+                tmem_ld_wait();                       // c0, c1 (issued during the previous tile)
+                tmem_ld16(ta + 32, c2);
+                tmem_ld16(ta + 48, c3);
+                fold16(c0, 0, key_mul, t1, t2, t3, bp);
+                fold16(c1, 16, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
-                fold32(ra, 0, c1, c2);
-                tmem_ld32(ta + 64, ra);
-                fold32(rb, 32, c1, c2);
-                tmem_ld32(ta + 96, rb);
+                tmem_ld16(ta + 64, c0);
+                tmem_ld16(ta + 80, c1);
+                fold16(c2, 32, key_mul, t1, t2, t3, bp);
+                fold16(c3, 48, key_mul, t1, t2, t3, bp);
+                tmem_ld_wait();
+                tmem_ld16(ta + 96, c2);
+                tmem_ld16(ta + 112, c3);
+                fold16(c0, 64, key_mul, t1, t2, t3, bp);
+                fold16(c1, 80, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + buf));  // accumulator is in registers: free it early
-                fold32(ra, 64, c1, c2);
-                fold32(rb, 96, c1, c2);
-                merge_top2(c1[0], c2[0], c1[1], c2[1]);
-                const float t1 = c1[0], t2 = c2[0];
-                if (t1 < g1) {
-                    if (t2 < g1) g2 = t2, j2 = jt; else g2 = g1, j2 = j1;
-                    g1 = t1, j1 = jt;
-                } else if (t1 < g2) {
-                    g2 = t1, j2 = jt;
+                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + stage * 2 + rt));  // accumulator is in registers: free it early
+                // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
+                const bool more = (jt + 1 < ktiles) || (i + 1 < my_tiles);
+                const uint32_t un = u + 1;
+                const uint32_t nbar = BAR(BAR_ACC_FULL + (un & 1) * 2 + rt), nph = (un >> 1) & 1;
+                const uint32_t tn = tmem + lane_addr + ((un & 1) * 2 + rt) * TN;
+                bool started = false;
+                if (more && mbar_test(nbar, nph)) {   // warp-uniform: every lane probes the same barrier
+                    tc_fence_after();
+                    tmem_ld16(tn, c0);
+                    tmem_ld16(tn + 16, c1);
+                    started = true;
                 }
+                fold16(c2, 96, key_mul, t1, t2, t3, bp);
+                fold16(c3, 112, key_mul, t1, t2, t3, bp);
+                if (more && !started) {
+                    mbar_wait(nbar, nph);
+                    tc_fence_after();
+                    tmem_ld16(tn, c0);
+                    tmem_ld16(tn + 16, c1);
+                }
+                // B grouping: top-2 of the tile's 8 group minima, merged into the row's
+                uint32_t u1 = 0xFFFFFFFFu, u2 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int pr = 0; pr < 4; pr++) {
+                    const uint32_t lo = min(bp[2 * pr], bp[2 * pr + 1]), hi = max(bp[2 * pr], bp[2 * pr + 1]);
+                    u2 = umin3(u2, hi, max(u1, lo));
+                    u1 = min(u1, lo);
+                }
+                h2 = umin3(h2, u2, max(h1, u1));
+                h1 = min(h1, u1);
+                // A grouping: merge the tile's sorted triple into the row's (equal keys keep the earlier tile)
+                const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
+                const bool p = t1 < g1;
+                const uint32_t xa = p ? g1 : g2, ya = p ? t2 : t1;
+                const int xt = p ? j1 : j2;
+                const bool qn = ya < xa;
+                g2 = min(xa, ya);
+                j2 = qn ? jt : xt;
+                g1 = min(g1, t1);
+                j1 = p ? jt : j1;
+                g3 = n3;
             }
-            // Runner-up safely behind the winner (beyond what the split-fp16 product can get wrong)?  Then the winner
-            // is final and its distance is read off the accumulator; otherwise the re-check warps decide in fp32.
-            const int64_t tile = worker + i * workers;
-            const int64_t row = tile * TM + row_in_tile;
-            const float v1 = __uint_as_float(__float_as_uint(g1) & 0xFFFFFF80u);
-            const float v2 = __uint_as_float(__float_as_uint(g2) & 0xFFFFFF80u);
-            const int ca = (tile0 + j1) * TN + (int)(__float_as_uint(g1) & 127u);
-            const int cb = (tile0 + j2) * TN + (int)(__float_as_uint(g2) & 127u);
-            const bool sliced = RESIDENT && nslices > 1;  // slices are merged on exact distances
-            const bool safe = !fallback && !sliced && (v2 - v1 > fmaf(fabsf(v1), 1.52587890625e-5f, tau_abs)) && ca < k;
-            if (safe && row < n) {
+            // ---- certification (accumulator units)
+            const float A1 = acc_of(g1), A2 = acc_of(min(g2, h2)), A3 = acc_of(g3);
+            const int ca = j1 * TN + (int)(g1 & 127u);
+            const int cb = j2 * TN + (int)(g2 & 127u);
+            const float v1 = fmaxf(A1 - BIAS, 0.f);
+            const float ub = v1 + 2.0f * e * cmax + tau_abs;                        // >= S^2 d_best
+            const float tau = TAU_SAFETY * (tau_abs + 4.0f * e * sqrtf(ub + tau_abs));
+            const bool second_ok = (A2 - A1) > tau;   // exact second smallest column: no other column can win
+            const bool third_ok = (A3 - A1) > tau;    // every column outside the two best A groups is out of reach
+#ifdef AT_TC_FORCE_CERT
+            const bool certified = true;
+#else
+            const bool certified = !fallback && second_ok && ca < k;
+#endif
+            const bool live = row < n;
+            if (certified && live) {
                 if (labels32) labels32[row] = ca;
                 if (labels64) labels64[row] = ca;
-                if (dist) dist[row] = fmaxf(v1, 0.f) * inv_s2;
+                if (dist) dist[row] = v1 * inv_s2;
             }
-            const uint32_t cbuf = (uint32_t)(i & 1);
-            mbar_wait(BAR(BAR_CAND_EMPTY + cbuf), (uint32_t)(((i >> 1) & 1) ^ 1));
-            cand[cbuf * 128 + row_in_tile] = make_int2(safe ? -1 : (ca | (fallback << 30)), cb);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_CAND_FULL + cbuf));
-        }
-    } else if (warp >= 12) {
-        // ================================================================== fp32 re-check + outputs
-        const int row_in_tile = (warp - 12) * 32 + lane;
-        const int2 *cand = reinterpret_cast<const int2 *>(sm + OFF_CAND);
-        for (int64_t i = 0; i < my_tiles; i++) {
-            const int64_t tile = worker + i * workers;
-            const int64_t row = tile * TM + row_in_tile;
-            const uint32_t cbuf = (uint32_t)(i & 1);
-            mbar_wait(BAR(BAR_CAND_FULL + cbuf), (uint32_t)((i >> 1) & 1));
-            int2 cc = cand[cbuf * 128 + row_in_tile];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(BAR_CAND_EMPTY + cbuf));
-            const bool live = row < n && cc.x >= 0;   // cc.x < 0: the scan already wrote this row
-            if (!__any_sync(0xffffffffu, live)) continue;
-            const int fallback = (cc.x >> 30) & 1;
-            cc.x &= 0x3FFFFFFF;
-            float xr[64];
-            float xn = 0.f;
-            if (live) {
-                const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
-#pragma unroll
-                for (int l = 0; l < 16; l++) {
-                    float4 v = __ldg(xp + l);
-                    xr[4 * l] = v.x, xr[4 * l + 1] = v.y, xr[4 * l + 2] = v.z, xr[4 * l + 3] = v.w;
+            // uncertified rows -> tail lists (warp-aggregated appends): candidate rows from the front, full-scan rows
+            // from the back of the same array
+            const bool want_full = live && !certified && (fallback || !third_ok || ca >= k);
+            const bool want_cand = live && !certified && !want_full;
+            const unsigned mc = __ballot_sync(0xffffffffu, want_cand), mf = __ballot_sync(0xffffffffu, want_full);
+            if (mc | mf) {
+                unsigned int sc = 0, sf = 0;
+                if (lane == 0) {
+                    if (mc) sc = atomicAdd(tail_count, (unsigned int)__popc(mc));
+                    if (mf) sf = atomicAdd(tail_count + 1, (unsigned int)__popc(mf));
                 }
-                float q[16];
-                if (l2norm) {
-#pragma unroll
-                    for (int l = 0; l < 16; l++) {
-                        float s = xr[4 * l] * xr[4 * l];
-                        s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
-                        q[l] = s;
-                    }
-                    const float den = l2_denominator(tree16(q));
-#pragma unroll
-                    for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
-                }
-#pragma unroll
-                for (int l = 0; l < 16; l++) {
-                    float s = xr[4 * l] * xr[4 * l];
-                    s = fmaf(xr[4 * l + 1], xr[4 * l + 1], s), s = fmaf(xr[4 * l + 2], xr[4 * l + 2], s), s = fmaf(xr[4 * l + 3], xr[4 * l + 3], s);
-                    q[l] = s;
-                }
-                xn = tree16(q);
-            }
-            if (live) {
-                int best = 0;
-                float bd = INFINITY;
-                if (!fallback) {
-                    int ca = cc.x, cb = cc.y;
-                    if (ca >= k) ca = tile0 * TN;  // cannot happen for finite data; keeps the loads in bounds
-                    if (cb >= k) cb = ca;
-                    const float da = exact_dist(xr, xn, c, cn, ca);
-                    const float db = exact_dist(xr, xn, c, cn, cb);
-                    const bool take_b = db < da || (db == da && cb < ca);
-                    best = take_b ? cb : ca;
-                    bd = take_b ? db : da;
-                } else {  // out-of-range row: exact scan of this CTA's centroid range (rare)
-                    const int jend = min(k, (tile0 + ntl) * TN);
-                    for (int j = tile0 * TN; j < jend; j++) {
-                        const float dj = exact_dist(xr, xn, c, cn, j);
-                        if (dj < bd) bd = dj, best = j;
-                    }
-                }
-                if (RESIDENT && nslices > 1) {
-                    part_dist[(size_t)slice * n + row] = bd;
-                    part_lab[(size_t)slice * n + row] = best;
-                } else {
-                    if (labels32) labels32[row] = best;
-                    if (labels64) labels64[row] = best;
-                    if (dist) dist[row] = bd;
-                }
+                sc = __shfl_sync(0xffffffffu, sc, 0), sf = __shfl_sync(0xffffffffu, sf, 0);
+                const unsigned lt = (1u << lane) - 1u;
+                if (want_cand) tail[sc + __popc(mc & lt)] = make_uint2((uint32_t)row, (uint32_t)ca | ((uint32_t)cb << 16));
+                if (want_full) tail[tail_cap - 1 - (sf + __popc(mf & lt))] = make_uint2((uint32_t)row, 0u);
             }
         }
     }
@@ -552,33 +635,145 @@ k_assign_tc(const float *__restrict__ x, int64_t n, int l2norm, const unsigned c
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
     }
 }
 
-// minimum over centroid slices (slices are in ascending label order: strict '<' keeps the lowest index on ties)
-__global__ void k_tc_merge(const float *__restrict__ part_dist, const int32_t *__restrict__ part_lab, int64_t n,
-                           int nslices, int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
-                           float *__restrict__ dist) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float bd = part_dist[i];
-    int best = part_lab[i];
-    for (int s = 1; s < nslices; s++) {
-        const float d = part_dist[(size_t)s * n + i];
-        if (d < bd) bd = d, best = part_lab[(size_t)s * n + i];
+// ------------------------------------------------------------------------------------------ tail
+// canonical row chunk (float4 chunk g of the row, normalised like normalize_vectors when asked) and its |x|^2
+__device__ __forceinline__ float4 tail_row(const float *__restrict__ x, int64_t row, int l2norm, int g, float &xn) {
+    float4 xv = __ldg(reinterpret_cast<const float4 *>(x + row * 64) + g);
+    if (l2norm) {
+        float q = xv.x * xv.x;
+        q = fmaf(xv.y, xv.y, q), q = fmaf(xv.z, xv.z, q), q = fmaf(xv.w, xv.w, q);
+        const float den = l2_denominator(half16_sum(q));
+        xv.x = __fdiv_rn(xv.x, den), xv.y = __fdiv_rn(xv.y, den), xv.z = __fdiv_rn(xv.z, den), xv.w = __fdiv_rn(xv.w, den);
     }
-    if (labels32) labels32[i] = best;
-    if (labels64) labels64[i] = best;
-    if (dist) dist[i] = bd;
+    float q = xv.x * xv.x;
+    q = fmaf(xv.y, xv.y, q), q = fmaf(xv.z, xv.z, q), q = fmaf(xv.w, xv.w, q);
+    xn = half16_sum(q);
+    return xv;
+}
+
+// Uncertified rows.  Full-scan rows (back of the list): one BLOCK per row, its sixteen 16-lane groups take every
+// sixteenth centroid, eight loads in flight each.  Candidate rows (front): one warp per row, 16-lane group `half` takes
+// the 8 columns of candidate A group `half` (the second may repeat the first).  Canonical fp32 arithmetic throughout.
+__global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, int l2norm, const float *__restrict__ c,
+                                                 const float *__restrict__ cn, int k, const uint2 *__restrict__ tail,
+                                                 const unsigned int *__restrict__ tail_count, unsigned int tail_cap,
+                                                 int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
+                                                 float *__restrict__ dist, unsigned long long *__restrict__ counters) {
+    __shared__ float s_bd[16];
+    __shared__ int s_best[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, g = lane & 15;
+    const unsigned int n_cand = tail_count[0], n_full = tail_count[1];
+    float4 cv[GA];
+    float cnv[GA];
+    // ---- full scans
+    for (unsigned int e = blockIdx.x; e < n_full; e += gridDim.x) {
+        const int64_t row = (int64_t)tail[tail_cap - 1 - e].x;
+        float xn;
+        const float4 xv = tail_row(x, row, l2norm, g, xn);
+        const int gi = warp * 2 + half;
+        float bd = INFINITY;
+        int best = 0x7FFFFFFF;
+        for (int j0 = 0; j0 < k; j0 += 16 * GA) {
+#pragma unroll
+            for (int t = 0; t < GA; t++) {
+                const int jj = min(j0 + 16 * t + gi, k - 1);
+                cv[t] = __ldg(reinterpret_cast<const float4 *>(c + (size_t)jj * 64) + g);
+                cnv[t] = __ldg(cn + jj);
+            }
+#pragma unroll
+            for (int t = 0; t < GA; t++) {
+                const int j = j0 + 16 * t + gi;
+                const float dj = coop_dist(xv, xn, cv[t], cnv[t]);
+                if (j < k && dj < bd) bd = dj, best = j;   // ascending j within the group: strict '<' keeps the lowest index
+            }
+        }
+        if (g == 0) s_bd[gi] = bd, s_best[gi] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < 16; q++)
+                if (s_bd[q] < bd || (s_bd[q] == bd && s_best[q] < best)) bd = s_bd[q], best = s_best[q];
+            if (labels32) labels32[row] = best;
+            if (labels64) labels64[row] = best;
+            if (dist) dist[row] = bd;
+        }
+        __syncthreads();
+    }
+    // ---- candidate rows
+    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n_cand; e += nwarps) {
+        const uint2 cc = tail[e];
+        const int64_t row = (int64_t)cc.x;
+        const int gbase = (int)((half ? (cc.y >> 16) : (cc.y & 0xFFFF)) & ~(uint32_t)(GA - 1));
+#pragma unroll
+        for (int t = 0; t < GA; t++) {   // issue the candidate loads before anything depends on them
+            const int jj = min(gbase + t, k - 1);
+            cv[t] = __ldg(reinterpret_cast<const float4 *>(c + (size_t)jj * 64) + g);
+            cnv[t] = __ldg(cn + jj);
+        }
+        float xn;
+        const float4 xv = tail_row(x, row, l2norm, g, xn);
+        float bd = INFINITY;
+        int best = 0x7FFFFFFF;
+#pragma unroll
+        for (int t = 0; t < GA; t++) {
+            const int j = gbase + t;
+            const float dj = coop_dist(xv, xn, cv[t], cnv[t]);
+            if (j < k && (dj < bd || (dj == bd && j < best))) bd = dj, best = j;
+        }
+        const float od = __shfl_xor_sync(0xffffffffu, bd, 16);
+        const int ob = __shfl_xor_sync(0xffffffffu, best, 16);
+        if (od < bd || (od == bd && ob < best)) bd = od, best = ob;
+        if (lane == 0) {
+            if (labels32) labels32[row] = best;
+            if (labels64) labels64[row] = best;
+            if (dist) dist[row] = bd;
+        }
+    }
+    if (counters && blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&counters[0], (unsigned long long)n_cand);
+        atomicAdd(&counters[1], (unsigned long long)n_full);
+    }
+}
+
+// canonical fp32 distance of every row to its label (second pass of at_index_search when distances are requested):
+// a 16-lane group per row.
+__global__ void __launch_bounds__(256) k_exact_dist(const float *__restrict__ x, int64_t n, int l2norm,
+                                                    const float *__restrict__ c, const float *__restrict__ cn,
+                                                    const int32_t *__restrict__ labels32,
+                                                    const int64_t *__restrict__ labels64, float *__restrict__ dist) {
+    const int g = threadIdx.x & 15;
+    const int64_t groups = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    const int64_t nloop = (n + groups - 1) / groups;   // warp-uniform trip count (full-mask shuffles)
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    for (int64_t it = 0; it < nloop; it++, row += groups) {
+        const bool live = row < n;
+        const int64_t rr = live ? row : 0;
+        float4 xv = __ldg(reinterpret_cast<const float4 *>(x + rr * 64) + g);
+        if (l2norm) {
+            float q = xv.x * xv.x;
+            q = fmaf(xv.y, xv.y, q), q = fmaf(xv.z, xv.z, q), q = fmaf(xv.w, xv.w, q);
+            const float den = l2_denominator(half16_sum(q));
+            xv.x = __fdiv_rn(xv.x, den), xv.y = __fdiv_rn(xv.y, den), xv.z = __fdiv_rn(xv.z, den), xv.w = __fdiv_rn(xv.w, den);
+        }
+        float q = xv.x * xv.x;
+        q = fmaf(xv.y, xv.y, q), q = fmaf(xv.z, xv.z, q), q = fmaf(xv.w, xv.w, q);
+        const float xn = half16_sum(q);
+        const int j = labels32 ? labels32[rr] : (int)labels64[rr];
+        const float dj = coop_dist(xv, xn, __ldg(reinterpret_cast<const float4 *>(c + (size_t)j * 64) + g), __ldg(cn + j));
+        if (live && g == 0) dist[row] = dj;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
-bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16 && ix->op != nullptr; }
+bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16 && ix->k <= 65536 && ix->op != nullptr; }
 
 int assign_tc_prepare(at_index *ix, cudaStream_t st) {
-    if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, 4 * sizeof(float)));
-    k_tc_scale<<<1, 1024, 0, st>>>(ix->c, ix->k * 64, ix->tc_scale);
+    if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, SC_COUNT * sizeof(float)));
+    k_tc_scale<<<1, 1024, 0, st>>>(ix->c, ix->cn, ix->k, ix->ext_sx, ix->tc_scale);
     AT_LAUNCH_OK();
     const int total = ix->ktiles * TN * 9;
     k_tc_prep<<<(total + 255) / 256, 256, 0, st>>>(ix->c, ix->cn, ix->k, ix->ktiles, ix->tc_scale,
@@ -587,53 +782,93 @@ int assign_tc_prepare(at_index *ix, cudaStream_t st) {
     return AT_OK;
 }
 
-int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32, int64_t *labels64,
-                     float *dist, cudaStream_t st) {
+void tc_rows_free(at_tc_rows *r) {
+    cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->tail_count);
+    *r = at_tc_rows();
+}
+
+// (Re)builds the operand image of x.  sx: device float, the image scale (a power of two).
+int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) {
         set_error("search: tensor path needs 16-byte aligned rows");
         return AT_ERR_UNSUPPORTED;
     }
+    if (n >= (1LL << 31)) {
+        set_error("search: tensor path takes fewer than 2^31 rows per call");
+        return AT_ERR_UNSUPPORTED;
+    }
+    const int64_t n_pad = (n + SROWS - 1) / SROWS * SROWS;
+    if (n_pad > r->cap) {
+        AT_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail);
+        r->img = nullptr, r->erow = r->xns = nullptr, r->tail = nullptr, r->cap = 0;
+        AT_CUDA_OK(cudaMalloc(&r->img, (size_t)(n_pad / TM) * A_TILE_BYTES));
+        AT_CUDA_OK(cudaMalloc(&r->erow, sizeof(float) * (size_t)n_pad));
+        AT_CUDA_OK(cudaMalloc(&r->xns, sizeof(float) * (size_t)n_pad));
+        AT_CUDA_OK(cudaMalloc(&r->tail, sizeof(uint2) * (size_t)n_pad));
+        if (!r->tail_count) AT_CUDA_OK(cudaMalloc(&r->tail_count, 2 * sizeof(unsigned int)));
+        r->cap = n_pad;
+    }
+    const int sms = sm_count() > 0 ? sm_count() : 1;
+    k_tc_rows<<<sms * 8, 256, 0, st>>>(x, n, n_pad, l2norm, sx, reinterpret_cast<unsigned char *>(r->img), r->erow, r->xns);
+    AT_LAUNCH_OK();
+    r->x = x, r->n = n, r->l2norm = l2norm;
+    return AT_OK;
+}
+
+// rows: a prepared image of exactly these rows (k-means), or nullptr to build one in the index's own workspace.
+int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32, int64_t *labels64,
+                     float *dist, int exact_dist, at_tc_rows *rows, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         configured = true;
     }
-    const int64_t ntiles = (n + TM - 1) / TM;
-    const int sms = sm_count() > 0 ? sm_count() : 1;
-    const unsigned char *op = reinterpret_cast<const unsigned char *>(ix->op);
-    const int nslices = (ix->ktiles + B_SLOTS - 1) / B_SLOTS;
-    const int mode = ix->tc_mode;  // 0 auto, 1 force stream, 2 force resident
-    const bool resident = mode == 2 ? nslices <= sms : (mode == 1 ? false : nslices <= 1);
-    if (resident) {
-        int workers = sms / nslices;
-        if (workers > ntiles) workers = (int)ntiles;
-        if (workers < 1) workers = 1;
-        if (nslices > 1 && (int64_t)nslices * n > ix->part_cap) {
-            AT_CUDA_OK(cudaStreamSynchronize(st));
-            cudaFree(ix->part_dist), cudaFree(ix->part_lab);
-            ix->part_dist = nullptr, ix->part_lab = nullptr, ix->part_cap = 0;
-            AT_CUDA_OK(cudaMalloc(&ix->part_dist, sizeof(float) * (size_t)nslices * n));
-            AT_CUDA_OK(cudaMalloc(&ix->part_lab, sizeof(int32_t) * (size_t)nslices * n));
-            ix->part_cap = (int64_t)nslices * n;
-        }
-        k_assign_tc<true><<<workers * nslices, TC_THREADS, TC_SMEM, st>>>(x, n, l2norm_rows, op, ix->ktiles, nslices, ix->k,
-                                                                         ix->c, ix->cn, ix->tc_scale, labels32, labels64,
-                                                                         dist, ix->part_dist, ix->part_lab);
-        AT_LAUNCH_OK();
-        if (nslices > 1) {
-            k_tc_merge<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ix->part_dist, ix->part_lab, n, nslices, labels32,
-                                                                    labels64, dist);
-            AT_LAUNCH_OK();
-        }
-        return AT_OK;
+    if (!rows) {
+        rows = &ix->rows;
+        int rc = tc_rows_build(rows, x, n, l2norm_rows, ix->tc_scale + SC_SX, st);
+        if (rc != AT_OK) return rc;
     }
+    // a distance request without labels still needs labels for the second pass
+    int32_t *l32 = labels32;
+    if (dist && exact_dist && !labels32 && !labels64) {
+        if (n > ix->part_cap) {
+            AT_CUDA_OK(cudaStreamSynchronize(st));
+            cudaFree(ix->part_lab);
+            ix->part_lab = nullptr, ix->part_cap = 0;
+            AT_CUDA_OK(cudaMalloc(&ix->part_lab, sizeof(int32_t) * (size_t)n));
+            ix->part_cap = n;
+        }
+        l32 = ix->part_lab;
+    }
+    const int64_t nsuper = (n + SROWS - 1) / SROWS;
+    const int sms = sm_count() > 0 ? sm_count() : 1;
     int grid = sms;
-    if (grid > ntiles) grid = (int)ntiles;
+    if (grid > nsuper) grid = (int)nsuper;
     if (grid < 1) grid = 1;
-    k_assign_tc<false><<<grid, TC_THREADS, TC_SMEM, st>>>(x, n, l2norm_rows, op, ix->ktiles, 1, ix->k, ix->c, ix->cn,
-                                                         ix->tc_scale, labels32, labels64, dist, nullptr, nullptr);
+    const unsigned char *op = reinterpret_cast<const unsigned char *>(ix->op);
+    const unsigned char *img = reinterpret_cast<const unsigned char *>(rows->img);
+    const int mode = ix->tc_mode;  // 0 auto, 1 force stream, 2 resident when the tiles fit
+    const bool resident = mode != 1 && ix->ktiles <= B_SLOTS;
+    float *kdist = (dist && exact_dist) ? nullptr : dist;
+    AT_CUDA_OK(cudaMemsetAsync(rows->tail_count, 0, 2 * sizeof(unsigned int), st));
+    if (resident)
+        k_assign_tc<true><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
+                                                            ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
+                                                            rows->tail_count, (unsigned int)rows->cap);
+    else
+        k_assign_tc<false><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
+                                                             ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
+                                                             rows->tail_count, (unsigned int)rows->cap);
     AT_LAUNCH_OK();
+    k_tc_tail<<<sms * 4, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
+                                      (unsigned int)rows->cap, l32, labels64, kdist, ix->tc_counters);
+    AT_LAUNCH_OK();
+    if (dist && exact_dist) {
+        k_exact_dist<<<sms * 8, 256, 0, st>>>(x, n, l2norm_rows, ix->c, ix->cn, l32, l32 ? nullptr : labels64, dist);
+        AT_LAUNCH_OK();
+    }
     return AT_OK;
 }
 

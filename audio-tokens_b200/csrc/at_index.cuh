@@ -4,6 +4,19 @@
 #include "at_common.cuh"
 #include <cuda_fp16.h>
 
+// Operand image of a set of rows for the tcgen05 search (at_assign_tc.cu: k_tc_rows) + the tail list of one search.
+struct at_tc_rows {
+    void *img = nullptr;        // (n_pad / 128) tiles of 20,480 bytes
+    float *erow = nullptr;      // (n_pad) |Sx delta| per row
+    float *xns = nullptr;       // (n_pad) Sx^2 |x|^2 per row
+    uint2 *tail = nullptr;      // (n_pad) uncertified rows of the last search
+    unsigned int *tail_count = nullptr;
+    int64_t cap = 0;            // rows allocated (multiple of 256)
+    const float *x = nullptr;   // what the image was built from
+    int64_t n = 0;
+    int l2norm = 0;
+};
+
 struct at_index {
     int d = 0;
     int k = 0;      // centroids currently held
@@ -13,10 +26,12 @@ struct at_index {
     // tcgen05 operands (d == 64 only): per 128-centroid tile one 36,864-byte image = hi | lo fp16 halves of
     // -2*S*c as 128x64 K-major SWIZZLE_128B tiles + a 128x16 no-swizzle tile carrying |c|^2 (at_assign_tc.cu)
     __half *op = nullptr;
-    float *tc_scale = nullptr;  // device: {S, S^2 / 4096}
-    int tc_mode = 0;            // 0 auto, 1 stream operand tiles, 2 keep them resident (K-sliced)
-    float *part_dist = nullptr; // (nslices, n) per-slice results of the K-sliced resident mode
-    int32_t *part_lab = nullptr;
+    float *tc_scale = nullptr;  // device: {S, -, 1 / S^2, tau, S max|c|, Sx, S / Sx}
+    const float *ext_sx = nullptr;  // device float: scale of an attached row image (k-means); nullptr = the index's own S
+    at_tc_rows rows;            // workspace of one-off searches
+    unsigned long long *tc_counters = nullptr;  // device: rows re-checked on 16 columns, rows scanned exactly (cumulative)
+    int tc_mode = 0;            // 0 auto, 1 stream operand tiles, 2 keep them resident when they fit
+    int32_t *part_lab = nullptr;  // scratch labels for a distance-only request
     int64_t part_cap = 0;
     int ktiles = 0;
 };
@@ -37,6 +52,11 @@ struct at_kmeans {
     unsigned long long *cursor = nullptr;  // k
     float *hassign = nullptr;   // k
     float *newc = nullptr;      // (k, d) scratch for finalize
+    // tensor path: operand image of the training rows, built at the first accumulate and re-used while the caller
+    // passes the same (x, n_local) -- the rows must not change between at_kmeans_begin and the last accumulate
+    at_tc_rows rows;
+    float *rows_sx = nullptr;   // device float: image scale, fixed by at_kmeans_begin from max |x|
+    bool rows_valid = false;
 };
 
 namespace at {
@@ -72,7 +92,9 @@ __device__ __forceinline__ float l2_denominator(float sumsq) { return __fadd_rn(
 // Implemented in at_assign_tc.cu.  Returns AT_ERR_UNSUPPORTED when the shape is outside the tensor path.
 int assign_tc_prepare(at_index *ix, cudaStream_t st);
 int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32,
-                     int64_t *labels64, float *dist, cudaStream_t st);
+                     int64_t *labels64, float *dist, int exact_dist, at_tc_rows *rows, cudaStream_t st);
+int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, cudaStream_t st);
+void tc_rows_free(at_tc_rows *r);
 bool assign_tc_supported(const at_index *ix);
 
 }  // namespace at

@@ -6,6 +6,7 @@
 //   accumulate  compute_centroids' per-cluster sums and counts (here: exact fixed-point, order independent)
 //   finalize    c = sum * (1/count); split_clusters with std::mt19937(1234), EPS = 1/1024
 #include "at_index.cuh"
+#include <stdlib.h>
 
 #include <math.h>
 #include <new>
@@ -419,8 +420,10 @@ static int launch_simt(const at_index *ix, const float *x, int64_t n, int l2norm
     return AT_OK;
 }
 
+// exact_dist: the tensor path reads certified rows' distances off the accumulator; 1 = re-evaluate them with the
+// canonical fp32 formula (what the public search returns), 0 = keep the read-out (k-means objective).
 static int index_search(at_index *ix, const float *x, int64_t n, int l2norm, int algo, int32_t *l32,
-                        int64_t *l64, float *dist, cudaStream_t st) {
+                        int64_t *l64, float *dist, int exact_dist, at_tc_rows *rows, cudaStream_t st) {
     if (n == 0) return AT_OK;
     bool tc = false;
     if (algo == AT_ALGO_TENSOR) {
@@ -433,7 +436,7 @@ static int index_search(at_index *ix, const float *x, int64_t n, int l2norm, int
         tc = assign_tc_supported(ix) && ix->k >= 64;
     }
     ProfScope prof(PROF_SEARCH, st);
-    if (tc) return assign_tc_search(ix, x, n, l2norm, l32, l64, dist, st);
+    if (tc) return assign_tc_search(ix, x, n, l2norm, l32, l64, dist, exact_dist, rows, st);
     return launch_simt(ix, x, n, l2norm, l32, l64, dist, st);
 }
 
@@ -470,7 +473,9 @@ int at_index_destroy(at_index *ix) {
     cudaFree(ix->cn);
     cudaFree(ix->op);
     cudaFree(ix->tc_scale);
-    cudaFree(ix->part_dist), cudaFree(ix->part_lab);
+    cudaFree(ix->tc_counters);
+    cudaFree(ix->part_lab);
+    tc_rows_free(&ix->rows);
     delete ix;
     return AT_OK;
 }
@@ -489,6 +494,10 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
         AT_CUDA_OK(cudaMalloc(&ix->cn, sizeof(float) * (size_t)k));
         if (ix->d == 64) {
             AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 36864));
+            if (!ix->tc_counters) {
+                AT_CUDA_OK(cudaMalloc(&ix->tc_counters, 8 * sizeof(unsigned long long)));
+                AT_CUDA_OK(cudaMemsetAsync(ix->tc_counters, 0, 8 * sizeof(unsigned long long), st));
+            }
         }
         ix->kcap = k;
     }
@@ -511,11 +520,23 @@ int at_index_set_tc_mode(at_index *ix, int mode) {
 }
 const float *at_index_centroids(const at_index *ix) { return ix ? ix->c : nullptr; }
 
+int at_index_tc_stats(at_index *ix, uint64_t out[2]) {
+    AT_REQUIRE(ix && out, "at_index_tc_stats: bad arguments");
+    out[0] = out[1] = 0;
+    if (!ix->tc_counters) return AT_OK;
+    AT_CUDA_OK(cudaDeviceSynchronize());
+    unsigned long long h[8];
+    AT_CUDA_OK(cudaMemcpy(h, ix->tc_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h[0], out[1] = h[1];
+    if (getenv("AT_TC_DEBUG")) fprintf(stderr, "tc counters: recheck %llu full %llu !groups %llu !sib %llu fallback %llu !third %llu\n", h[0], h[1], h[2], h[3], h[4], h[5]);
+    return AT_OK;
+}
+
 int at_index_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int algo, int32_t *labels32,
                     int64_t *labels64, float *dist, void *stream) {
     AT_REQUIRE(ix && (x || n == 0) && n >= 0, "at_index_search: bad arguments");
     AT_REQUIRE(ix->k > 0, "at_index_search: index is empty");
-    return index_search(ix, x, n, l2norm_rows, algo, labels32, labels64, dist, (cudaStream_t)stream);
+    return index_search(ix, x, n, l2norm_rows, algo, labels32, labels64, dist, 1, nullptr, (cudaStream_t)stream);
 }
 
 // ----------------------------------------------------------------------------------- k-means
@@ -548,6 +569,8 @@ int at_kmeans_destroy(at_kmeans *km) {
     at_index_destroy(km->index);
     cudaFree(km->labels), cudaFree(km->dist), cudaFree(km->order);
     cudaFree(km->off), cudaFree(km->cursor), cudaFree(km->hassign), cudaFree(km->newc);
+    cudaFree(km->rows_sx);
+    tc_rows_free(&km->rows);
     delete km;
     return AT_OK;
 }
@@ -584,6 +607,29 @@ int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total) {
     if (km->e_obj > 100) km->e_obj = 100;
     km->n_total = n_total;
     km->begun = true;
+    // tensor path: fix the scale of the rows' fp16 operand image (Sx max|x| in [64, 128)) and re-derive the centroid
+    // operands for it; the image itself is built by the first accumulate
+    km->rows_valid = false;
+    if (km->d == 64) {
+        float sx = 1.0f;
+        if (max_abs > 0.f) {
+            int ex;
+            frexpf(max_abs, &ex);       // max_abs = f * 2^ex, f in [0.5, 1)
+            int e = 7 - ex;             // max_abs * 2^e in [64, 128)
+            if (e > 60) e = 60;
+            if (e < -60) e = -60;
+            sx = ldexpf(1.0f, e);
+        }
+        AT_CUDA_OK(cudaDeviceSynchronize());
+        if (!km->rows_sx) AT_CUDA_OK(cudaMalloc(&km->rows_sx, sizeof(float)));
+        AT_CUDA_OK(cudaMemcpy(km->rows_sx, &sx, sizeof(float), cudaMemcpyHostToDevice));
+        km->index->ext_sx = km->rows_sx;
+        if (km->index->k > 0 && assign_tc_supported(km->index)) {
+            int rc = assign_tc_prepare(km->index, nullptr);
+            if (rc != AT_OK) return rc;
+            AT_CUDA_OK(cudaDeviceSynchronize());
+        }
+    }
     return AT_OK;
 }
 
@@ -616,7 +662,18 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     int rc = km_reserve(km, n_local, st);
     if (rc != AT_OK) return rc;
     int32_t *labels = labels32 ? labels32 : km->labels;
-    rc = index_search(km->index, x, n_local, 0, algo, labels, nullptr, km->dist, st);
+    // tensor path: the operand image of the rows is built once and re-used while (x, n_local) stay the same
+    at_tc_rows *rows = nullptr;
+    const bool tc = algo == AT_ALGO_TENSOR || (algo == AT_ALGO_AUTO && assign_tc_supported(km->index) && km->index->k >= 64);
+    if (tc && assign_tc_supported(km->index) && km->rows_sx) {
+        if (!km->rows_valid || km->rows.x != x || km->rows.n != n_local) {
+            rc = tc_rows_build(&km->rows, x, n_local, 0, km->rows_sx, st);
+            if (rc != AT_OK) return rc;
+            km->rows_valid = true;
+        }
+        rows = &km->rows;
+    }
+    rc = index_search(km->index, x, n_local, 0, algo, labels, nullptr, km->dist, 0, rows, st);
     if (rc != AT_OK) return rc;
     unsigned long long *acc = (unsigned long long *)accum;
     ProfScope prof(PROF_UPDATE, st);

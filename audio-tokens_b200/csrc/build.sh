@@ -5,7 +5,7 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../at_b200/libat_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /usr/bin/g++
-       -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -Xptxas -v)
+       -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -Xptxas -v ${AT_EXTRA_FLAGS:-})
 mkdir -p "$HERE/obj"
 pids=()
 for f in at_util at_kmeans at_mel at_assign_tc; do

@@ -320,8 +320,9 @@ def run_b200(args):
                     "frac": (ach / pk["tensor_sustained"]) if ach else None, "traffic": traffic,
                     "launches": n_search, "avg_ms": ms_search / max(n_search, 1),
                     "algorithmic_flops_per_launch": flops,
-                    "note": "algorithmic 2*N*K*D flops; the kernel executes 3.25x as many fp16 MMA flops (split-fp16 "
-                            "hi/lo products + one K-step carrying the norms); peak = bf16 sustained, " + pk["source"]}
+                    "note": "algorithmic 2*N*K*D flops; the kernel executes 2.25x as many fp16 MMA flops (fp16 rows x "
+                            "split-fp16 centroids + one K-step carrying the norms); avg_ms covers the search launches "
+                            "(row image when rebuilt + scan + tail); peak = bf16 sustained, " + pk["source"]}
         n_mel, ms_mel = prof["mel"]
         n_upd, ms_upd = prof["update"]
         mel_bytes = B * (L * 4 + T * N_MELS * 4)
@@ -340,7 +341,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": n_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (search contraction: split-fp16 tcgen05 MMA, fp32 accumulate + fp32 re-check)",
+            "vs_baseline": None, "dtype": "f32 (search contraction: fp16 x split-fp16 tcgen05 MMA, fp32 accumulate, certified or re-checked in fp32)",
             "data": "synthetic", "config": workload_config(args, world),
             "stages": {
                 "mel_frames_per_s": frames_local * world / (stage_ms[0] * 1e-3),

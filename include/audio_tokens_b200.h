@@ -112,15 +112,20 @@ int at_index_destroy(at_index *index);
  * (norms; for the tcgen05 path the split-fp16 tiles). */
 int at_index_set_centroids(at_index *index, const float *centroids, int k, void *stream);
 int at_index_ntotal(const at_index *index);
-/* Operand policy of the tcgen05 kernel: 0 auto (default), 1 stream centroid tiles through a ring for every row tile,
- * 2 keep up to 512 centroids per CTA resident in shared memory and split larger vocabularies into slices. */
+/* Operand policy of the tcgen05 kernel: 0 auto (default: resident when the operand tiles fit), 1 always stream
+ * centroid tiles through the shared-memory ring, 2 same as 0. */
 int at_index_set_tc_mode(at_index *index, int mode);
+/* Cumulative counters of the tcgen05 kernel (synchronises the device): out[0] = rows whose label was decided by the
+ * fp32 re-check of the two best column groups, out[1] = rows scanned exactly over all centroids.  Every other row
+ * was certified from the accumulator (at_assign_tc.cu, "Certification"). */
+int at_index_tc_stats(at_index *index, uint64_t out[2]);
 /* fp32 (k, d) centroids currently held (device pointer, valid until the next set / destroy). */
 const float *at_index_centroids(const at_index *index);
 /* search(x, 1).  l2norm_rows != 0 applies normalize_vectors to each row while loading.
  * Any of labels32 / labels64 / dist may be NULL.  algo: AT_ALGO_*; AUTO picks the tcgen05 kernel when
  * d == 64 and k >= 64, else the exact fp32 SIMT kernel.  Both return the argmin of the same fp32 formula
- * (the tensor path re-checks its top-2 candidates with it). */
+ * (the tensor path certifies each row from its accumulators or re-checks the candidates with it) and, in dist,
+ * that formula's value for the returned label. */
 int at_index_search(at_index *index, const float *x, int64_t n, int l2norm_rows, int algo,
                     int32_t *labels32, int64_t *labels64, float *dist, void *stream);
 
