@@ -133,13 +133,23 @@ __device__ __forceinline__ int64_t reflect_index(int64_t s, int64_t L) {
     return s;
 }
 
-constexpr int MEL_WARPS = 16;
-constexpr int MEL_THREADS = MEL_WARPS * 32;
+// A CTA holds MEL_GROUPS independent groups of MEL_WARPS warps.  Each group runs its own clips through its own
+// exchange / power / staging buffers and synchronises on its own named barrier, so one group's FFT phase overlaps the
+// other's mel projection, write-out and clip epilogue (one 16-warp group spends a third of its cycles at barriers).
+constexpr int MEL_GROUPS = 2;
+constexpr int MEL_WARPS = 8;                            // per group
+constexpr int MEL_THREADS = MEL_WARPS * 32;             // per group
+constexpr int CTA_THREADS = MEL_GROUPS * MEL_THREADS;
 constexpr int XCH_STRIDE = 33;                          // floats per exchange row (32 + 1 pad)
 constexpr int XCH_WARP_F = 32 * XCH_STRIDE;             // floats per warp (real and imaginary parts go through in turn)
-constexpr int XCH_BYTES = MEL_WARPS * XCH_WARP_F * 4;   // 67,584
-constexpr int STAGE_FLOATS = 16896;                     // staged sample window: 31 * 512 + 1024 samples (67,584 B)
+constexpr int XCH_BYTES = MEL_WARPS * XCH_WARP_F * 4;   // 33,792 per group
+constexpr int STAGE_FLOATS = 8704;                      // staged sample window: 15 * 512 + 1024 samples (34,816 B) per group
 constexpr int WT_SMEM_FLOATS = 2048;                    // filterbank weights kept in shared memory when they fit
+constexpr int PAR_SMEM_MELS = 256;                      // filter parameters (first bin, groups of four, weight offset)
+
+__device__ __forceinline__ void group_sync(int grp) {   // named barrier 1 + grp over the group's 256 threads
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(MEL_THREADS) : "memory");
+}
 
 template <int LOG2NF>
 struct MelCfg {
@@ -151,13 +161,17 @@ struct MelCfg {
     static constexpr int BF = MEL_WARPS * FR;  // frames per batch
     static constexpr int NB = NF / 2 + 1;    // bins
     static constexpr int P_FLOATS = BF * NB;
-    // [exchange | power tile | twiddles | window | staged samples]; the dB tile aliases exchange + power-tile space
+    // per group: [exchange | power tile | staged samples] (the dB tile aliases exchange + power-tile space);
+    // then, shared by the groups: [twiddles | window | filter weights | filter parameters]
     static constexpr size_t OFF_P = XCH_BYTES;
-    static constexpr size_t OFF_TW = OFF_P + (size_t)P_FLOATS * 4;
+    static constexpr size_t OFF_STAGE = (OFF_P + (size_t)P_FLOATS * 4 + 127) & ~(size_t)127;
+    static constexpr size_t GROUP_BYTES = OFF_STAGE + (size_t)STAGE_FLOATS * 4;
+    static constexpr size_t OFF_TW = MEL_GROUPS * GROUP_BYTES;
     static constexpr size_t OFF_WIN = OFF_TW + (size_t)N2 * 32 * 8;
-    static constexpr size_t OFF_STAGE = (OFF_WIN + (size_t)NF * 4 + 127) & ~(size_t)127;
-    static constexpr size_t OFF_WT = OFF_STAGE + (size_t)STAGE_FLOATS * 4;
-    static constexpr size_t SMEM = OFF_WT + (size_t)WT_SMEM_FLOATS * 4;
+    static constexpr size_t OFF_WT = OFF_WIN + (size_t)NF * 4;
+    static constexpr size_t OFF_PAR = OFF_WT + (size_t)WT_SMEM_FLOATS * 4;
+    static constexpr size_t SMEM = OFF_PAR + (size_t)PAR_SMEM_MELS * 3 * 4;
+    static_assert(GROUP_BYTES % 128 == 0 && SMEM <= 232448, "shared memory layout");
 };
 
 // One unit of CTA work: a batch of BF consecutive frames of one clip.
@@ -171,7 +185,7 @@ struct MelItem {
 };
 
 template <int LOG2NF>
-__global__ void __launch_bounds__(MEL_THREADS, 1)
+__global__ void __launch_bounds__(CTA_THREADS, 1)
 k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets,
       const int64_t *__restrict__ frame_offsets, int64_t uniform_samples, int B, int hop, int n_mels,
       int normalize, const float *__restrict__ g_win, const float2 *__restrict__ g_tw,
@@ -181,29 +195,38 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
     using C = MelCfg<LOG2NF>;
     constexpr int NF = C::NF, N2 = C::N2, G = C::G, FR = C::FR, BF = C::BF, NB = C::NB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *xch_all = reinterpret_cast<float *>(smem_raw);
-    float *dtile = reinterpret_cast<float *>(smem_raw);  // aliases the exchange region (mel stage only)
-    float *ptile = reinterpret_cast<float *>(smem_raw + C::OFF_P);
+    const int grp = threadIdx.x / MEL_THREADS;            // group of this thread
+    const int tid = threadIdx.x % MEL_THREADS, lane = tid & 31, warp = tid >> 5;   // position inside the group
+    unsigned char *gsm = smem_raw + (size_t)grp * C::GROUP_BYTES;
+    float *xch_all = reinterpret_cast<float *>(gsm);
+    float *dtile = reinterpret_cast<float *>(gsm);  // aliases the exchange region (mel stage only)
+    float *ptile = reinterpret_cast<float *>(gsm + C::OFF_P);
+    float *s_stage = reinterpret_cast<float *>(gsm + C::OFF_STAGE);
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw + C::OFF_TW);
     float *s_win = reinterpret_cast<float *>(smem_raw + C::OFF_WIN);
-    float *s_stage = reinterpret_cast<float *>(smem_raw + C::OFF_STAGE);
     float *s_wt = reinterpret_cast<float *>(smem_raw + C::OFF_WT);
-    __shared__ float s_red[2][MEL_WARPS];
-    __shared__ int s_flag;
-    __shared__ __align__(8) unsigned long long s_bar;
+    int *s_par = reinterpret_cast<int *>(smem_raw + C::OFF_PAR);   // [m]{first bin, groups of four, weight offset}
+    __shared__ float s_red_all[MEL_GROUPS][2][MEL_WARPS];
+    __shared__ int s_flag_all[MEL_GROUPS];
+    __shared__ __align__(8) unsigned long long s_bar_all[MEL_GROUPS];
+    float (*s_red)[MEL_WARPS] = s_red_all[grp];
+    int &s_flag = s_flag_all[grp];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < N2 * 32; i += MEL_THREADS) s_tw[i] = g_tw[i];
-    for (int i = tid; i < NF; i += MEL_THREADS) s_win[i] = g_win[i];
-    const bool wt_in_smem = wt_count <= WT_SMEM_FLOATS;
-    if (wt_in_smem)
-        for (int i = tid; i < wt_count; i += MEL_THREADS) s_wt[i] = wt[i];
-    const uint32_t bar = smem_u32(&s_bar);
+    for (int i = threadIdx.x; i < N2 * 32; i += CTA_THREADS) s_tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < NF; i += CTA_THREADS) s_win[i] = g_win[i];
+    const bool wt_in_smem = wt_count <= WT_SMEM_FLOATS && n_mels <= PAR_SMEM_MELS;
+    if (wt_in_smem) {
+        for (int i = threadIdx.x; i < wt_count; i += CTA_THREADS) s_wt[i] = wt[i];
+        for (int i = threadIdx.x; i < n_mels; i += CTA_THREADS)
+            s_par[3 * i] = fstart[i], s_par[3 * i + 1] = fcnt[i], s_par[3 * i + 2] = woff[i];
+    }
+    const uint32_t bar = smem_u32(&s_bar_all[grp]);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const int n_groups = (int)gridDim.x * MEL_GROUPS;     // clips are dealt round-robin to the groups of the grid
 
     float *xch = xch_all + warp * XCH_WARP_F;
     const int dstride = n_mels + 4;  // rows stay 16-byte aligned for the vector write-out
@@ -224,7 +247,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
             if (it.L > NF / 2) return true;
             // torch's reflect pad raises when the pad is not smaller than the input: flag 2, no output
             if (tid == 0 && bad_flags) bad_flags[it.clip] = 2;
-            it.clip += gridDim.x;
+            it.clip += n_groups;
         }
         return false;
     };
@@ -241,7 +264,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
         if (cur.t0 + BF < cur.T) {
             nx.t0 = cur.t0 + BF;
         } else {
-            nx.clip = cur.clip + gridDim.x;
+            nx.clip = cur.clip + n_groups;
             nx.t0 = 0;
             if (!load_clip(nx)) return false;
         }
@@ -256,7 +279,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
     };
 
     MelItem cur;
-    cur.clip = blockIdx.x;
+    cur.clip = (int)blockIdx.x * MEL_GROUPS + grp;
     cur.t0 = 0;
     bool have = load_clip(cur);
     if (have) {
@@ -358,24 +381,28 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 pb[NF / 2] = 4.f * Zi * Zi;
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // the staged window has been consumed by every warp: start fetching the next batch's window now, it lands
         // while this batch goes through the mel projection and the write-out
         if (tid == 0 && have_next) issue_stage(nxt);
         // ------------------------------------------------------------ phase C: sparse mel + dB
         {
-            constexpr int FG = BF / 32;  // frame groups of 32
-            for (int item = warp; item < FG * n_mels; item += MEL_WARPS) {
-                const int fg = item % FG, m = item / FG;
-                const int f = fg * 32 + lane;
-                const float *prow = ptile + (size_t)f * NB + fstart[m];
-                const int cnt4 = fcnt[m];
+            // a warp item = FPW frames x MPW filters (lanes <-> frames first: power-tile rows are 513 floats apart,
+            // conflict-free; with 16-frame batches the two half-warps take two adjacent filters)
+            constexpr int FPW = BF < 32 ? BF : 32, MPW = 32 / FPW, FG = BF / FPW;
+            const int mgroups = (n_mels + MPW - 1) / MPW;
+            for (int item = warp; item < FG * mgroups; item += MEL_WARPS) {
+                const int fg = item % FG, m = (item / FG) * MPW + lane / FPW;
+                const int f = fg * FPW + lane % FPW;
+                if (m >= n_mels) continue;
+                const float *prow = ptile + (size_t)f * NB + (wt_in_smem ? s_par[3 * m] : fstart[m]);
+                const int cnt4 = wt_in_smem ? s_par[3 * m + 1] : fcnt[m];
                 float acc = 0.f;
                 if (wt_in_smem) {
-                    const float4 *w4 = reinterpret_cast<const float4 *>(s_wt + woff[m]);
+                    const float4 *w4 = reinterpret_cast<const float4 *>(s_wt + s_par[3 * m + 2]);
 #pragma unroll 2
                     for (int i = 0; i < cnt4; i++) {
-                        const float4 w = w4[i];  // broadcast: every lane reads the same filter segment
+                        const float4 w = w4[i];  // broadcast: the lanes of a filter read the same segment
                         acc = fmaf(w.x, prow[4 * i], acc);
                         acc = fmaf(w.y, prow[4 * i + 1], acc);
                         acc = fmaf(w.z, prow[4 * i + 2], acc);
@@ -388,15 +415,15 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 dtile[f * dstride + m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
             }
         }
-        __syncthreads();
+        group_sync(grp);
         // ------------------------------------------------------------ phase D: coalesced write-out
         {
             const int nf = (int)min((int64_t)BF, T - t0);
             float *o = dst + t0 * n_mels;
             if ((n_mels & 3) == 0) {
-                const int q4 = n_mels >> 2;  // float4 per frame; a warp takes whole frames (no integer division)
-                for (int f = warp; f < nf; f += MEL_WARPS) {
-                    for (int j = lane; j < q4; j += 32) {
+                const int q4 = n_mels >> 2;  // float4 per frame; a half-warp takes whole frames (no integer division)
+                for (int f = warp * 2 + (lane >> 4); f < nf; f += MEL_WARPS * 2) {
+                    for (int j = lane & 15; j < q4; j += 16) {
                         const float4 v = *reinterpret_cast<const float4 *>(dtile + f * dstride + 4 * j);
                         vmin = fminf(fminf(vmin, v.x), fminf(fminf(v.y, v.z), v.w));
                         vmax = fmaxf(fmaxf(vmax, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
@@ -416,7 +443,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 }
             }
         }
-        __syncthreads();
+        group_sync(grp);
 
         if (t0 + BF >= T) {
             // ---------------------------------------------------------------- clip epilogue
@@ -424,7 +451,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
             vmax = warp_max(vmax);
             if (lane == 0) s_red[0][warp] = vmin, s_red[1][warp] = vmax;
             if (tid == 0) s_flag = 0;
-            __syncthreads();
+            group_sync(grp);
             float mn = s_red[0][0], mx = s_red[1][0];
 #pragma unroll
             for (int w = 1; w < MEL_WARPS; w++) mn = fminf(mn, s_red[0][w]), mx = fmaxf(mx, s_red[1][w]);
@@ -440,6 +467,30 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                     const bool live = r < T;
                     float *row = dst + (live ? r : 0) * n_mels;
                     float q = 0.f;
+                    if (vec && n_mels <= 64) {   // one float4 per lane (the 64-mel configuration of the reference)
+                        const bool on = live && 4 * g < n_mels;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (on) v = __ldcg(reinterpret_cast<const float4 *>(row + 4 * g));
+                        if (normalize) {
+                            v.x = __fmul_rn(__fsub_rn(v.x, mn), inv_range), v.y = __fmul_rn(__fsub_rn(v.y, mn), inv_range);
+                            v.z = __fmul_rn(__fsub_rn(v.z, mn), inv_range), v.w = __fmul_rn(__fsub_rn(v.w, mn), inv_range);
+                            if (on) {
+                                nonfinite |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+                                *reinterpret_cast<float4 *>(row + 4 * g) = v;
+                            } else {
+                                v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
+                        if (out_l2) {
+                            q = v.x * v.x;
+                            q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
+                            const float den = l2_denominator(half16_sum(q));
+                            if (on)
+                                *reinterpret_cast<float4 *>(out_l2 + (cur.f0 + r) * n_mels + 4 * g) =
+                                    make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
+                        }
+                        continue;
+                    }
                     if (vec) {
                         float4 v[4];
 #pragma unroll
@@ -510,9 +561,9 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 }
             }
             if (nonfinite) s_flag = 1;
-            __syncthreads();
+            group_sync(grp);
             if (tid == 0 && bad_flags) bad_flags[cur.clip] = s_flag;
-            __syncthreads();
+            group_sync(grp);
             vmin = INFINITY, vmax = -INFINITY, nonfinite = 0;
         }
         cur = nxt;
@@ -600,10 +651,10 @@ static int launch_mel(at_mel_plan *p, const float *wave, const int64_t *so, cons
         configured = true;
     }
     int grid = sm_count();
-    if (grid > B) grid = B;
+    if (grid > (B + MEL_GROUPS - 1) / MEL_GROUPS) grid = (B + MEL_GROUPS - 1) / MEL_GROUPS;
     if (grid < 1) grid = 1;
     ProfScope prof(PROF_MEL, st);
-    k_mel<LOG2NF><<<grid, MEL_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->win,
+    k_mel<LOG2NF><<<grid, CTA_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->win,
                                                      p->tw, p->fstart, p->fcnt, p->woff, p->wt, p->wt_count, out, out_l2,
                                                      bad);
     AT_LAUNCH_OK();
@@ -623,8 +674,8 @@ int at_mel_plan_create(int sample_rate, int n_fft, int hop_length, int n_mels, i
         set_error("at_mel_plan_create: n_fft=%d is not covered (256, 512, 1024 are)", n_fft);
         return AT_ERR_UNSUPPORTED;
     }
-    // the dB tile of one batch (16 * 2048 / n_fft frames x (n_mels + 1) floats) must fit the 67,584-byte exchange area
-    const int max_mels = 67584 / (4 * (16 * 2048 / n_fft)) - 4 < 256 ? 67584 / (4 * (16 * 2048 / n_fft)) - 4 : 256;
+    // the dB tile of one batch (8 * 2048 / n_fft frames x (n_mels + 4) floats) must fit a group's 33,792-byte exchange area
+    const int max_mels = 33792 / (4 * (8 * 2048 / n_fft)) - 4 < 256 ? 33792 / (4 * (8 * 2048 / n_fft)) - 4 : 256;
     if (n_mels > max_mels) {
         set_error("at_mel_plan_create: n_mels=%d > %d is not covered for n_fft=%d", n_mels, max_mels, n_fft);
         return AT_ERR_UNSUPPORTED;
