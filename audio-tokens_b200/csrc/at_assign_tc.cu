@@ -44,35 +44,37 @@
 //
 // Roofline note: 2*N*K*64 algorithmic flops are executed as 2.25x that many fp16 MMA flops.
 //
-// k_assign_tc: persistent CTAs (one per SM), 12 warps; the unit of work is a SUPER TILE of 256 rows (two 128-row MMA
-// tiles) so every centroid operand tile fetched from L2 is used twice:
-//   warp 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into a 3-slot ring (or once, when all
+// k_assign_tc: persistent CTAs (one per SM), 16 warps; the unit of work is a SUPER TILE of 384 rows (three 128-row MMA
+// tiles) so every centroid operand tile fetched from L2 is used three times and every scheduler holds three scanning
+// warps (the scan is alu-pipe work: a third warp per scheduler hides its dependent-issue latency):
+//   warp 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into a 2-slot ring (or once, when all
 //            tiles fit: RESIDENT)
 //   warp 1   issues tcgen05.mma, commits to mbarriers
-//   warp 2   TMEM allocation / deallocation (all 512 columns: 2 row tiles x 2 accumulator stages)
-//   warp 3   bulk-copies the row operand image, one 40 KB super tile at a time, double-buffered
-//   warps 4-11  epilogue: warps 4-7 scan row tile 0, warps 8-11 row tile 1 (tcgen05.ld -> keys -> top-3 / top-2)
+//   warp 2   TMEM allocation / deallocation (all 512 columns = a ring of four 128-column accumulators)
+//   warp 3   bulk-copies the row operand image, one 60 KB super tile at a time, double-buffered
+//   warps 4-15  epilogue: warps 4-7 scan row tile 0, 8-11 row tile 1, 12-15 row tile 2 (tcgen05.ld -> keys -> top-3 / top-2)
 // Producer, MMA and row-image warps run their loops converged and issue from one elected lane (uniform operands).
 #include "at_index.cuh"
 #include "at_ptx.cuh"
 
 namespace at {
 
-constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS = 512;
 constexpr int TM = 128;          // rows per MMA tile (UMMA M)
 constexpr int TN = 128;          // centroids per tile (UMMA N)
-constexpr int RT = 2;            // row tiles per super tile
-constexpr int SROWS = RT * TM;   // 256
-constexpr int B_SLOTS = 3;       // operand tiles resident per CTA / ring depth
+constexpr int RT = 3;            // row tiles per super tile
+constexpr int SROWS = RT * TM;   // 384
+constexpr int B_SLOTS = 2;       // operand tiles resident per CTA / ring depth
+constexpr int ACC_SLOTS = 4;     // 128-column accumulators in TMEM, used as a ring by consecutive (centroid tile, row tile) pairs
 constexpr uint32_t A_MAIN_BYTES = TM * 128;              // 128 rows x 64 fp16
 constexpr uint32_t AUG_BYTES = TM * 32;                  // 128 rows x 16 fp16, no-swizzle core matrices
 constexpr uint32_t A_TILE_BYTES = A_MAIN_BYTES + AUG_BYTES;      // 20,480
-constexpr uint32_t A_BUF_BYTES = RT * A_TILE_BYTES;              // 40,960
+constexpr uint32_t A_BUF_BYTES = RT * A_TILE_BYTES;              // 61,440
 constexpr uint32_t B_TILE_BYTES = 2 * TN * 128 + TN * 32;        // hi | lo | aug = 36,864
 
 // shared memory map (dynamic, 1024-B aligned base)
 constexpr uint32_t OFF_A = 0;                                    // 2 buffers
-constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 3 slots
+constexpr uint32_t OFF_B = OFF_A + 2 * A_BUF_BYTES;              // 2 slots
 constexpr uint32_t OFF_BAR = OFF_B + B_SLOTS * B_TILE_BYTES;     // mbarriers
 constexpr uint32_t TC_SMEM = OFF_BAR + 256 + 1024;               // + slack for manual 1024-B alignment
 static_assert(OFF_A % 1024 == 0 && OFF_B % 1024 == 0 && A_TILE_BYTES % 1024 == 0 && B_TILE_BYTES % 1024 == 0, "align");
@@ -83,7 +85,7 @@ enum {
     BAR_A_EMPTY = 2,     // +2   (MMA commit)
     BAR_B_FULL = 4,      // +3   (bulk copy tx)
     BAR_B_EMPTY = 7,     // +3   (MMA commit)
-    BAR_ACC_FULL = 10,   // +4   [stage*2 + row tile]  (MMA commit)
+    BAR_ACC_FULL = 10,   // +4   [accumulator slot]  (MMA commit)
     BAR_ACC_EMPTY = 14,  // +4   (4 epilogue warps)
     BAR_COUNT = 18
 };
@@ -471,7 +473,6 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             const uint32_t a0 = base + OFF_A + ab * A_BUF_BYTES;
             for (int jt = 0; jt < ktiles; jt++, u++) {
                 const uint32_t slot = RESIDENT ? (uint32_t)jt : st;
-                const uint32_t stage = u & 1, aph = (u >> 1) & 1;
                 if (!RESIDENT || i == 0) mbar_wait(BAR(BAR_B_FULL + slot), RESIDENT ? 0u : bph);
                 const uint32_t b_hi = base + OFF_B + slot * B_TILE_BYTES;
                 const uint64_t dB_hi = desc_sw128(b_hi), dB_lo = desc_sw128(b_hi + TN * 128), dB_aug = desc_nosw(b_hi + 2 * TN * 128);
@@ -479,16 +480,17 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 for (int rt = 0; rt < RT; rt++) {
                     const uint32_t a_hi = a0 + rt * A_TILE_BYTES;
                     const uint64_t dA = desc_sw128(a_hi), dA_aug = desc_nosw(a_hi + A_MAIN_BYTES);
-                    mbar_wait(BAR(BAR_ACC_EMPTY + stage * 2 + rt), aph ^ 1);
+                    const uint32_t v = u * RT + rt, acc = v % ACC_SLOTS, aph = (v / ACC_SLOTS) & 1;
+                    mbar_wait(BAR(BAR_ACC_EMPTY + acc), aph ^ 1);
                     tc_fence_after();
-                    const uint32_t d = tmem + (stage * 2 + rt) * TN;
+                    const uint32_t d = tmem + acc * TN;
                     // descriptor start addresses are in 16-byte units: a K step of 16 fp16 = 32 bytes = +2
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_hi + 2 * kk, IDESC, kk > 0);
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_lo + 2 * kk, IDESC, 1);
                     umma_f16(d, dA_aug, dB_aug, IDESC, 1);
-                    umma_commit(BAR(BAR_ACC_FULL + stage * 2 + rt));
+                    umma_commit(BAR(BAR_ACC_FULL + acc));
                 }
                 if (!RESIDENT) {
                     umma_commit(BAR(BAR_B_EMPTY + slot));
@@ -518,16 +520,17 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             // Accumulator read-out in eight 16-column loads through four register buffers: two loads are always in flight
             // behind two folds, and the first two loads of the NEXT tile are issued before the last two folds of this one.
             if (!primed) {   // very first tile of this warp
-                mbar_wait(BAR(BAR_ACC_FULL + (u & 1) * 2 + rt), (u >> 1) & 1);
+                const uint32_t v0 = u * RT + rt;
+                mbar_wait(BAR(BAR_ACC_FULL + v0 % ACC_SLOTS), (v0 / ACC_SLOTS) & 1);
                 tc_fence_after();
-                const uint32_t ta = tmem + lane_addr + ((u & 1) * 2 + rt) * TN;
+                const uint32_t ta = tmem + lane_addr + (v0 % ACC_SLOTS) * TN;
                 tmem_ld16(ta, c0);
                 tmem_ld16(ta + 16, c1);
                 primed = true;
             }
             for (int jt = 0; jt < ktiles; jt++, u++) {
-                const uint32_t stage = u & 1;
-                const uint32_t ta = tmem + lane_addr + (stage * 2 + rt) * TN;
+                const uint32_t acc = (u * RT + rt) % ACC_SLOTS;
+                const uint32_t ta = tmem + lane_addr + acc * TN;
                 uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;
                 uint32_t bp[8];
 #pragma unroll
@@ -550,12 +553,12 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + stage * 2 + rt));  // accumulator is in registers: free it early
+                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + acc));  // accumulator is in registers: free it early
                 // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
                 const bool more = (jt + 1 < ktiles) || (i + 1 < my_tiles);
-                const uint32_t un = u + 1;
-                const uint32_t nbar = BAR(BAR_ACC_FULL + (un & 1) * 2 + rt), nph = (un >> 1) & 1;
-                const uint32_t tn = tmem + lane_addr + ((un & 1) * 2 + rt) * TN;
+                const uint32_t vn = (u + 1) * RT + rt;
+                const uint32_t nbar = BAR(BAR_ACC_FULL + vn % ACC_SLOTS), nph = (vn / ACC_SLOTS) & 1;
+                const uint32_t tn = tmem + lane_addr + (vn % ACC_SLOTS) * TN;
                 bool started = false;
                 if (more && mbar_test(nbar, nph)) {   // warp-uniform: every lane probes the same barrier
                     tc_fence_after();
