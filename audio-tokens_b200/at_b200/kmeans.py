@@ -103,6 +103,10 @@ class LloydTrainer:
         assert c.is_cuda and c.dtype == torch.float32 and tuple(c.shape) == (self.k, self.d) and c.is_contiguous()
         _lib.check(self.lib.at_kmeans_set_centroids(self.h, _lib.ptr(c), _lib.stream_ptr()))
 
+    def set_incremental(self, on: bool):
+        """Incremental update (only rows whose label changed move between the exact integer sums) on / off."""
+        _lib.check(self.lib.at_kmeans_set_incremental(self.h, int(bool(on))))
+
     def get_centroids(self):
         import torch
 

@@ -57,6 +57,17 @@ struct at_kmeans {
     at_tc_rows rows;
     float *rows_sx = nullptr;   // device float: image scale, fixed by at_kmeans_begin from max |x|
     bool rows_valid = false;
+    // incremental update: the local sums / counts persist between accumulate calls (exact integers), so an iteration
+    // only moves the rows whose label changed: -x from the old cluster, +x to the new one (same invariant on x as above)
+    unsigned long long *lacc = nullptr;    // k*d sums + k counts
+    int32_t *prev = nullptr;               // labels of the previous accumulate (ncap)
+    const float *prev_x = nullptr;
+    int64_t prev_n = 0;
+    bool prev_valid = false;
+    bool incremental_on = true;
+    int32_t *d_row = nullptr, *d_lab = nullptr, *d_order = nullptr;   // 2 items per changed row (2 * ncap)
+    unsigned int *d_count = nullptr;       // device: changed rows of the last accumulate
+    unsigned long long *d_hist = nullptr;  // k
 };
 
 namespace at {

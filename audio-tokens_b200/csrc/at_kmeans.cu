@@ -175,7 +175,67 @@ __global__ void k_objective(const float *__restrict__ dist, int64_t n, float obj
     }
 }
 
-__global__ void k_counts(const int32_t *__restrict__ labels, int64_t n, unsigned long long *__restrict__ counts) {
+// Rows whose label changed since the previous accumulate: two delta items each (leave the old cluster, join the new
+// one), prev updated; the objective is summed on the way (as k_objective).  List slots are reserved once per block
+// step (a per-warp atomic on the single counter serialises in L2).
+__global__ void __launch_bounds__(256) k_diff(const int32_t *__restrict__ labels, int32_t *__restrict__ prev,
+                                              const float *__restrict__ dist, int64_t n, float obj_scale,
+                                              int32_t *__restrict__ d_row, int32_t *__restrict__ d_lab,
+                                              unsigned int *__restrict__ d_count, unsigned long long *__restrict__ obj_word) {
+    __shared__ unsigned int s_cnt[8];
+    __shared__ unsigned int s_base;
+    __shared__ long long ws[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long local = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {   // block-uniform trip count
+        const int64_t i = base + threadIdx.x;
+        bool changed = false;
+        int l = 0, p = 0;
+        if (i < n) {
+            l = labels[i], p = prev[i];
+            changed = l != p;
+            local += __float2ll_rn(dist[i] * obj_scale);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, changed);
+        if (lane == 0) s_cnt[w] = (unsigned int)__popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int tot = 0;
+            for (int q = 0; q < 8; q++) {
+                const unsigned int c = s_cnt[q];
+                s_cnt[q] = tot;
+                tot += c;
+            }
+            s_base = tot ? atomicAdd(d_count, tot) : 0u;
+        }
+        __syncthreads();
+        if (changed) {
+            const unsigned int s = s_base + s_cnt[w] + __popc(m & ((1u << lane) - 1u));
+            d_row[2 * s] = (int32_t)((uint32_t)i | 0x80000000u), d_lab[2 * s] = p;
+            d_row[2 * s + 1] = (int32_t)i, d_lab[2 * s + 1] = l;
+            prev[i] = l;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0) ws[w] = local;
+    __syncthreads();
+    if (w == 0) {
+        long long v = lane < 8 ? ws[lane] : 0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(obj_word, (unsigned long long)v);
+    }
+}
+
+// Delta form (items != nullptr): besides the histogram of the items, the persistent per-cluster counts move by -1 /
+// +1 per item (bit 31 of the item = the row leaves the cluster).
+__global__ void k_counts(const int32_t *__restrict__ labels, int64_t n, unsigned long long *__restrict__ counts,
+                         const unsigned int *__restrict__ n_dev = nullptr, int n_mult = 1,
+                         const int32_t *__restrict__ items = nullptr, unsigned long long *__restrict__ lcounts = nullptr) {
+    if (n_dev) n = (int64_t)n_mult * (int64_t)*n_dev;
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     // warp-uniform trip count so the full-mask match below is always convergent
@@ -185,6 +245,14 @@ __global__ void k_counts(const int32_t *__restrict__ labels, int64_t n, unsigned
         // warp-aggregate identical labels before touching L2
         unsigned peers = __match_any_sync(0xffffffffu, l);
         if (l >= 0 && (__ffs(peers) - 1) == lane) atomicAdd(&counts[l], (unsigned long long)__popc(peers));
+        if (items) {
+            const int leaves = (i < n) ? (int)((uint32_t)items[i] >> 31) : 0;
+            const unsigned peers2 = __match_any_sync(0xffffffffu, 2 * l + leaves);
+            if (l >= 0 && (__ffs(peers2) - 1) == lane) {
+                const unsigned long long c = (unsigned long long)__popc(peers2);
+                atomicAdd(&lcounts[l], leaves ? (0ULL - c) : c);
+            }
+        }
     }
 }
 
@@ -217,7 +285,8 @@ __global__ void k_scan_counts(const unsigned long long *__restrict__ counts, int
 
 // order[cursor[label]++] = row  (order within a cluster is arbitrary: the sums below are exact integers)
 __global__ void k_place(const int32_t *__restrict__ labels, int64_t n, unsigned long long *__restrict__ cursor,
-                        int32_t *__restrict__ order) {
+                        int32_t *__restrict__ order, const unsigned int *__restrict__ n_dev = nullptr, int n_mult = 1) {
+    if (n_dev) n = (int64_t)n_mult * (int64_t)*n_dev;
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
@@ -234,11 +303,16 @@ __global__ void k_place(const int32_t *__restrict__ labels, int64_t n, unsigned 
 
 // Each warp owns an equal slice of the cluster-grouped order[] array and accumulates x rows as int64
 // fixed point (x * 2^e_sum), flushing to sums[c] with 64-bit atomics whenever the cluster changes.
+// Delta form (items != nullptr): order[] indexes items[], an item is a row with bit 31 set when the row LEAVES the
+// cluster (its value is subtracted); the item count is 2 * *n_dev.
 template <int DPL>  // dims per lane = ceil(d / 32)
 __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x, int d,
                                                     const int32_t *__restrict__ order,
                                                     const int64_t *__restrict__ off, int k, int64_t n,
-                                                    float scale, unsigned long long *__restrict__ sums) {
+                                                    float scale, unsigned long long *__restrict__ sums,
+                                                    const int32_t *__restrict__ items = nullptr,
+                                                    const unsigned int *__restrict__ n_dev = nullptr) {
+    if (n_dev) n = 2 * (int64_t)*n_dev;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -262,8 +336,17 @@ __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x,
     for (int64_t p = p0; p < p1; p += U) {
         int32_t rows[U];
         float v[U][DPL];
+        float sgn[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) rows[u] = (p + u < p1) ? order[p + u] : -1;
+        for (int u = 0; u < U; u++) {
+            rows[u] = (p + u < p1) ? order[p + u] : -1;
+            sgn[u] = scale;
+            if (items && rows[u] >= 0) {
+                const uint32_t it = (uint32_t)items[rows[u]];
+                rows[u] = (int32_t)(it & 0x7FFFFFFFu);
+                if (it >> 31) sgn[u] = -scale;
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; u++) {
 #pragma unroll
@@ -286,7 +369,7 @@ __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x,
                 cend = off[c + 1];
             }
 #pragma unroll
-            for (int w = 0; w < DPL; w++) acc[w] += __float2ll_rn(v[u][w] * scale);
+            for (int w = 0; w < DPL; w++) acc[w] += __float2ll_rn(v[u][w] * sgn[u]);
         }
     }
 #pragma unroll
@@ -571,12 +654,22 @@ int at_kmeans_destroy(at_kmeans *km) {
     cudaFree(km->off), cudaFree(km->cursor), cudaFree(km->hassign), cudaFree(km->newc);
     cudaFree(km->rows_sx);
     tc_rows_free(&km->rows);
+    cudaFree(km->lacc), cudaFree(km->prev), cudaFree(km->d_row), cudaFree(km->d_lab), cudaFree(km->d_order);
+    cudaFree(km->d_count), cudaFree(km->d_hist);
     delete km;
+    return AT_OK;
+}
+
+int at_kmeans_set_incremental(at_kmeans *km, int on) {
+    AT_REQUIRE(km, "at_kmeans_set_incremental: bad arguments");
+    km->incremental_on = on != 0;
+    km->prev_valid = false;
     return AT_OK;
 }
 
 int at_kmeans_set_centroids(at_kmeans *km, const float *centroids, void *stream) {
     AT_REQUIRE(km && centroids, "at_kmeans_set_centroids: bad arguments");
+    km->prev_valid = false;   // new centroids from outside: the next accumulate regroups every row
     return at_index_set_centroids(km->index, centroids, km->k, stream);
 }
 
@@ -610,6 +703,7 @@ int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total) {
     // tensor path: fix the scale of the rows' fp16 operand image (Sx max|x| in [64, 128)) and re-derive the centroid
     // operands for it; the image itself is built by the first accumulate
     km->rows_valid = false;
+    km->prev_valid = false;
     if (km->d == 64) {
         float sx = 1.0f;
         if (max_abs > 0.f) {
@@ -639,10 +733,19 @@ static int km_reserve(at_kmeans *km, int64_t n, cudaStream_t st) {
     if (n <= km->ncap) return AT_OK;
     AT_CUDA_OK(cudaStreamSynchronize(st));
     cudaFree(km->labels), cudaFree(km->dist), cudaFree(km->order);
+    cudaFree(km->prev), cudaFree(km->d_row), cudaFree(km->d_lab), cudaFree(km->d_order);
     km->labels = km->order = nullptr, km->dist = nullptr, km->ncap = 0;
+    km->prev = km->d_row = km->d_lab = km->d_order = nullptr, km->prev_valid = false;
     AT_CUDA_OK(cudaMalloc(&km->labels, sizeof(int32_t) * (size_t)n));
     AT_CUDA_OK(cudaMalloc(&km->dist, sizeof(float) * (size_t)n));
     AT_CUDA_OK(cudaMalloc(&km->order, sizeof(int32_t) * (size_t)n));
+    AT_CUDA_OK(cudaMalloc(&km->prev, sizeof(int32_t) * (size_t)n));
+    AT_CUDA_OK(cudaMalloc(&km->d_row, sizeof(int32_t) * (size_t)n * 2));
+    AT_CUDA_OK(cudaMalloc(&km->d_lab, sizeof(int32_t) * (size_t)n * 2));
+    AT_CUDA_OK(cudaMalloc(&km->d_order, sizeof(int32_t) * (size_t)n * 2));
+    if (!km->d_count) AT_CUDA_OK(cudaMalloc(&km->d_count, sizeof(unsigned int)));
+    if (!km->d_hist) AT_CUDA_OK(cudaMalloc(&km->d_hist, sizeof(unsigned long long) * (size_t)km->k));
+    if (!km->lacc) AT_CUDA_OK(cudaMalloc(&km->lacc, sizeof(unsigned long long) * ((size_t)km->k * km->d + km->k)));
     km->ncap = n;
     return AT_OK;
 }
@@ -676,26 +779,56 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     rc = index_search(km->index, x, n_local, 0, algo, labels, nullptr, km->dist, 0, rows, st);
     if (rc != AT_OK) return rc;
     unsigned long long *acc = (unsigned long long *)accum;
+    unsigned long long *lacc = km->lacc;
     ProfScope prof(PROF_UPDATE, st);
-    int blocks = sm_count() * 8;
-    k_counts<<<blocks, 256, 0, st>>>(labels, n_local, acc + kd);
-    AT_LAUNCH_OK();
-    k_objective<<<blocks, 256, 0, st>>>(km->dist, n_local, ldexpf(1.0f, km->e_obj), acc + kd + k);
-    AT_LAUNCH_OK();
-    k_scan_counts<<<1, 1024, 0, st>>>(acc + kd, k, km->off, km->cursor);
-    AT_LAUNCH_OK();
-    k_place<<<blocks, 256, 0, st>>>(labels, n_local, km->cursor, km->order);
-    AT_LAUNCH_OK();
+    const int blocks = sm_count() * 8;
+    const int gblocks = sm_count() * 8;  // 8 warps per block
     const float scale = ldexpf(1.0f, km->e_sum);
-    int gblocks = sm_count() * 8;  // 8 warps per block
-    int dpl = (d + 31) / 32;
-    if (dpl <= 1)
-        k_gather_sum<1><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, acc);
-    else if (dpl == 2)
-        k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, acc);
-    else
-        k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, acc);
-    AT_LAUNCH_OK();
+    const float obj_scale = ldexpf(1.0f, km->e_obj);
+    const int dpl = (d + 31) / 32;
+    const bool incremental = km->incremental_on && km->prev_valid && km->prev_x == x && km->prev_n == n_local;
+    if (!incremental) {
+        // every row: counts, cluster-grouped order, exact gather-sum into the persistent local accumulator
+        AT_CUDA_OK(cudaMemsetAsync(lacc, 0, sizeof(int64_t) * (size_t)(kd + k), st));
+        k_counts<<<blocks, 256, 0, st>>>(labels, n_local, lacc + kd);
+        AT_LAUNCH_OK();
+        k_objective<<<blocks, 256, 0, st>>>(km->dist, n_local, obj_scale, acc + kd + k);
+        AT_LAUNCH_OK();
+        k_scan_counts<<<1, 1024, 0, st>>>(lacc + kd, k, km->off, km->cursor);
+        AT_LAUNCH_OK();
+        k_place<<<blocks, 256, 0, st>>>(labels, n_local, km->cursor, km->order);
+        AT_LAUNCH_OK();
+        if (dpl <= 1)
+            k_gather_sum<1><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc);
+        else if (dpl == 2)
+            k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc);
+        else
+            k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc);
+        AT_LAUNCH_OK();
+        AT_CUDA_OK(cudaMemcpyAsync(km->prev, labels, sizeof(int32_t) * (size_t)n_local, cudaMemcpyDeviceToDevice, st));
+        km->prev_valid = true, km->prev_x = x, km->prev_n = n_local;
+    } else {
+        // only the rows whose label changed: two delta items each, grouped by cluster and summed exactly like the rest
+        AT_CUDA_OK(cudaMemsetAsync(km->d_count, 0, sizeof(unsigned int), st));
+        AT_CUDA_OK(cudaMemsetAsync(km->d_hist, 0, sizeof(unsigned long long) * (size_t)k, st));
+        k_diff<<<blocks, 256, 0, st>>>(labels, km->prev, km->dist, n_local, obj_scale, km->d_row, km->d_lab, km->d_count,
+                                      acc + kd + k);
+        AT_LAUNCH_OK();
+        k_counts<<<blocks, 256, 0, st>>>(km->d_lab, 0, km->d_hist, km->d_count, 2, km->d_row, lacc + kd);
+        AT_LAUNCH_OK();
+        k_scan_counts<<<1, 1024, 0, st>>>(km->d_hist, k, km->off, km->cursor);
+        AT_LAUNCH_OK();
+        k_place<<<blocks, 256, 0, st>>>(km->d_lab, 0, km->cursor, km->d_order, km->d_count, 2);
+        AT_LAUNCH_OK();
+        if (dpl <= 1)
+            k_gather_sum<1><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
+        else if (dpl == 2)
+            k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
+        else
+            k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
+        AT_LAUNCH_OK();
+    }
+    AT_CUDA_OK(cudaMemcpyAsync(acc, lacc, sizeof(int64_t) * (size_t)(kd + k), cudaMemcpyDeviceToDevice, st));
     return AT_OK;
 }
 

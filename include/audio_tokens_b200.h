@@ -158,6 +158,11 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
  * (already all-reduced) accum.  stats (device float[4], may be NULL): objective, nsplit, imbalance factor,
  * number of empty clusters before the split. */
 int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, float *stats, void *stream);
+/* Between two accumulate calls over the SAME rows (same pointer, same n_local, no at_kmeans_begin /
+ * at_kmeans_set_centroids in between) only the rows whose label changed are moved: their value is subtracted from
+ * the old cluster's exact integer sum and added to the new one, which gives bit-identical sums to regrouping every
+ * row.  on = 0 switches this off (every accumulate regroups every row); default on. */
+int at_kmeans_set_incremental(at_kmeans *km, int on);
 
 /* faiss::rand_perm(perm, n, seed) (faiss/utils/random.cpp): forward Fisher-Yates driven by std::mt19937(seed),
  * i2 = i + mt() % (n - i).  HOST function, HOST pointer.  Used for FAISS's training-set subsample (seed 1234)

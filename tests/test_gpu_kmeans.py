@@ -300,3 +300,33 @@ def test_lloyd_tensor_vs_simt_bit_identical_centroids():
     assert torch.equal(outs[0][0], outs[1][0])           # centroids: bit-identical
     assert torch.equal(outs[0][1][:, 1:], outs[1][1][:, 1:])  # nsplit, imbalance, empties
     torch.testing.assert_close(outs[0][1][:, 0], outs[1][1][:, 0], rtol=1e-4, atol=0)  # objective
+
+
+@pytest.mark.parametrize("k", [16, 128, 1000])
+def test_lloyd_incremental_update_bit_identical_to_full_regroup(k):
+    """The incremental update (rows whose label changed leave one exact integer sum and join another) and the
+    full regroup of every row give bit-identical centroids, counts-derived stats and labels at every iteration."""
+    import torch
+    from at_b200 import LloydTrainer
+
+    _, l2 = _frames(120)
+    n = l2.shape[0]
+    init = l2[:: n // k][:k].contiguous()
+    outs = []
+    for inc in (False, True):
+        tr = LloydTrainer(64, k)
+        tr.set_incremental(inc)
+        tr.begin(l2)
+        tr.set_centroids(init)
+        st = torch.zeros(8, 4, device="cuda")
+        labs = torch.empty(8, n, dtype=torch.int32, device="cuda")
+        cents = []
+        for it in range(8):
+            tr.step(l2, st[it], labs[it])
+            cents.append(tr.get_centroids())
+        outs.append((torch.stack(cents), st.clone(), labs))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert torch.equal(outs[0][1], outs[1][1])
+    changed = (outs[1][2][1:] != outs[1][2][:-1]).sum(dim=1)
+    assert int(changed[0]) > 0   # the incremental path had rows to move
