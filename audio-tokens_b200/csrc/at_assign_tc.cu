@@ -64,13 +64,13 @@ constexpr int TM = 128;          // rows per MMA tile (UMMA M)
 constexpr int TN = 128;          // centroids per tile (UMMA N)
 constexpr int RT = 3;            // row tiles per super tile
 constexpr int SROWS = RT * TM;   // 384
-constexpr int B_SLOTS = 2;       // operand tiles resident per CTA / ring depth
+constexpr int B_SLOTS = 4;       // operand tiles resident per CTA / ring depth
 constexpr int ACC_SLOTS = 4;     // 128-column accumulators in TMEM, used as a ring by consecutive (centroid tile, row tile) pairs
 constexpr uint32_t A_MAIN_BYTES = TM * 128;              // 128 rows x 64 fp16
 constexpr uint32_t AUG_BYTES = TM * 32;                  // 128 rows x 16 fp16, no-swizzle core matrices
 constexpr uint32_t A_TILE_BYTES = A_MAIN_BYTES + AUG_BYTES;      // 20,480
 constexpr uint32_t A_BUF_BYTES = RT * A_TILE_BYTES;              // 61,440
-constexpr uint32_t B_TILE_BYTES = 2 * TN * 128 + TN * 32;        // hi | lo | aug = 36,864
+constexpr uint32_t B_TILE_BYTES = TN * 128 + TN * 32;            // main | aug = 20,480
 
 // shared memory map (dynamic, 1024-B aligned base)
 constexpr uint32_t OFF_A = 0;                                    // 2 buffers
@@ -83,11 +83,11 @@ static_assert(TC_SMEM <= 232448, "shared memory budget");
 enum {
     BAR_A_FULL = 0,      // +2   (bulk copy tx)
     BAR_A_EMPTY = 2,     // +2   (MMA commit)
-    BAR_B_FULL = 4,      // +3   (bulk copy tx)
-    BAR_B_EMPTY = 7,     // +3   (MMA commit)
-    BAR_ACC_FULL = 10,   // +4   [accumulator slot]  (MMA commit)
-    BAR_ACC_EMPTY = 14,  // +4   (4 epilogue warps)
-    BAR_COUNT = 18
+    BAR_B_FULL = 4,      // +4   (bulk copy tx)
+    BAR_B_EMPTY = 8,     // +4   (MMA commit)
+    BAR_ACC_FULL = 12,   // +4   [accumulator slot]  (MMA commit)
+    BAR_ACC_EMPTY = 16,  // +4   (4 epilogue warps)
+    BAR_COUNT = 20
 };
 static_assert(BAR_COUNT * 8 <= 256, "barrier area");
 
@@ -103,7 +103,7 @@ constexpr float TAU_SAFETY = 1.0625f;
 
 // scale[] layout (device floats written by k_tc_scale).  Sx is the scale of the row image (x~ = fp16(Sx x)): the
 // index's own S unless a prepared image with its own scale is attached (k-means), R = S / Sx.
-enum { SC_S = 0, SC_INV_S2 = 2, SC_TAU = 3, SC_CMAX = 4, SC_SX = 5, SC_RATIO = 6, SC_COUNT = 8 };
+enum { SC_S = 0, SC_EMAX = 1, SC_INV_S2 = 2, SC_TAU = 3, SC_CMAX = 4, SC_SX = 5, SC_RATIO = 6, SC_COUNT = 8 };
 
 // (mbarrier / bulk-copy wrappers: at_ptx.cuh)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -207,17 +207,10 @@ __device__ __host__ __forceinline__ uint32_t aug_off(int r, int kc) { return (ui
 // ------------------------------------------------------------------------------------------ operand prep
 // S = 2^s, the largest power of two with S * max|c_j| <= SC_LIMIT (so P d + BIAS stays inside [2^13, 2^17) for every
 // row with S |x| <= X_LIMIT); tau = absolute part of the certification threshold in accumulator units.
-__global__ void k_tc_scale(const float *__restrict__ c, const float *__restrict__ cn, int k,
-                           const float *__restrict__ ext_sx, float *__restrict__ scale) {
-    __shared__ float red[2][32];
-    float m = 0.f, n2 = 0.f;
-    for (int i = threadIdx.x; i < k * 64; i += blockDim.x) m = fmaxf(m, fabsf(c[i]));
-    for (int i = threadIdx.x; i < k; i += blockDim.x) n2 = fmaxf(n2, cn[i]);
-    m = warp_max(m), n2 = warp_max(n2);
-    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = m, red[1][threadIdx.x >> 5] = n2;
-    __syncthreads();
+__global__ void k_tc_scale(unsigned int *__restrict__ maxes, const float *__restrict__ ext_sx, float *__restrict__ scale) {
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, red[0][w]), n2 = fmaxf(n2, red[1][w]);
+        const float m = __uint_as_float(maxes[0]), n2 = __uint_as_float(maxes[1]);
+        maxes[0] = 0u, maxes[1] = 0u;   // ready for the next set of centroids
         const float cmax = sqrtf(n2) * 1.0009765625f;
         int e = 0;
         if (cmax > 0.f && isfinite(cmax)) {
@@ -238,9 +231,9 @@ __global__ void k_tc_scale(const float *__restrict__ c, const float *__restrict_
             if (S < Sx * 0.0009765625f) S = Sx * 0.0009765625f;
         }
         scale[SC_S] = S;
-        scale[1] = 0.f;
+        scale[SC_EMAX] = 0.f;   // max_j |fp16(-2 Sc c_j) - (-2 Sc c_j)|, raised by k_tc_prep
         scale[SC_INV_S2] = 1.0f / (S * S);
-        // split-fp16 centroid products carry ~2^-21 of |x||c| S^2, fp32 accumulation a few 2^-24 of the partial sums
+        // the three-piece norms carry ~2^-21 of S^2 (|x|^2 + |c|^2), fp32 accumulation a few 2^-24 of the partial sums
         // (|.| <= 2^17): 2^-19 S^2 64 m^2 (>= 2^-19 S^2 |c|^2) plus 8 ulps of the accumulator leaves a factor ~4
         scale[SC_TAU] = ldexpf(S * S * 64.0f * m * m, -19) + 0.0625f;
         scale[SC_CMAX] = S * cmax;
@@ -250,30 +243,40 @@ __global__ void k_tc_scale(const float *__restrict__ c, const float *__restrict_
     }
 }
 
-// one thread per (padded centroid, 16-byte chunk): chunks 0..7 main columns, chunk 8 = aug.
-// Padding columns (j >= k) repeat centroid k-1 with PAD_BUMP added to the norm: always behind the real column by far
-// more than any threshold, inside the key range, skipped by the tail kernel.
-__global__ void k_tc_prep(const float *__restrict__ c, const float *__restrict__ cn, int k, int ktiles,
-                          const float *__restrict__ scale, unsigned char *__restrict__ op) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = idx / 9, chunk = idx % 9;
-    if (j >= ktiles * TN) return;
+// eight lanes per padded centroid: lane `chunk` rounds 8 elements of -2 Sc c to fp16 and writes its 16-byte chunk of the
+// K-major tile; the eight partial sums of the squared rounding error are combined in the group and the largest
+// per-centroid error norm goes to scale[SC_EMAX] (non-negative floats order like their bit patterns); lane 0 also
+// writes the aug chunk.  Padding columns (j >= k) repeat centroid k-1 with PAD_BUMP added to the norm: always behind the
+// real column by far more than any threshold, inside the key range, skipped by the tail kernel.
+__global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, const float *__restrict__ cn, int k, int ktiles,
+                                                 float *__restrict__ scale, unsigned char *__restrict__ op) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = idx >> 3, chunk = idx & 7;
+    if (j >= ktiles * TN) return;   // whole warps: ktiles * TN * 8 is a multiple of 256
     const float S = scale[SC_S], R = scale[SC_RATIO];
     const float Sc = S * R;   // x~ carries Sx: -2 Sc c with Sx Sc = S^2
     unsigned char *tile = op + (size_t)(j / TN) * B_TILE_BYTES;
     const int r = j % TN;
     const int js = j < k ? j : k - 1;
-    if (chunk < 8) {
-        __align__(16) __half hi[8], lo[8];
+    __align__(16) __half hi[8];
+    float e2 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            float v = -2.0f * Sc * c[(size_t)js * 64 + chunk * 8 + e];
-            hi[e] = __float2half_rn(v);
-            lo[e] = __float2half_rn(v - __half2float(hi[e]));
-        }
-        *reinterpret_cast<uint4 *>(tile + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(hi);
-        *reinterpret_cast<uint4 *>(tile + TN * 128 + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(lo);
-    } else {
+    for (int e = 0; e < 8; e++) {
+        const float v = -2.0f * Sc * c[(size_t)js * 64 + chunk * 8 + e];
+        hi[e] = __float2half_rn(v);
+        const float err = v - __half2float(hi[e]);
+        e2 = fmaf(err, err, e2);
+    }
+    *reinterpret_cast<uint4 *>(tile + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(hi);
+    e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
+    e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
+    e2 += __shfl_xor_sync(0xffffffffu, e2, 4);
+    float en = sqrtf(e2) * 1.001f;
+    if (!(en == en)) en = INFINITY;   // a non-finite centroid: nothing is certified
+    en = fmaxf(en, __shfl_xor_sync(0xffffffffu, en, 8));
+    en = fmaxf(en, __shfl_xor_sync(0xffffffffu, en, 16));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int *>(scale + SC_EMAX), __float_as_uint(en));
+    if (chunk == 0) {
         // row side: [pieces of xn Sx^2 / 4096 | 4096 4096 4096]; this side: [w w w | pieces of (cn S^2 + BIAS) / 4096],
         // w = 4096 R^2 (a power of two <= 4096)
         __align__(16) __half a[8];
@@ -281,7 +284,7 @@ __global__ void k_tc_prep(const float *__restrict__ c, const float *__restrict__
         a[0] = a[1] = a[2] = w;
         split3(fmaf(cn[js], S * S * AUG_INV, (j < k ? BIAS : BIAS + PAD_BUMP) * AUG_INV), a[3], a[4], a[5]);
         a[6] = a[7] = zero;
-        unsigned char *aug = tile + 2 * TN * 128;
+        unsigned char *aug = tile + TN * 128;
         *reinterpret_cast<uint4 *>(aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
         *reinterpret_cast<uint4 *>(aug + aug_off(r, 1)) = make_uint4(0, 0, 0, 0);
     }
@@ -371,27 +374,35 @@ __device__ __forceinline__ float coop_dist(const float4 xv, float xn, const floa
     return l2_expanded(xn, cnj, half16_sum(s));
 }
 
-constexpr int GA = 8;   // columns per A group
 
-// 16 accumulator columns -> keys.  Two orthogonal groupings of the tile's 128 columns:
-//   A: 16 groups of 8 adjacent columns -> exact running top-3 over the group minima (keys carry the column);
-//   B: 8 groups of 16 columns with the same position mod 8 -> bp[h], the running minimum of group h over the tile.
-// Two columns never share both an A and a B group, so the second smallest COLUMN of a row is exactly
-// min(second smallest A-group minimum, second smallest B-group minimum): the runner-up can hide behind the winner in
-// one grouping, never in both.   alu: 8 (A minima) + 8 (A top-3) + 8 (B) per 16 columns; fma pipe: 16 IMAD.
-__device__ __forceinline__ void fold16(const uint32_t (&r)[16], const int cb, const uint32_t mul, uint32_t &t1,
-                                       uint32_t &t2, uint32_t &t3, uint32_t (&bp)[8]) {
-    uint32_t kx[16];
+// min of 16 keys: 8 alu instructions
+__device__ __forceinline__ uint32_t umin16(const uint32_t *k) {
+    const uint32_t a = umin3(k[0], k[1], k[2]), b = umin3(k[3], k[4], k[5]), c = umin3(k[6], k[7], k[8]);
+    const uint32_t d = umin3(k[9], k[10], k[11]), e = umin3(k[12], k[13], k[14]);
+    return min(umin3(a, b, c), umin3(d, e, k[15]));
+}
+
+// 32 accumulator columns (two 16-column loads, column base cb a multiple of 32) -> keys.  Two orthogonal groupings:
+//   A: the tile's 8 groups of 16 adjacent columns -> exact running top-3 over the group minima of the tile;
+//   B: 16 classes = column mod 16, running over ALL tiles of the row's sweep -> bp[h], the minimum of class h.
+// A group (tile, columns 16a .. 16a+15) and a B class share exactly one column, so two columns never share both: the
+// second smallest COLUMN of a row is exactly min(second smallest A-group minimum, second smallest B-class minimum) -- a
+// runner-up can hide behind the winner in one grouping, never in both.
+// alu: 16 (A minima) + 8 (A top-3) + 16 (B) per 32 columns = 1.25 per score; fma pipe: 32 IMAD.
+__device__ __forceinline__ void fold32(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const int cb, const uint32_t mul,
+                                       uint32_t &t1, uint32_t &t2, uint32_t &t3, uint32_t (&bp)[16]) {
+    uint32_t ka[16], kb[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) kx[i] = r[i] * mul + (uint32_t)(cb + i);   // IMAD R, R, Rmul, imm
-    const uint32_t ga0 = min(umin3(umin3(kx[0], kx[1], kx[2]), kx[3], kx[4]), umin3(kx[5], kx[6], kx[7]));
-    const uint32_t ga1 = min(umin3(umin3(kx[8], kx[9], kx[10]), kx[11], kx[12]), umin3(kx[13], kx[14], kx[15]));
+    for (int i = 0; i < 16; i++) ka[i] = ra[i] * mul + (uint32_t)(cb + i);        // IMAD R, R, Rmul, imm
+#pragma unroll
+    for (int i = 0; i < 16; i++) kb[i] = rb[i] * mul + (uint32_t)(cb + 16 + i);
+    const uint32_t ga0 = umin16(ka), ga1 = umin16(kb);
     const uint32_t lo = min(ga0, ga1), hi = max(ga0, ga1);
     t3 = umin3(t3, max(t2, lo), max(t1, hi));
     t2 = umin3(t2, hi, max(t1, lo));
     t1 = min(t1, lo);
 #pragma unroll
-    for (int h = 0; h < 8; h++) bp[h] = umin3(bp[h], kx[h], kx[h + 8]);
+    for (int h = 0; h < 16; h++) bp[h] = umin3(bp[h], ka[h], kb[h]);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ erow, const float *__restrict__ xns, int64_t n,
             const unsigned char *__restrict__ op, int ktiles, int k, const float *__restrict__ scale, uint32_t key_mul,
             int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist,
-            uint2 *__restrict__ tail, unsigned int *__restrict__ tail_count, unsigned int tail_cap) {
+            uint4 *__restrict__ tail, unsigned int *__restrict__ tail_count, unsigned int tail_cap) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ uint32_t s_tmem_base;
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -436,8 +447,10 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
-
+    // register re-partition: the producer / MMA / allocator warps (warp group 0) keep 56 registers each, the three
+    // scanning warp groups take 152 (128 * 56 + 384 * 152 = the 65,536 the CTA was launched with)
     if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================================================== centroid-tile producer (whole warp, elected lane)
         if (my_tiles > 0) {
             if (RESIDENT) {
@@ -457,6 +470,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             }
         }
     } else if (warp == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================================================== row-image producer
         for (int64_t i = 0; i < my_tiles; i++) {
             const uint32_t ab = (uint32_t)(i & 1);
@@ -464,7 +478,10 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             bulk_g2s_elect(base + OFF_A + ab * A_BUF_BYTES, img + (size_t)(worker + i * workers) * A_BUF_BYTES, A_BUF_BYTES,
                            BAR(BAR_A_FULL + ab));
         }
+    } else if (warp == 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================================================================== MMA issuer (whole warp, elected lane)
         uint32_t st = 0, bph = 0, u = 0;
         for (int64_t i = 0; i < my_tiles; i++) {
@@ -475,7 +492,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 const uint32_t slot = RESIDENT ? (uint32_t)jt : st;
                 if (!RESIDENT || i == 0) mbar_wait(BAR(BAR_B_FULL + slot), RESIDENT ? 0u : bph);
                 const uint32_t b_hi = base + OFF_B + slot * B_TILE_BYTES;
-                const uint64_t dB_hi = desc_sw128(b_hi), dB_lo = desc_sw128(b_hi + TN * 128), dB_aug = desc_nosw(b_hi + 2 * TN * 128);
+                const uint64_t dB_hi = desc_sw128(b_hi), dB_aug = desc_nosw(b_hi + TN * 128);
 #pragma unroll
                 for (int rt = 0; rt < RT; rt++) {
                     const uint32_t a_hi = a0 + rt * A_TILE_BYTES;
@@ -487,8 +504,6 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                     // descriptor start addresses are in 16-byte units: a K step of 16 fp16 = 32 bytes = +2
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_hi + 2 * kk, IDESC, kk > 0);
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_lo + 2 * kk, IDESC, 1);
                     umma_f16(d, dA_aug, dB_aug, IDESC, 1);
                     umma_commit(BAR(BAR_ACC_FULL + acc));
                 }
@@ -500,25 +515,24 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             umma_commit(BAR(BAR_A_EMPTY + ab));
         }
     } else if (warp >= 4) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         // ================================================================== epilogue: accumulator scan
         const int rt = (warp - 4) >> 2;   // row tile of the super tile
         const int ew = warp & 3;          // the TMEM lane quadrant this warp may read
         const int row_in_super = rt * TM + ew * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-        const float inv_s2 = scale[SC_INV_S2], tau_abs = scale[SC_TAU], cmax = scale[SC_CMAX], R = scale[SC_RATIO];
         uint32_t u = 0;
         bool primed = false;
         uint32_t c0[16], c1[16], c2[16], c3[16];
         for (int64_t i = 0; i < my_tiles; i++) {
             uint32_t g1 = 0xFFFFFFFFu, g2 = 0xFFFFFFFFu, g3 = 0xFFFFFFFFu;   // A grouping: best three group minima of the row
-            uint32_t h1 = 0xFFFFFFFFu, h2 = 0xFFFFFFFFu;                     // B grouping: best two
-            int j1 = 0, j2 = 0;
+            uint32_t bp[16];                               // B grouping: class minima over the whole sweep
+#pragma unroll
+            for (int h = 0; h < 16; h++) bp[h] = 0xFFFFFFFFu;
+            int j1 = 0, j2 = 0;                            // centroid tiles of g1, g2
             const int64_t row = (worker + i * workers) * SROWS + row_in_super;
-            const float e = R * __ldg(erow + row);           // S |delta|
-            const float xnP = R * R * __ldg(xns + row);      // S^2 |x|^2
-            const bool fallback = !(xnP <= X_LIMIT * X_LIMIT);   // outside the accumulator range, Inf, NaN
             // Accumulator read-out in eight 16-column loads through four register buffers: two loads are always in flight
-            // behind two folds, and the first two loads of the NEXT tile are issued before the last two folds of this one.
+            // behind a fold of two, and the first two loads of the NEXT tile are issued before the last fold of this one.
             if (!primed) {   // very first tile of this warp
                 const uint32_t v0 = u * RT + rt;
                 mbar_wait(BAR(BAR_ACC_FULL + v0 % ACC_SLOTS), (v0 / ACC_SLOTS) & 1);
@@ -532,24 +546,18 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 const uint32_t acc = (u * RT + rt) % ACC_SLOTS;
                 const uint32_t ta = tmem + lane_addr + acc * TN;
                 uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;
-                uint32_t bp[8];
-#pragma unroll
-                for (int h = 0; h < 8; h++) bp[h] = 0xFFFFFFFFu;
                 tmem_ld_wait();                       // c0, c1 (issued during the previous tile)
                 tmem_ld16(ta + 32, c2);
                 tmem_ld16(ta + 48, c3);
-                fold16(c0, 0, key_mul, t1, t2, t3, bp);
-                fold16(c1, 16, key_mul, t1, t2, t3, bp);
+                fold32(c0, c1, 0, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tmem_ld16(ta + 64, c0);
                 tmem_ld16(ta + 80, c1);
-                fold16(c2, 32, key_mul, t1, t2, t3, bp);
-                fold16(c3, 48, key_mul, t1, t2, t3, bp);
+                fold32(c2, c3, 32, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tmem_ld16(ta + 96, c2);
                 tmem_ld16(ta + 112, c3);
-                fold16(c0, 64, key_mul, t1, t2, t3, bp);
-                fold16(c1, 80, key_mul, t1, t2, t3, bp);
+                fold32(c0, c1, 64, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -566,27 +574,16 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                     tmem_ld16(tn + 16, c1);
                     started = true;
                 }
-                fold16(c2, 96, key_mul, t1, t2, t3, bp);
-                fold16(c3, 112, key_mul, t1, t2, t3, bp);
+                fold32(c2, c3, 96, key_mul, t1, t2, t3, bp);
                 if (more && !started) {
                     mbar_wait(nbar, nph);
                     tc_fence_after();
                     tmem_ld16(tn, c0);
                     tmem_ld16(tn + 16, c1);
                 }
-                // B grouping: top-2 of the tile's 8 group minima, merged into the row's
-                uint32_t u1 = 0xFFFFFFFFu, u2 = 0xFFFFFFFFu;
-#pragma unroll
-                for (int pr = 0; pr < 4; pr++) {
-                    const uint32_t lo = min(bp[2 * pr], bp[2 * pr + 1]), hi = max(bp[2 * pr], bp[2 * pr + 1]);
-                    u2 = umin3(u2, hi, max(u1, lo));
-                    u1 = min(u1, lo);
-                }
-                h2 = umin3(h2, u2, max(h1, u1));
-                h1 = min(h1, u1);
                 // A grouping: merge the tile's sorted triple into the row's (equal keys keep the earlier tile)
-                const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
                 const bool p = t1 < g1;
+                const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
                 const uint32_t xa = p ? g1 : g2, ya = p ? t2 : t1;
                 const int xt = p ? j1 : j2;
                 const bool qn = ya < xa;
@@ -596,15 +593,33 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 j1 = p ? jt : j1;
                 g3 = n3;
             }
+            // B grouping: top-3 of the 16 class minima (h1 == g1: the row minimum is the same in both groupings)
+            uint32_t h1 = min(bp[0], bp[1]), h2 = max(bp[0], bp[1]), h3 = 0xFFFFFFFFu;
+#pragma unroll
+            for (int pr = 1; pr < 8; pr++) {
+                const uint32_t lo = min(bp[2 * pr], bp[2 * pr + 1]), hi = max(bp[2 * pr], bp[2 * pr + 1]);
+                const uint32_t m3 = umin3(h3, max(h2, lo), max(h1, hi));
+                h2 = umin3(h2, hi, max(h1, lo));
+                h1 = min(h1, lo);
+                h3 = m3;
+            }
+            // (the scale constants are re-read per super tile rather than held in registers across the scan)
+            const float inv_s2 = __ldg(scale + SC_INV_S2), tau_abs = __ldg(scale + SC_TAU), cmax = __ldg(scale + SC_CMAX);
+            const float R = __ldg(scale + SC_RATIO), emax = __ldg(scale + SC_EMAX);
+            const float e = R * __ldg(erow + row);           // S |delta|
+            const float xnS = __ldg(xns + row);              // Sx^2 |x|^2
+            const float xnP = R * R * xnS;                   // S^2 |x|^2
+            const bool fallback = !(xnP <= X_LIMIT * X_LIMIT);   // outside the accumulator range, Inf, NaN
             // ---- certification (accumulator units)
-            const float A1 = acc_of(g1), A2 = acc_of(min(g2, h2)), A3 = acc_of(g3);
+            const float A1 = acc_of(g1), A2 = acc_of(min(g2, h2)), A3 = acc_of(min(g3, h3));
             const int ca = j1 * TN + (int)(g1 & 127u);
-            const int cb = j2 * TN + (int)(g2 & 127u);
             const float v1 = fmaxf(A1 - BIAS, 0.f);
-            const float ub = v1 + 2.0f * e * cmax + tau_abs;                        // >= S^2 d_best
-            const float tau = TAU_SAFETY * (tau_abs + 4.0f * e * sqrtf(ub + tau_abs));
+            const float cterm = sqrtf(xnS) * 1.001f * emax;                          // >= |<x~, e_j>| for every column j
+            const float ub = v1 + 2.0f * e * cmax + tau_abs + cterm;                 // >= S^2 d_best
+            const float tau = TAU_SAFETY * (tau_abs + 4.0f * e * sqrtf(ub + tau_abs) + 2.0f * cterm);
             const bool second_ok = (A2 - A1) > tau;   // exact second smallest column: no other column can win
-            const bool third_ok = (A3 - A1) > tau;    // every column outside the two best A groups is out of reach
+            // every column outside (best two A groups) x (best two B groups) is out of reach
+            const bool third_ok = (A3 - A1) > tau;
 #ifdef AT_TC_FORCE_CERT
             const bool certified = true;
 #else
@@ -617,7 +632,8 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 if (dist) dist[row] = v1 * inv_s2;
             }
             // uncertified rows -> tail lists (warp-aggregated appends): candidate rows from the front, full-scan rows
-            // from the back of the same array
+            // from the back of the same array.  Candidates: the four columns where one of the two best A groups meets one of
+            // the two best B classes.
             const bool want_full = live && !certified && (fallback || !third_ok || ca >= k);
             const bool want_cand = live && !certified && !want_full;
             const unsigned mc = __ballot_sync(0xffffffffu, want_cand), mf = __ballot_sync(0xffffffffu, want_full);
@@ -629,8 +645,14 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 }
                 sc = __shfl_sync(0xffffffffu, sc, 0), sf = __shfl_sync(0xffffffffu, sf, 0);
                 const unsigned lt = (1u << lane) - 1u;
-                if (want_cand) tail[sc + __popc(mc & lt)] = make_uint2((uint32_t)row, (uint32_t)ca | ((uint32_t)cb << 16));
-                if (want_full) tail[tail_cap - 1 - (sf + __popc(mf & lt))] = make_uint2((uint32_t)row, 0u);
+                if (want_cand) {
+                    const int a1 = (int)(g1 & 112u), b1 = (int)(g1 & 15u), a2 = (int)(g2 & 112u), b2 = (int)(h2 & 15u);
+                    int c1 = j1 * TN + a1 + b2, c2 = j2 * TN + a2 + b1, c3 = j2 * TN + a2 + b2;
+                    c1 = c1 < k ? c1 : ca, c2 = c2 < k ? c2 : ca, c3 = c3 < k ? c3 : ca;
+                    tail[sc + __popc(mc & lt)] = make_uint4((uint32_t)row, (uint32_t)ca | ((uint32_t)c1 << 16),
+                                                            (uint32_t)c2 | ((uint32_t)c3 << 16), 0u);
+                }
+                if (want_full) tail[tail_cap - 1 - (sf + __popc(mf & lt))] = make_uint4((uint32_t)row, 0u, 0u, 0u);
             }
         }
     }
@@ -658,79 +680,40 @@ __device__ __forceinline__ float4 tail_row(const float *__restrict__ x, int64_t 
     return xv;
 }
 
-// Uncertified rows.  Full-scan rows (back of the list): one BLOCK per row, its sixteen 16-lane groups take every
-// sixteenth centroid, eight loads in flight each.  Candidate rows (front): one warp per row, 16-lane group `half` takes
-// the 8 columns of candidate A group `half` (the second may repeat the first).  Canonical fp32 arithmetic throughout.
+// Uncertified rows with a candidate list (front of the tail array): a 16-lane group per row evaluates the (at most four)
+// candidate columns with the canonical fp32 arithmetic; the lowest index wins exact ties like the exact kernel's scan.
 __global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, int l2norm, const float *__restrict__ c,
-                                                 const float *__restrict__ cn, int k, const uint2 *__restrict__ tail,
-                                                 const unsigned int *__restrict__ tail_count, unsigned int tail_cap,
+                                                 const float *__restrict__ cn, const uint4 *__restrict__ tail,
+                                                 const unsigned int *__restrict__ tail_count,
                                                  int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
                                                  float *__restrict__ dist, unsigned long long *__restrict__ counters) {
-    __shared__ float s_bd[16];
-    __shared__ int s_best[16];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, g = lane & 15;
-    const unsigned int n_cand = tail_count[0], n_full = tail_count[1];
-    float4 cv[GA];
-    float cnv[GA];
-    // ---- full scans
-    for (unsigned int e = blockIdx.x; e < n_full; e += gridDim.x) {
-        const int64_t row = (int64_t)tail[tail_cap - 1 - e].x;
-        float xn;
-        const float4 xv = tail_row(x, row, l2norm, g, xn);
-        const int gi = warp * 2 + half;
-        float bd = INFINITY;
-        int best = 0x7FFFFFFF;
-        for (int j0 = 0; j0 < k; j0 += 16 * GA) {
-#pragma unroll
-            for (int t = 0; t < GA; t++) {
-                const int jj = min(j0 + 16 * t + gi, k - 1);
-                cv[t] = __ldg(reinterpret_cast<const float4 *>(c + (size_t)jj * 64) + g);
-                cnv[t] = __ldg(cn + jj);
-            }
-#pragma unroll
-            for (int t = 0; t < GA; t++) {
-                const int j = j0 + 16 * t + gi;
-                const float dj = coop_dist(xv, xn, cv[t], cnv[t]);
-                if (j < k && dj < bd) bd = dj, best = j;   // ascending j within the group: strict '<' keeps the lowest index
-            }
-        }
-        if (g == 0) s_bd[gi] = bd, s_best[gi] = best;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int q = 1; q < 16; q++)
-                if (s_bd[q] < bd || (s_bd[q] == bd && s_best[q] < best)) bd = s_bd[q], best = s_best[q];
-            if (labels32) labels32[row] = best;
-            if (labels64) labels64[row] = best;
-            if (dist) dist[row] = bd;
-        }
-        __syncthreads();
-    }
-    // ---- candidate rows
+    const int lane = threadIdx.x & 31, half = lane >> 4, g = lane & 15;
+    const unsigned int n_cand = tail_count[0];
     const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n_cand; e += nwarps) {
-        const uint2 cc = tail[e];
+    // warp-uniform trip count: the 16-lane reductions shuffle with the full mask
+    for (unsigned int e0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; e0 < n_cand; e0 += nwarps * 2) {
+        const unsigned int e = e0 + half;
+        const bool live = e < n_cand;
+        const uint4 cc = tail[live ? e : e0];
         const int64_t row = (int64_t)cc.x;
-        const int gbase = (int)((half ? (cc.y >> 16) : (cc.y & 0xFFFF)) & ~(uint32_t)(GA - 1));
+        int cols[4] = {(int)(cc.y & 0xFFFFu), (int)(cc.y >> 16), (int)(cc.z & 0xFFFFu), (int)(cc.z >> 16)};
+        float4 cv[4];
+        float cnv[4];
 #pragma unroll
-        for (int t = 0; t < GA; t++) {   // issue the candidate loads before anything depends on them
-            const int jj = min(gbase + t, k - 1);
-            cv[t] = __ldg(reinterpret_cast<const float4 *>(c + (size_t)jj * 64) + g);
-            cnv[t] = __ldg(cn + jj);
+        for (int t = 0; t < 4; t++) {   // issue the candidate loads before anything depends on them
+            cv[t] = __ldg(reinterpret_cast<const float4 *>(c + (size_t)cols[t] * 64) + g);
+            cnv[t] = __ldg(cn + cols[t]);
         }
         float xn;
         const float4 xv = tail_row(x, row, l2norm, g, xn);
         float bd = INFINITY;
         int best = 0x7FFFFFFF;
 #pragma unroll
-        for (int t = 0; t < GA; t++) {
-            const int j = gbase + t;
+        for (int t = 0; t < 4; t++) {
             const float dj = coop_dist(xv, xn, cv[t], cnv[t]);
-            if (j < k && (dj < bd || (dj == bd && j < best))) bd = dj, best = j;
+            if (dj < bd || (dj == bd && cols[t] < best)) bd = dj, best = cols[t];
         }
-        const float od = __shfl_xor_sync(0xffffffffu, bd, 16);
-        const int ob = __shfl_xor_sync(0xffffffffu, best, 16);
-        if (od < bd || (od == bd && ob < best)) bd = od, best = ob;
-        if (lane == 0) {
+        if (live && g == 0) {
             if (labels32) labels32[row] = best;
             if (labels64) labels64[row] = best;
             if (dist) dist[row] = bd;
@@ -738,7 +721,82 @@ __global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, in
     }
     if (counters && blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&counters[0], (unsigned long long)n_cand);
-        atomicAdd(&counters[1], (unsigned long long)n_full);
+        atomicAdd(&counters[1], (unsigned long long)tail_count[1]);
+    }
+}
+
+// Uncertified rows without a usable candidate list (back of the tail array): exact scan of every centroid, a thread per
+// listed row with the row in registers and the centroids streamed through shared memory once per 64 rows -- the exact
+// SIMT kernel's arithmetic (canonical chunk partials + xor tree, strict '<' in ascending index order).
+constexpr int FULL_ROWS = 64, FULL_KT = 32;
+__global__ void __launch_bounds__(FULL_ROWS) k_tc_full(const float *__restrict__ x, int l2norm, const float *__restrict__ c,
+                                                       const float *__restrict__ cn, int k, const uint4 *__restrict__ tail,
+                                                       const unsigned int *__restrict__ tail_count, unsigned int tail_cap,
+                                                       int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
+                                                       float *__restrict__ dist) {
+    __shared__ __align__(16) float ctile[FULL_KT][64];
+    __shared__ float cns[FULL_KT];
+    const int tid = threadIdx.x;
+    const unsigned int n_full = tail_count[1];
+    for (unsigned int base = blockIdx.x * FULL_ROWS; base < n_full; base += gridDim.x * FULL_ROWS) {
+        const unsigned int e = base + tid;
+        const bool live = e < n_full;
+        const int64_t row = (int64_t)tail[tail_cap - 1 - (live ? e : base)].x;
+        float xr[64];
+        {
+            const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+                const float4 v = __ldg(xp + t);
+                xr[4 * t] = v.x, xr[4 * t + 1] = v.y, xr[4 * t + 2] = v.z, xr[4 * t + 3] = v.w;
+            }
+        }
+        float q[16];
+        if (l2norm) {
+#pragma unroll
+            for (int l = 0; l < 16; l++) q[l] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 64; t++) q[t >> 2] = fmaf(xr[t], xr[t], q[t >> 2]);
+            const float den = l2_denominator(tree16(q));
+#pragma unroll
+            for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
+        }
+#pragma unroll
+        for (int l = 0; l < 16; l++) q[l] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 64; t++) q[t >> 2] = fmaf(xr[t], xr[t], q[t >> 2]);
+        const float xn = tree16(q);
+        float bd = INFINITY;
+        int best = 0;
+        for (int j0 = 0; j0 < k; j0 += FULL_KT) {
+            const int kt = min(FULL_KT, k - j0);
+            __syncthreads();   // the previous tile has been consumed
+            for (int i = tid; i < FULL_KT * 16; i += FULL_ROWS) {
+                const int jj = i >> 4;
+                reinterpret_cast<float4 *>(&ctile[0][0])[i] =
+                    jj < kt ? __ldg(reinterpret_cast<const float4 *>(c + (size_t)j0 * 64) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (tid < FULL_KT) cns[tid] = tid < kt ? cn[j0 + tid] : INFINITY;
+            __syncthreads();
+            for (int jj = 0; jj < kt; jj++) {
+#pragma unroll
+                for (int l = 0; l < 16; l++) {
+                    const float4 cv = *reinterpret_cast<const float4 *>(&ctile[jj][4 * l]);
+                    float s = xr[4 * l] * cv.x;
+                    s = fmaf(xr[4 * l + 1], cv.y, s);
+                    s = fmaf(xr[4 * l + 2], cv.z, s);
+                    s = fmaf(xr[4 * l + 3], cv.w, s);
+                    q[l] = s;
+                }
+                const float dj = l2_expanded(xn, cns[jj], tree16(q));
+                if (dj < bd) bd = dj, best = j0 + jj;
+            }
+        }
+        if (live) {
+            if (labels32) labels32[row] = best;
+            if (labels64) labels64[row] = best;
+            if (dist) dist[row] = bd;
+        }
     }
 }
 
@@ -776,9 +834,9 @@ bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16
 
 int assign_tc_prepare(at_index *ix, cudaStream_t st) {
     if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, SC_COUNT * sizeof(float)));
-    k_tc_scale<<<1, 1024, 0, st>>>(ix->c, ix->cn, ix->k, ix->ext_sx, ix->tc_scale);
+    k_tc_scale<<<1, 32, 0, st>>>(ix->tc_max, ix->ext_sx, ix->tc_scale);
     AT_LAUNCH_OK();
-    const int total = ix->ktiles * TN * 9;
+    const int total = ix->ktiles * TN * 8;
     k_tc_prep<<<(total + 255) / 256, 256, 0, st>>>(ix->c, ix->cn, ix->k, ix->ktiles, ix->tc_scale,
                                                   reinterpret_cast<unsigned char *>(ix->op));
     AT_LAUNCH_OK();
@@ -808,7 +866,7 @@ int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const fl
         AT_CUDA_OK(cudaMalloc(&r->img, (size_t)(n_pad / TM) * A_TILE_BYTES));
         AT_CUDA_OK(cudaMalloc(&r->erow, sizeof(float) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->xns, sizeof(float) * (size_t)n_pad));
-        AT_CUDA_OK(cudaMalloc(&r->tail, sizeof(uint2) * (size_t)n_pad));
+        AT_CUDA_OK(cudaMalloc(&r->tail, sizeof(uint4) * (size_t)n_pad));
         if (!r->tail_count) AT_CUDA_OK(cudaMalloc(&r->tail_count, 2 * sizeof(unsigned int)));
         r->cap = n_pad;
     }
@@ -865,8 +923,11 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
                                                              ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
                                                              rows->tail_count, (unsigned int)rows->cap);
     AT_LAUNCH_OK();
-    k_tc_tail<<<sms * 4, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
-                                      (unsigned int)rows->cap, l32, labels64, kdist, ix->tc_counters);
+    k_tc_tail<<<sms * 8, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, rows->tail, rows->tail_count, l32, labels64, kdist,
+                                      ix->tc_counters);
+    AT_LAUNCH_OK();
+    k_tc_full<<<sms * 4, FULL_ROWS, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
+                                            (unsigned int)rows->cap, l32, labels64, kdist);
     AT_LAUNCH_OK();
     if (dist && exact_dist) {
         k_exact_dist<<<sms * 8, 256, 0, st>>>(x, n, l2norm_rows, ix->c, ix->cn, l32, l32 ? nullptr : labels64, dist);

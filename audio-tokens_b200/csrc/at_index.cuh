@@ -9,7 +9,7 @@ struct at_tc_rows {
     void *img = nullptr;        // (n_pad / 128) tiles of 20,480 bytes
     float *erow = nullptr;      // (n_pad) |Sx delta| per row
     float *xns = nullptr;       // (n_pad) Sx^2 |x|^2 per row
-    uint2 *tail = nullptr;      // (n_pad) uncertified rows of the last search
+    uint4 *tail = nullptr;      // (n_pad) uncertified rows of the last search: {row, candidate columns 0|1, 2|3, -}
     unsigned int *tail_count = nullptr;
     int64_t cap = 0;            // rows allocated (multiple of 256)
     const float *x = nullptr;   // what the image was built from
@@ -23,13 +23,14 @@ struct at_index {
     int kcap = 0;   // allocation, in centroids
     float *c = nullptr;    // (kcap, d) fp32 centroids
     float *cn = nullptr;   // (kcap) canonical |c|^2
-    // tcgen05 operands (d == 64 only): per 128-centroid tile one 36,864-byte image = hi | lo fp16 halves of
-    // -2*S*c as 128x64 K-major SWIZZLE_128B tiles + a 128x16 no-swizzle tile carrying |c|^2 (at_assign_tc.cu)
+    // tcgen05 operands (d == 64 only): per 128-centroid tile one 20,480-byte image = fp16(-2*Sc*c) as a 128x64 K-major
+    // SWIZZLE_128B tile + a 128x16 no-swizzle tile carrying |c|^2 (at_assign_tc.cu)
     __half *op = nullptr;
-    float *tc_scale = nullptr;  // device: {S, -, 1 / S^2, tau, S max|c|, Sx, S / Sx}
+    float *tc_scale = nullptr;  // device: {S, max centroid rounding error, 1 / S^2, tau, S max|c|, Sx, S / Sx}
+    unsigned int *tc_max = nullptr;  // device: {max |c_ij|, max |c_j|^2} bit patterns (k_centroid_norms -> k_tc_scale)
     const float *ext_sx = nullptr;  // device float: scale of an attached row image (k-means); nullptr = the index's own S
     at_tc_rows rows;            // workspace of one-off searches
-    unsigned long long *tc_counters = nullptr;  // device: rows re-checked on 16 columns, rows scanned exactly (cumulative)
+    unsigned long long *tc_counters = nullptr;  // device: rows re-checked on their candidate columns, rows scanned exactly (cumulative)
     int tc_mode = 0;            // 0 auto, 1 stream operand tiles, 2 keep them resident when they fit
     int32_t *part_lab = nullptr;  // scratch labels for a distance-only request
     int64_t part_cap = 0;
@@ -46,12 +47,12 @@ struct at_kmeans {
     // workspaces sized for the largest n_local seen
     int64_t ncap = 0;
     int32_t *labels = nullptr;
-    float *dist = nullptr;
     int32_t *order = nullptr;
     int64_t *off = nullptr;     // k+1
     unsigned long long *cursor = nullptr;  // k
     float *hassign = nullptr;   // k
     float *newc = nullptr;      // (k, d) scratch for finalize
+    double *fin = nullptr;      // per-block partials of finalize's statistics
     // tensor path: operand image of the training rows, built at the first accumulate and re-used while the caller
     // passes the same (x, n_local) -- the rows must not change between at_kmeans_begin and the last accumulate
     at_tc_rows rows;

@@ -43,24 +43,41 @@ __global__ void k_row_l2norm(const float *__restrict__ x, int64_t n, int d, floa
     }
 }
 
-// canonical |c|^2, one thread per centroid (k is small)
-__global__ void k_centroid_norms(const float *__restrict__ c, int k, int d, float *__restrict__ cn) {
+// canonical |c|^2, one thread per centroid (k is small).  maxes (may be null): {max |c_ij|, max |c_j|^2} as float bit
+// patterns raised with atomicMax (non-negative floats order like their patterns; NaN patterns sort above every number,
+// so a non-finite centroid is seen by the consumer), consumed and reset by k_tc_scale.
+__global__ void k_centroid_norms(const float *__restrict__ c, int k, int d, float *__restrict__ cn,
+                                 unsigned int *__restrict__ maxes) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= k) return;
-    float q[16];
+    float m = 0.f, n2 = 0.f;
+    if (j < k) {
+        float q[16];
 #pragma unroll
-    for (int l = 0; l < 16; l++) q[l] = 0.f;
-    const float *cj = c + (int64_t)j * d;
-    for (int base = 0; base < d; base += 64) {
+        for (int l = 0; l < 16; l++) q[l] = 0.f;
+        const float *cj = c + (int64_t)j * d;
+        for (int base = 0; base < d; base += 64) {
 #pragma unroll
-        for (int t = 0; t < 64; t++) {
-            if (base + t < d) {
-                float v = cj[base + t];
-                q[(t >> 2) & 15] = fmaf(v, v, q[(t >> 2) & 15]);
+            for (int t = 0; t < 64; t++) {
+                if (base + t < d) {
+                    float v = cj[base + t];
+                    q[(t >> 2) & 15] = fmaf(v, v, q[(t >> 2) & 15]);
+                    m = fmaxf(m, fabsf(v));
+                    if (!(v == v)) m = v;
+                }
             }
         }
+        n2 = tree16(q);
+        cn[j] = n2;
     }
-    cn[j] = tree16(q);
+    if (maxes) {
+        unsigned int um = __float_as_uint(fabsf(m)), un = __float_as_uint(fabsf(n2));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            um = max(um, __shfl_xor_sync(0xffffffffu, um, o));
+            un = max(un, __shfl_xor_sync(0xffffffffu, un, o));
+        }
+        if ((threadIdx.x & 31) == 0) atomicMax(maxes, um), atomicMax(maxes + 1, un);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,41 +169,15 @@ __global__ void __launch_bounds__(128) k_assign_simt(const float *__restrict__ x
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k-means accumulate: counts + objective, offsets, placement, exact gather-sum.
-// ---------------------------------------------------------------------------------------------
-// accum layout (int64 words): [0, k*d) sums, [k*d, k*d+k) counts, [k*d+k] objective.
-__global__ void k_objective(const float *__restrict__ dist, int64_t n, float obj_scale,
-                            unsigned long long *__restrict__ obj_word) {
-    long long local = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        local += __float2ll_rn(dist[i] * obj_scale);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    __shared__ long long ws[32];
-    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) ws[w] = local;
-    __syncthreads();
-    if (w == 0) {
-        long long v = lane < (int)(blockDim.x >> 5) ? ws[lane] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd(obj_word, (unsigned long long)v);
-    }
-}
-
 // Rows whose label changed since the previous accumulate: two delta items each (leave the old cluster, join the new
-// one), prev updated; the objective is summed on the way (as k_objective).  List slots are reserved once per block
-// step (a per-warp atomic on the single counter serialises in L2).
-__global__ void __launch_bounds__(256) k_diff(const int32_t *__restrict__ labels, int32_t *__restrict__ prev,
-                                              const float *__restrict__ dist, int64_t n, float obj_scale,
+// one), prev updated.  List slots are reserved once per block step (a per-warp atomic on the single counter serialises
+// in L2).
+__global__ void __launch_bounds__(256) k_diff(const int32_t *__restrict__ labels, int32_t *__restrict__ prev, int64_t n,
                                               int32_t *__restrict__ d_row, int32_t *__restrict__ d_lab,
-                                              unsigned int *__restrict__ d_count, unsigned long long *__restrict__ obj_word) {
+                                              unsigned int *__restrict__ d_count) {
     __shared__ unsigned int s_cnt[8];
     __shared__ unsigned int s_base;
-    __shared__ long long ws[8];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    long long local = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += stride) {   // block-uniform trip count
         const int64_t i = base + threadIdx.x;
@@ -195,7 +186,6 @@ __global__ void __launch_bounds__(256) k_diff(const int32_t *__restrict__ labels
         if (i < n) {
             l = labels[i], p = prev[i];
             changed = l != p;
-            local += __float2ll_rn(dist[i] * obj_scale);
         }
         const unsigned m = __ballot_sync(0xffffffffu, changed);
         if (lane == 0) s_cnt[w] = (unsigned int)__popc(m);
@@ -217,16 +207,6 @@ __global__ void __launch_bounds__(256) k_diff(const int32_t *__restrict__ labels
             prev[i] = l;
         }
         __syncthreads();
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if (lane == 0) ws[w] = local;
-    __syncthreads();
-    if (w == 0) {
-        long long v = lane < 8 ? ws[lane] : 0;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd(obj_word, (unsigned long long)v);
     }
 }
 
@@ -311,7 +291,8 @@ __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x,
                                                     const int64_t *__restrict__ off, int k, int64_t n,
                                                     float scale, unsigned long long *__restrict__ sums,
                                                     const int32_t *__restrict__ items = nullptr,
-                                                    const unsigned int *__restrict__ n_dev = nullptr) {
+                                                    const unsigned int *__restrict__ n_dev = nullptr,
+                                                    unsigned long long *__restrict__ sumsq = nullptr, float sq_scale = 0.f) {
     if (n_dev) n = 2 * (int64_t)*n_dev;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -331,6 +312,7 @@ __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x,
     long long acc[DPL];
 #pragma unroll
     for (int u = 0; u < DPL; u++) acc[u] = 0;
+    long long sq = 0;   // sum of x^2 over this warp's rows (fixed point), the constant term of the objective
 
     constexpr int U = 8;
     for (int64_t p = p0; p < p1; p += U) {
@@ -370,7 +352,16 @@ __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x,
             }
 #pragma unroll
             for (int w = 0; w < DPL; w++) acc[w] += __float2ll_rn(v[u][w] * sgn[u]);
+            if (sumsq) {
+#pragma unroll
+                for (int w = 0; w < DPL; w++) sq += __float2ll_rn(v[u][w] * v[u][w] * sq_scale);
+            }
         }
+    }
+    if (sumsq) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) atomicAdd(sumsq, (unsigned long long)sq);
     }
 #pragma unroll
     for (int w = 0; w < DPL; w++) {
@@ -411,49 +402,82 @@ struct Mt19937 {
     __device__ float rand_float() { return __fdiv_rn((float)next(), 4294967296.0f); }
 };
 
-__global__ void __launch_bounds__(1024) k_finalize(const long long *__restrict__ accum, int k, int d,
-                                                   int64_t n_total, double inv_sum_scale,
-                                                   double inv_obj_scale, float *__restrict__ centroids,
-                                                   float *__restrict__ hassign, float *__restrict__ stats) {
-    __shared__ Mt19937 rng;
-    __shared__ double s_imb[32];
-    __shared__ int s_empty[32];
-    const int tid = threadIdx.x;
+// compute_centroids' division, one warp per cluster: c[j] = sum * (1 / count) (empty clusters stay zero), plus the
+// cluster's share of the objective against the centroids the rows were assigned with,
+//     sum_i |x_i - c_old|^2 = sum_i |x_i|^2 + count |c_old|^2 - 2 <sum_i x_i, c_old>      (exact sums, double arithmetic),
+// of the imbalance factor and of the empty-cluster count, as one partial triple per block (summed in a fixed order by
+// k_finalize_split, so the statistics are reproducible bit for bit).
+constexpr int FIN_WARPS = 8;
+__global__ void __launch_bounds__(FIN_WARPS * 32) k_finalize_div(const long long *__restrict__ accum, int k, int d,
+                                                               double inv_sum_scale, const float *__restrict__ c_old,
+                                                               float *__restrict__ centroids, float *__restrict__ hassign,
+                                                               double *__restrict__ part) {
+    __shared__ double s_part[FIN_WARPS][3];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * FIN_WARPS + w;
     const int64_t kd = (int64_t)k * d;
-    double imb = 0.0;
-    int nempty = 0;
-    for (int c = tid; c < k; c += blockDim.x) {
-        long long cnt = accum[kd + c];
-        hassign[c] = (float)cnt;
-        imb += (double)cnt * (double)cnt;
-        nempty += cnt == 0;
-    }
-    for (int64_t i = tid; i < kd; i += blockDim.x) {
-        int c = (int)(i / d);
-        long long cnt = accum[kd + c];
-        float v = 0.f;
-        if (cnt != 0) {
-            // compute_centroids: c[j] = sum * (1 / hassign)
-            float sum = __double2float_rn(__ll2double_rn(accum[i]) * inv_sum_scale);
-            float norm = __fdiv_rn(1.0f, (float)cnt);
-            v = __fmul_rn(sum, norm);
+    double obj = 0.0, imb = 0.0, ne = 0.0;
+    if (c < k) {
+        const long long cnt = accum[kd + c];
+        const float norm = cnt != 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
+        double dot = 0.0, cc = 0.0;
+        for (int t = lane; t < d; t += 32) {
+            const double sd = __ll2double_rn(accum[(int64_t)c * d + t]) * inv_sum_scale;
+            const double co = (double)c_old[(int64_t)c * d + t];
+            dot = fma(sd, co, dot);
+            cc = fma(co, co, cc);
+            centroids[(int64_t)c * d + t] = cnt != 0 ? __fmul_rn(__double2float_rn(sd), norm) : 0.f;
         }
-        centroids[i] = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            cc += __shfl_xor_sync(0xffffffffu, cc, o);
+        }
+        obj = (double)cnt * cc - 2.0 * dot;
+        imb = (double)cnt * (double)cnt;
+        ne = cnt == 0 ? 1.0 : 0.0;
+        if (lane == 0) hassign[c] = (float)cnt;
+    }
+    if (lane == 0) s_part[w][0] = obj, s_part[w][1] = imb, s_part[w][2] = ne;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int q = 0; q < FIN_WARPS; q++) v += s_part[q][threadIdx.x];
+        part[(int64_t)blockIdx.x * 3 + threadIdx.x] = v;
+    }
+}
+
+// statistics + faiss::split_clusters.  One block; the split itself is sequential by construction.
+__global__ void __launch_bounds__(256) k_finalize_split(const long long *__restrict__ accum, int k, int d, int64_t n_total,
+                                                        double inv_obj_scale, const double *__restrict__ part, int nblk,
+                                                        float *__restrict__ centroids, float *__restrict__ hassign,
+                                                        float *__restrict__ stats) {
+    __shared__ Mt19937 rng;
+    __shared__ double s_red[3][256];
+    const int tid = threadIdx.x;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int b = tid; b < nblk; b += 256) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) v[q] += part[(int64_t)b * 3 + q];
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        imb += __shfl_xor_sync(0xffffffffu, imb, o);
-        nempty += __shfl_xor_sync(0xffffffffu, nempty, o);
-    }
-    if ((tid & 31) == 0) s_imb[tid >> 5] = imb, s_empty[tid >> 5] = nempty;
+    for (int q = 0; q < 3; q++) s_red[q][tid] = v[q];
     __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) s_red[q][tid] += s_red[q][tid + o];
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
-        double tot = 0;
-        int ne = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_imb[w], ne += s_empty[w];
+        const int64_t kd = (int64_t)k * d;
+        const double obj = (double)accum[kd + k] * inv_obj_scale + s_red[0][0];   // accum[kd + k]: sum of |x_i|^2, fixed point
+        const double tot = s_red[1][0];
+        const int ne = (int)(s_red[2][0] + 0.5);
         int nsplit = 0;
         if (ne > 0) {
-            // faiss::split_clusters (Clustering.cpp), sequential by construction
+            // faiss::split_clusters (Clustering.cpp)
             rng.seed(1234u);
             for (int ci = 0; ci < k; ci++) {
                 if (hassign[ci] == 0.f) {
@@ -464,8 +488,8 @@ __global__ void __launch_bounds__(1024) k_finalize(const long long *__restrict__
                         if (r < p) break;
                     }
                     for (int j = 0; j < d; j++) {
-                        float v = centroids[(int64_t)cj * d + j];
-                        float up = __fmul_rn(v, 1.0009765625f), dn = __fmul_rn(v, 0.9990234375f);
+                        float c0 = centroids[(int64_t)cj * d + j];
+                        float up = __fmul_rn(c0, 1.0009765625f), dn = __fmul_rn(c0, 0.9990234375f);
                         centroids[(int64_t)ci * d + j] = (j % 2 == 0) ? up : dn;
                         centroids[(int64_t)cj * d + j] = (j % 2 == 0) ? dn : up;
                     }
@@ -476,7 +500,7 @@ __global__ void __launch_bounds__(1024) k_finalize(const long long *__restrict__
             }
         }
         if (stats) {
-            stats[0] = (float)((double)accum[kd + k] * inv_obj_scale);
+            stats[0] = (float)fmax(obj, 0.0);
             stats[1] = (float)nsplit;
             stats[2] = (float)(tot * (double)k / ((double)n_total * (double)n_total));
             stats[3] = (float)ne;
@@ -556,10 +580,20 @@ int at_index_destroy(at_index *ix) {
     cudaFree(ix->cn);
     cudaFree(ix->op);
     cudaFree(ix->tc_scale);
+    cudaFree(ix->tc_max);
     cudaFree(ix->tc_counters);
     cudaFree(ix->part_lab);
     tc_rows_free(&ix->rows);
     delete ix;
+    return AT_OK;
+}
+
+// canonical norms + (d == 64) the tensor operands of the centroids currently in ix->c
+static int index_refresh(at_index *ix, cudaStream_t st) {
+    const bool tc = assign_tc_supported(ix);
+    k_centroid_norms<<<(ix->k + 127) / 128, 128, 0, st>>>(ix->c, ix->k, ix->d, ix->cn, tc ? ix->tc_max : nullptr);
+    AT_LAUNCH_OK();
+    if (tc) return assign_tc_prepare(ix, st);
     return AT_OK;
 }
 
@@ -576,7 +610,11 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
         AT_CUDA_OK(cudaMalloc(&ix->c, sizeof(float) * (size_t)k * ix->d));
         AT_CUDA_OK(cudaMalloc(&ix->cn, sizeof(float) * (size_t)k));
         if (ix->d == 64) {
-            AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 36864));
+            AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 20480));
+            if (!ix->tc_max) {
+                AT_CUDA_OK(cudaMalloc(&ix->tc_max, 2 * sizeof(unsigned int)));
+                AT_CUDA_OK(cudaMemsetAsync(ix->tc_max, 0, 2 * sizeof(unsigned int), st));
+            }
             if (!ix->tc_counters) {
                 AT_CUDA_OK(cudaMalloc(&ix->tc_counters, 8 * sizeof(unsigned long long)));
                 AT_CUDA_OK(cudaMemsetAsync(ix->tc_counters, 0, 8 * sizeof(unsigned long long), st));
@@ -588,10 +626,7 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
     ix->ktiles = (k + 127) / 128;
     if (centroids != ix->c)
         AT_CUDA_OK(cudaMemcpyAsync(ix->c, centroids, sizeof(float) * (size_t)k * ix->d, cudaMemcpyDeviceToDevice, st));
-    k_centroid_norms<<<(k + 127) / 128, 128, 0, st>>>(ix->c, k, ix->d, ix->cn);
-    AT_LAUNCH_OK();
-    if (assign_tc_supported(ix)) return assign_tc_prepare(ix, st);
-    return AT_OK;
+    return index_refresh(ix, st);
 }
 
 int at_index_ntotal(const at_index *ix) { return ix ? ix->k : 0; }
@@ -638,6 +673,7 @@ int at_kmeans_create(int d, int k, at_kmeans **out) {
     if (e == cudaSuccess) e = cudaMalloc(&km->cursor, sizeof(unsigned long long) * (size_t)k);
     if (e == cudaSuccess) e = cudaMalloc(&km->hassign, sizeof(float) * (size_t)k);
     if (e == cudaSuccess) e = cudaMalloc(&km->newc, sizeof(float) * (size_t)k * d);
+    if (e == cudaSuccess) e = cudaMalloc(&km->fin, sizeof(double) * 3 * (size_t)((k + FIN_WARPS - 1) / FIN_WARPS));
     if (e != cudaSuccess) {
         set_error("at_kmeans_create: cudaMalloc failed: %s", cudaGetErrorString(e));
         at_kmeans_destroy(km);
@@ -650,8 +686,8 @@ int at_kmeans_create(int d, int k, at_kmeans **out) {
 int at_kmeans_destroy(at_kmeans *km) {
     if (!km) return AT_OK;
     at_index_destroy(km->index);
-    cudaFree(km->labels), cudaFree(km->dist), cudaFree(km->order);
-    cudaFree(km->off), cudaFree(km->cursor), cudaFree(km->hassign), cudaFree(km->newc);
+    cudaFree(km->labels), cudaFree(km->order);
+    cudaFree(km->off), cudaFree(km->cursor), cudaFree(km->hassign), cudaFree(km->newc), cudaFree(km->fin);
     cudaFree(km->rows_sx);
     tc_rows_free(&km->rows);
     cudaFree(km->lacc), cudaFree(km->prev), cudaFree(km->d_row), cudaFree(km->d_lab), cudaFree(km->d_order);
@@ -719,7 +755,7 @@ int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total) {
         AT_CUDA_OK(cudaMemcpy(km->rows_sx, &sx, sizeof(float), cudaMemcpyHostToDevice));
         km->index->ext_sx = km->rows_sx;
         if (km->index->k > 0 && assign_tc_supported(km->index)) {
-            int rc = assign_tc_prepare(km->index, nullptr);
+            int rc = index_refresh(km->index, nullptr);
             if (rc != AT_OK) return rc;
             AT_CUDA_OK(cudaDeviceSynchronize());
         }
@@ -732,12 +768,11 @@ int64_t at_kmeans_accum_words(const at_kmeans *km) { return km ? (int64_t)km->k 
 static int km_reserve(at_kmeans *km, int64_t n, cudaStream_t st) {
     if (n <= km->ncap) return AT_OK;
     AT_CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(km->labels), cudaFree(km->dist), cudaFree(km->order);
+    cudaFree(km->labels), cudaFree(km->order);
     cudaFree(km->prev), cudaFree(km->d_row), cudaFree(km->d_lab), cudaFree(km->d_order);
-    km->labels = km->order = nullptr, km->dist = nullptr, km->ncap = 0;
+    km->labels = km->order = nullptr, km->ncap = 0;
     km->prev = km->d_row = km->d_lab = km->d_order = nullptr, km->prev_valid = false;
     AT_CUDA_OK(cudaMalloc(&km->labels, sizeof(int32_t) * (size_t)n));
-    AT_CUDA_OK(cudaMalloc(&km->dist, sizeof(float) * (size_t)n));
     AT_CUDA_OK(cudaMalloc(&km->order, sizeof(int32_t) * (size_t)n));
     AT_CUDA_OK(cudaMalloc(&km->prev, sizeof(int32_t) * (size_t)n));
     AT_CUDA_OK(cudaMalloc(&km->d_row, sizeof(int32_t) * (size_t)n * 2));
@@ -745,7 +780,7 @@ static int km_reserve(at_kmeans *km, int64_t n, cudaStream_t st) {
     AT_CUDA_OK(cudaMalloc(&km->d_order, sizeof(int32_t) * (size_t)n * 2));
     if (!km->d_count) AT_CUDA_OK(cudaMalloc(&km->d_count, sizeof(unsigned int)));
     if (!km->d_hist) AT_CUDA_OK(cudaMalloc(&km->d_hist, sizeof(unsigned long long) * (size_t)km->k));
-    if (!km->lacc) AT_CUDA_OK(cudaMalloc(&km->lacc, sizeof(unsigned long long) * ((size_t)km->k * km->d + km->k)));
+    if (!km->lacc) AT_CUDA_OK(cudaMalloc(&km->lacc, sizeof(unsigned long long) * ((size_t)km->k * km->d + km->k + 1)));
     km->ncap = n;
     return AT_OK;
 }
@@ -760,8 +795,10 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     cudaStream_t st = (cudaStream_t)stream;
     const int k = km->k, d = km->d;
     const int64_t kd = (int64_t)k * d;
-    AT_CUDA_OK(cudaMemsetAsync(accum, 0, sizeof(int64_t) * (size_t)(kd + k + 1), st));
-    if (n_local == 0) return AT_OK;
+    if (n_local == 0) {
+        AT_CUDA_OK(cudaMemsetAsync(accum, 0, sizeof(int64_t) * (size_t)(kd + k + 1), st));
+        return AT_OK;
+    }
     int rc = km_reserve(km, n_local, st);
     if (rc != AT_OK) return rc;
     int32_t *labels = labels32 ? labels32 : km->labels;
@@ -776,7 +813,7 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
         }
         rows = &km->rows;
     }
-    rc = index_search(km->index, x, n_local, 0, algo, labels, nullptr, km->dist, 0, rows, st);
+    rc = index_search(km->index, x, n_local, 0, algo, labels, nullptr, nullptr, 0, rows, st);
     if (rc != AT_OK) return rc;
     unsigned long long *acc = (unsigned long long *)accum;
     unsigned long long *lacc = km->lacc;
@@ -789,21 +826,22 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     const bool incremental = km->incremental_on && km->prev_valid && km->prev_x == x && km->prev_n == n_local;
     if (!incremental) {
         // every row: counts, cluster-grouped order, exact gather-sum into the persistent local accumulator
-        AT_CUDA_OK(cudaMemsetAsync(lacc, 0, sizeof(int64_t) * (size_t)(kd + k), st));
+        AT_CUDA_OK(cudaMemsetAsync(lacc, 0, sizeof(int64_t) * (size_t)(kd + k + 1), st));
         k_counts<<<blocks, 256, 0, st>>>(labels, n_local, lacc + kd);
-        AT_LAUNCH_OK();
-        k_objective<<<blocks, 256, 0, st>>>(km->dist, n_local, obj_scale, acc + kd + k);
         AT_LAUNCH_OK();
         k_scan_counts<<<1, 1024, 0, st>>>(lacc + kd, k, km->off, km->cursor);
         AT_LAUNCH_OK();
         k_place<<<blocks, 256, 0, st>>>(labels, n_local, km->cursor, km->order);
         AT_LAUNCH_OK();
         if (dpl <= 1)
-            k_gather_sum<1><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc);
+            k_gather_sum<1><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
+                                                         lacc + kd + k, obj_scale);
         else if (dpl == 2)
-            k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc);
+            k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
+                                                         lacc + kd + k, obj_scale);
         else
-            k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc);
+            k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
+                                                         lacc + kd + k, obj_scale);
         AT_LAUNCH_OK();
         AT_CUDA_OK(cudaMemcpyAsync(km->prev, labels, sizeof(int32_t) * (size_t)n_local, cudaMemcpyDeviceToDevice, st));
         km->prev_valid = true, km->prev_x = x, km->prev_n = n_local;
@@ -811,8 +849,7 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
         // only the rows whose label changed: two delta items each, grouped by cluster and summed exactly like the rest
         AT_CUDA_OK(cudaMemsetAsync(km->d_count, 0, sizeof(unsigned int), st));
         AT_CUDA_OK(cudaMemsetAsync(km->d_hist, 0, sizeof(unsigned long long) * (size_t)k, st));
-        k_diff<<<blocks, 256, 0, st>>>(labels, km->prev, km->dist, n_local, obj_scale, km->d_row, km->d_lab, km->d_count,
-                                      acc + kd + k);
+        k_diff<<<blocks, 256, 0, st>>>(labels, km->prev, n_local, km->d_row, km->d_lab, km->d_count);
         AT_LAUNCH_OK();
         k_counts<<<blocks, 256, 0, st>>>(km->d_lab, 0, km->d_hist, km->d_count, 2, km->d_row, lacc + kd);
         AT_LAUNCH_OK();
@@ -828,7 +865,7 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
             k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
         AT_LAUNCH_OK();
     }
-    AT_CUDA_OK(cudaMemcpyAsync(acc, lacc, sizeof(int64_t) * (size_t)(kd + k), cudaMemcpyDeviceToDevice, st));
+    AT_CUDA_OK(cudaMemcpyAsync(acc, lacc, sizeof(int64_t) * (size_t)(kd + k + 1), cudaMemcpyDeviceToDevice, st));
     return AT_OK;
 }
 
@@ -837,8 +874,12 @@ int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, flo
     AT_REQUIRE(km->begun, "at_kmeans_finalize: call at_kmeans_begin first");
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_FINALIZE, st);
-    k_finalize<<<1, 1024, 0, st>>>((const long long *)accum, km->k, km->d, n_total, ldexp(1.0, -km->e_sum),
-                                   ldexp(1.0, -km->e_obj), km->newc, km->hassign, stats);
+    const int nblk = (km->k + FIN_WARPS - 1) / FIN_WARPS;
+    k_finalize_div<<<nblk, FIN_WARPS * 32, 0, st>>>((const long long *)accum, km->k, km->d, ldexp(1.0, -km->e_sum),
+                                                  km->index->c, km->newc, km->hassign, km->fin);
+    AT_LAUNCH_OK();
+    k_finalize_split<<<1, 256, 0, st>>>((const long long *)accum, km->k, km->d, n_total, ldexp(1.0, -km->e_obj), km->fin,
+                                        nblk, km->newc, km->hassign, stats);
     AT_LAUNCH_OK();
     return at_index_set_centroids(km->index, km->newc, km->k, st);
 }

@@ -146,10 +146,11 @@ int at_kmeans_get_centroids(const at_kmeans *km, float *out, void *stream);
  * ALL ranks' rows (at_absmax computes the local one). */
 int at_absmax(const float *x, int64_t n_elems, float *out_dev, void *stream);
 int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total);
-/* Number of int64 words in the accumulator buffer: k*d sums + k counts + 1 objective. */
+/* Number of int64 words in the accumulator buffer: k*d sums + k counts + 1 (the sum of |x_i|^2, from which finalize
+ * derives the objective). */
 int64_t at_kmeans_accum_words(const at_kmeans *km);
 /* Search the local rows against the current centroids and accumulate per-cluster fixed-point sums, counts
- * and the objective into accum (device int64[at_kmeans_accum_words], overwritten).  labels32 may be NULL.
+ * and the sum of |x_i|^2 into accum (device int64[at_kmeans_accum_words], overwritten).  labels32 may be NULL.
  * Sums are exact integers, so adding the buffers of several ranks (all-reduce SUM on int64) gives a result
  * that does not depend on the rank count or on summation order. */
 int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2norm_rows, int algo,
