@@ -174,13 +174,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// arrive from one elected lane of a converged warp
+__device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+        "}" ::"r"(bar) : "memory");
+}
 // one non-blocking probe of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"   // test_wait never suspends the warp
         "selp.u32 %0, 1, 0, p;\n\t"
         "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
@@ -531,6 +540,8 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             for (int h = 0; h < 16; h++) bp[h] = 0xFFFFFFFFu;
             int j1 = 0, j2 = 0;                            // centroid tiles of g1, g2
             const int64_t row = (worker + i * workers) * SROWS + row_in_super;
+            const float erow_r = __ldg(erow + row);          // Sx |delta|
+            const float xnS = __ldg(xns + row);              // Sx^2 |x|^2
             // Accumulator read-out in eight 16-column loads through four register buffers: two loads are always in flight
             // behind a fold of two, and the first two loads of the NEXT tile are issued before the last fold of this one.
             if (!primed) {   // very first tile of this warp
@@ -561,7 +572,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(BAR_ACC_EMPTY + acc));  // accumulator is in registers: free it early
+                mbar_arrive_elect(BAR(BAR_ACC_EMPTY + acc));  // accumulator is in registers: free it early
                 // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
                 const bool more = (jt + 1 < ktiles) || (i + 1 < my_tiles);
                 const uint32_t vn = (u + 1) * RT + rt;
@@ -606,8 +617,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             // (the scale constants are re-read per super tile rather than held in registers across the scan)
             const float inv_s2 = __ldg(scale + SC_INV_S2), tau_abs = __ldg(scale + SC_TAU), cmax = __ldg(scale + SC_CMAX);
             const float R = __ldg(scale + SC_RATIO), emax = __ldg(scale + SC_EMAX);
-            const float e = R * __ldg(erow + row);           // S |delta|
-            const float xnS = __ldg(xns + row);              // Sx^2 |x|^2
+            const float e = R * erow_r;                      // S |delta|
             const float xnP = R * R * xnS;                   // S^2 |x|^2
             const bool fallback = !(xnP <= X_LIMIT * X_LIMIT);   // outside the accumulator range, Inf, NaN
             // ---- certification (accumulator units)
@@ -725,21 +735,23 @@ __global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, in
     }
 }
 
-// Uncertified rows without a usable candidate list (back of the tail array): exact scan of every centroid, a thread per
-// listed row with the row in registers and the centroids streamed through shared memory once per 64 rows -- the exact
-// SIMT kernel's arithmetic (canonical chunk partials + xor tree, strict '<' in ascending index order).
-constexpr int FULL_ROWS = 64, FULL_KT = 32;
-__global__ void __launch_bounds__(FULL_ROWS) k_tc_full(const float *__restrict__ x, int l2norm, const float *__restrict__ c,
-                                                       const float *__restrict__ cn, int k, const uint4 *__restrict__ tail,
-                                                       const unsigned int *__restrict__ tail_count, unsigned int tail_cap,
-                                                       int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
-                                                       float *__restrict__ dist) {
+// Uncertified rows without a usable candidate list (back of the tail array): exact scan of every centroid.  A block takes
+// 64 listed rows; four threads share a row (the row in registers in each), thread slice q scanning centroids 8q .. 8q+7
+// of every 32-centroid tile streamed through shared memory -- the exact SIMT kernel's arithmetic (canonical chunk
+// partials + xor tree); the lowest index wins exact ties.
+constexpr int FULL_ROWS = 64, FULL_KT = 32, FULL_SLICES = 4;
+__global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
+    const float *__restrict__ x, int l2norm, const float *__restrict__ c, const float *__restrict__ cn, int k,
+    const uint4 *__restrict__ tail, const unsigned int *__restrict__ tail_count, unsigned int tail_cap,
+    int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist) {
     __shared__ __align__(16) float ctile[FULL_KT][64];
     __shared__ float cns[FULL_KT];
-    const int tid = threadIdx.x;
+    __shared__ float s_bd[FULL_SLICES][FULL_ROWS];
+    __shared__ int s_best[FULL_SLICES][FULL_ROWS];
+    const int tid = threadIdx.x, r = tid & (FULL_ROWS - 1), q = tid / FULL_ROWS;
     const unsigned int n_full = tail_count[1];
     for (unsigned int base = blockIdx.x * FULL_ROWS; base < n_full; base += gridDim.x * FULL_ROWS) {
-        const unsigned int e = base + tid;
+        const unsigned int e = base + r;
         const bool live = e < n_full;
         const int64_t row = (int64_t)tail[tail_cap - 1 - (live ? e : base)].x;
         float xr[64];
@@ -751,48 +763,58 @@ __global__ void __launch_bounds__(FULL_ROWS) k_tc_full(const float *__restrict__
                 xr[4 * t] = v.x, xr[4 * t + 1] = v.y, xr[4 * t + 2] = v.z, xr[4 * t + 3] = v.w;
             }
         }
-        float q[16];
+        float qq[16];
         if (l2norm) {
 #pragma unroll
-            for (int l = 0; l < 16; l++) q[l] = 0.f;
+            for (int l = 0; l < 16; l++) qq[l] = 0.f;
 #pragma unroll
-            for (int t = 0; t < 64; t++) q[t >> 2] = fmaf(xr[t], xr[t], q[t >> 2]);
-            const float den = l2_denominator(tree16(q));
+            for (int t = 0; t < 64; t++) qq[t >> 2] = fmaf(xr[t], xr[t], qq[t >> 2]);
+            const float den = l2_denominator(tree16(qq));
 #pragma unroll
             for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
         }
 #pragma unroll
-        for (int l = 0; l < 16; l++) q[l] = 0.f;
+        for (int l = 0; l < 16; l++) qq[l] = 0.f;
 #pragma unroll
-        for (int t = 0; t < 64; t++) q[t >> 2] = fmaf(xr[t], xr[t], q[t >> 2]);
-        const float xn = tree16(q);
+        for (int t = 0; t < 64; t++) qq[t >> 2] = fmaf(xr[t], xr[t], qq[t >> 2]);
+        const float xn = tree16(qq);
         float bd = INFINITY;
-        int best = 0;
+        int best = 0x7FFFFFFF;
         for (int j0 = 0; j0 < k; j0 += FULL_KT) {
             const int kt = min(FULL_KT, k - j0);
             __syncthreads();   // the previous tile has been consumed
-            for (int i = tid; i < FULL_KT * 16; i += FULL_ROWS) {
+            for (int i = tid; i < FULL_KT * 16; i += FULL_ROWS * FULL_SLICES) {
                 const int jj = i >> 4;
                 reinterpret_cast<float4 *>(&ctile[0][0])[i] =
                     jj < kt ? __ldg(reinterpret_cast<const float4 *>(c + (size_t)j0 * 64) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (tid < FULL_KT) cns[tid] = tid < kt ? cn[j0 + tid] : INFINITY;
             __syncthreads();
-            for (int jj = 0; jj < kt; jj++) {
+#pragma unroll 2
+            for (int jj = q * (FULL_KT / FULL_SLICES); jj < (q + 1) * (FULL_KT / FULL_SLICES); jj++) {
 #pragma unroll
                 for (int l = 0; l < 16; l++) {
                     const float4 cv = *reinterpret_cast<const float4 *>(&ctile[jj][4 * l]);
-                    float s = xr[4 * l] * cv.x;
-                    s = fmaf(xr[4 * l + 1], cv.y, s);
-                    s = fmaf(xr[4 * l + 2], cv.z, s);
-                    s = fmaf(xr[4 * l + 3], cv.w, s);
-                    q[l] = s;
+                    float sacc = xr[4 * l] * cv.x;
+                    sacc = fmaf(xr[4 * l + 1], cv.y, sacc);
+                    sacc = fmaf(xr[4 * l + 2], cv.z, sacc);
+                    sacc = fmaf(xr[4 * l + 3], cv.w, sacc);
+                    qq[l] = sacc;
                 }
-                const float dj = l2_expanded(xn, cns[jj], tree16(q));
-                if (dj < bd) bd = dj, best = j0 + jj;
+                const float dj = l2_expanded(xn, cns[jj], tree16(qq));
+                if (jj < kt && dj < bd) bd = dj, best = j0 + jj;   // ascending index within the slice: strict '<'
             }
         }
-        if (live) {
+        s_bd[q][r] = bd, s_best[q][r] = best;
+        __syncthreads();
+        if (q == 0 && live) {
+#pragma unroll
+            for (int o = 1; o < FULL_SLICES; o++) {
+                const float od = s_bd[o][r];
+                const int ob = s_best[o][r];
+                if (od < bd || (od == bd && ob < best)) bd = od, best = ob;
+            }
+            if (best == 0x7FFFFFFF) best = 0;   // every distance NaN: label 0 like the exact kernel
             if (labels32) labels32[row] = best;
             if (labels64) labels64[row] = best;
             if (dist) dist[row] = bd;
@@ -926,7 +948,7 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     k_tc_tail<<<sms * 8, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, rows->tail, rows->tail_count, l32, labels64, kdist,
                                       ix->tc_counters);
     AT_LAUNCH_OK();
-    k_tc_full<<<sms * 4, FULL_ROWS, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
+    k_tc_full<<<sms * 4, FULL_ROWS * FULL_SLICES, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
                                             (unsigned int)rows->cap, l32, labels64, kdist);
     AT_LAUNCH_OK();
     if (dist && exact_dist) {
