@@ -12,8 +12,22 @@ from .synth import sine_table, synth_clips
 
 __all__ = [
     "_lib", "MelPlan", "FlatL2", "IndexFlatL2", "Kmeans", "ClusteringParameters", "LloydTrainer",
-    "synth_clips", "sine_table", "get_num_gpus", "row_l2norm",
+    "synth_clips", "sine_table", "get_num_gpus", "row_l2norm", "pcm16_to_f32",
 ]
+
+
+def pcm16_to_f32(pcm, out=None):
+    """16-bit PCM CUDA tensor -> fp32 waveform in [-1, 1) (sample / 32768: what torchaudio.load yields for a 16-bit
+    file, processors/spectrogram_generator.py:99)."""
+    import torch
+
+    _lib.require_cuda()
+    assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+    if out is None:
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+    assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= pcm.numel()
+    _lib.check(_lib.load().at_pcm16_to_f32(_lib.ptr(pcm), pcm.numel(), _lib.ptr(out), _lib.stream_ptr()))
+    return out
 
 
 def get_num_gpus() -> int:

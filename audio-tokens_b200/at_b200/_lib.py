@@ -50,6 +50,7 @@ PROTOTYPES = {
     "at_kmeans_accumulate": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "at_kmeans_finalize": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "at_kmeans_set_incremental": (c_int, [c_ptr, c_int]),
+    "at_pcm16_to_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "at_bincount": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     "at_synth_clips": (c_int, [ctypes.c_uint32, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "at_rand_perm_host": (c_int, [c_ptr, c_i64, c_i64]),

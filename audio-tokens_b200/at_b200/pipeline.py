@@ -85,11 +85,14 @@ class HotPath:
         return tok, cents, bad
 
     def run_host(self, wave_host, bufs, chunk_clips=296, row_offset=0, n_total=None):
-        """End to end from HOST memory: wave_host (B, L) pinned fp32 tensor.  Chunks are copied H2D on a copy stream
-        while the mel kernel works on the previous chunk; tokens (int64) and centroids are copied back into the
-        pinned host tensors bufs["tokens_host"], bufs["centroids_host"].  Blocks until they are there."""
+        """End to end from HOST memory: wave_host (B, L) pinned tensor, fp32 waveforms or the decoder's int16 PCM (half
+        the PCIe bytes; widened on the device with at_pcm16_to_f32, bufs from alloc_bufs(..., pcm16=True)).  Chunks are
+        copied H2D on a copy stream while the mel kernel works on the previous chunk; tokens (int64) and centroids are
+        copied back into the pinned host tensors bufs["tokens_host"], bufs["centroids_host"].  Blocks until they are
+        there."""
         import torch
 
+        pcm16 = wave_host.dtype == torch.int16
         B, L = wave_host.shape
         T = self.plan.num_frames(L)
         spec, l2 = bufs["spec"], bufs["l2"]
@@ -105,10 +108,13 @@ class HotPath:
             with torch.cuda.stream(copy):
                 if ev_free[sb] is not None:
                     copy.wait_event(ev_free[sb])
-                stage[sb, :nb].copy_(wave_host[b0:b0 + nb], non_blocking=True)
+                (bufs["stage16"] if pcm16 else stage)[sb, :nb].copy_(wave_host[b0:b0 + nb], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
             main.wait_event(ev)
+            if pcm16:
+                _lib.check(self.plan.lib.at_pcm16_to_f32(_lib.ptr(bufs["stage16"][sb]), nb * L, _lib.ptr(stage[sb]),
+                                                         _lib.stream_ptr()))
             _lib.check(self.plan.lib.at_mel_forward(self.plan.h, _lib.ptr(stage[sb]), None, None, L, nb,
                                                     _lib.ptr(spec[b0:]), _lib.ptr(l2[b0:]), _lib.ptr(bad[b0:]),
                                                     _lib.stream_ptr()))
@@ -121,7 +127,7 @@ class HotPath:
         main.synchronize()
         return bufs["tokens_host"], bufs["centroids_host"], bufs["bad_host"]
 
-    def alloc_bufs(self, B, L, host=False, chunk_clips=296):
+    def alloc_bufs(self, B, L, host=False, chunk_clips=296, pcm16=False):
         import torch
 
         T = self.plan.num_frames(L)
@@ -138,4 +144,6 @@ class HotPath:
                 centroids_host=torch.empty((self.k, self.d), dtype=torch.float32, pin_memory=True),
                 bad_host=torch.empty(B, dtype=torch.int32, pin_memory=True),
             )
+            if pcm16:
+                bufs["stage16"] = torch.empty((2, chunk_clips, L), dtype=torch.int16, device="cuda")
         return bufs

@@ -139,6 +139,28 @@ __global__ void k_synth(uint32_t seed, int64_t first, int64_t n_samples, const i
 
 using namespace at;
 
+// 16-bit PCM -> fp32 in [-1, 1): sample / 32768, exactly what torchaudio.load(normalize=True) returns for a 16-bit file
+// (processors/spectrogram_generator.py:99).  Eight samples per thread step when both pointers allow 16-byte accesses.
+__global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t *__restrict__ pcm, int64_t n, float *__restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(pcm) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t n8 = vec ? n >> 3 : 0;
+    for (int64_t i = tid; i < n8; i += nth) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(pcm) + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            f[2 * j] = (float)(int16_t)(w[j] & 0xFFFFu) * (1.0f / 32768.0f);
+            f[2 * j + 1] = (float)(int16_t)(w[j] >> 16) * (1.0f / 32768.0f);
+        }
+        float4 *o = reinterpret_cast<float4 *>(out) + 2 * i;
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (int64_t i = (n8 << 3) + tid; i < n; i += nth) out[i] = (float)pcm[i] * (1.0f / 32768.0f);
+}
+
 extern "C" {
 
 int at_version(void) { return AT_B200_VERSION; }
@@ -186,6 +208,16 @@ int at_absmax(const float *x, int64_t n_elems, float *out_dev, void *stream) {
     int blocks = (int)(ceil_div(n_elems, 256 * 8) < (int64_t)sm_count() * 8 ? ceil_div(n_elems, 256 * 8) : (int64_t)sm_count() * 8);
     if (blocks < 1) blocks = 1;
     k_absmax<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n_elems, out_dev);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+int at_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, void *stream) {
+    AT_REQUIRE(pcm && out && n >= 0, "at_pcm16_to_f32: bad arguments");
+    if (n == 0) return AT_OK;
+    int blocks = sm_count() * 16;
+    if (blocks < 1) blocks = 1;
+    k_pcm16_to_f32<<<blocks, 256, 0, (cudaStream_t)stream>>>(pcm, n, out);
     AT_LAUNCH_OK();
     return AT_OK;
 }

@@ -171,6 +171,13 @@ int at_kmeans_set_incremental(at_kmeans *km, int on);
 int at_rand_perm_host(int32_t *perm, int64_t n, int64_t seed);
 
 /* ------------------------------------------------------------------------------------------------
+ * 16-bit PCM -> fp32 waveform (the step before the path: processors/spectrogram_generator.py:97-107,
+ * preprocess_waveform -> torchaudio.load, which yields sample / 32768 for a 16-bit file).  Lets a caller ship
+ * the decoder's native int16 samples over PCIe (half the bytes) and widen them on the device; device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+int at_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Token histogram (SpecTokenizer.analyze_tokens' Counter) and int32 -> int64 widening
  * ---------------------------------------------------------------------------------------------- */
 int at_bincount(const int32_t *labels, int64_t n, int k, int64_t *counts, void *stream);

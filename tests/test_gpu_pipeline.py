@@ -140,3 +140,25 @@ def test_hot_path_in_hbm_matches_the_staged_classes(tmp_path):
     wh.copy_(wave)
     th, ch, bh = hp.run_host(wh, hb, chunk_clips=8)
     assert torch.equal(th.cuda(), tok) and torch.equal(ch.cuda(), cents)
+
+
+def test_pcm16_host_path_matches_fp32_host_path():
+    """16-bit PCM host buffers (half the PCIe bytes, widened on the device as sample / 32768 like torchaudio.load) give
+    bit-identical tokens and centroids to the fp32 host path."""
+    import torch
+    from at_b200 import pcm16_to_f32, synth_clips
+    from at_b200.pipeline import HotPath
+
+    B, L, K = 48, 22050, 64
+    wave = synth_clips(4242, 0, B, L)
+    pcm = (wave * 32768.0).to(torch.int16)
+    assert torch.equal(pcm16_to_f32(pcm), wave)
+    odd = pcm.reshape(-1)[1:1001].clone()          # unaligned source pointer: scalar path
+    assert torch.equal(pcm16_to_f32(odd), wave.reshape(-1)[1:1001])
+    hp = HotPath(22050, 1024, 512, 64, True, K, 3)
+    outs = []
+    for host in (wave.cpu().pin_memory(), pcm.cpu().pin_memory()):
+        bufs = hp.alloc_bufs(B, L, host=True, chunk_clips=20, pcm16=host.dtype == torch.int16)
+        tok, cen, bad = hp.run_host(host, bufs, chunk_clips=20)
+        outs.append((tok.clone(), cen.clone(), bad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
