@@ -511,9 +511,13 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                     tc_fence_after();
                     const uint32_t d = tmem + acc * TN;
                     // descriptor start addresses are in 16-byte units: a K step of 16 fp16 = 32 bytes = +2
+#ifdef AT_TC_ONE_MMA   // timing experiment only (wrong results): how much of the scan's time is spent waiting for the MMAs
+                    umma_f16(d, dA_aug, dB_aug, IDESC, 0);
+#else
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_hi + 2 * kk, IDESC, kk > 0);
                     umma_f16(d, dA_aug, dB_aug, IDESC, 1);
+#endif
                     umma_commit(BAR(BAR_ACC_FULL + acc));
                 }
                 if (!RESIDENT) {
@@ -568,11 +572,15 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 tmem_ld_wait();
                 tmem_ld16(ta + 96, c2);
                 tmem_ld16(ta + 112, c3);
-                fold32(c0, c1, 64, key_mul, t1, t2, t3, bp);
+                // Release the accumulator as soon as its last columns are in registers, i.e. half way through the tile's
+                // scan (a short stall on the load latency, covered by the scheduler's other scanning warps): the three
+                // scanning groups of a CTA run in lockstep and share ONE spare TMEM slot, so a slot released after the
+                // third fold would have the next round of MMAs finish after the groups need them.
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                mbar_arrive_elect(BAR(BAR_ACC_EMPTY + acc));  // accumulator is in registers: free it early
+                mbar_arrive_elect(BAR(BAR_ACC_EMPTY + acc));
+                fold32(c0, c1, 64, key_mul, t1, t2, t3, bp);
                 // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
                 const bool more = (jt + 1 < ktiles) || (i + 1 < my_tiles);
                 const uint32_t vn = (u + 1) * RT + rt;
@@ -736,10 +744,11 @@ __global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, in
 }
 
 // Uncertified rows without a usable candidate list (back of the tail array): exact scan of every centroid.  A block takes
-// 64 listed rows; four threads share a row (the row in registers in each), thread slice q scanning centroids 8q .. 8q+7
-// of every 32-centroid tile streamed through shared memory -- the exact SIMT kernel's arithmetic (canonical chunk
-// partials + xor tree); the lowest index wins exact ties.
-constexpr int FULL_ROWS = 64, FULL_KT = 32, FULL_SLICES = 4;
+// 32 listed rows; its eight warps share them (lane = row, the row in registers in each warp), warp q scanning centroids
+// 4q .. 4q+3 of every 32-centroid tile streamed through shared memory (the next tile is fetched into registers while the
+// current one is scanned) -- the exact SIMT kernel's arithmetic (canonical chunk partials + xor tree); the lowest index
+// wins exact ties.
+constexpr int FULL_ROWS = 32, FULL_KT = 32, FULL_SLICES = 8;
 __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
     const float *__restrict__ x, int l2norm, const float *__restrict__ c, const float *__restrict__ cn, int k,
     const uint4 *__restrict__ tail, const unsigned int *__restrict__ tail_count, unsigned int tail_cap,
@@ -750,6 +759,10 @@ __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
     __shared__ int s_best[FULL_SLICES][FULL_ROWS];
     const int tid = threadIdx.x, r = tid & (FULL_ROWS - 1), q = tid / FULL_ROWS;
     const unsigned int n_full = tail_count[1];
+    constexpr int PER = FULL_KT / FULL_SLICES;                      // centroids per warp per tile
+    constexpr int LD = FULL_KT * 16 / (FULL_ROWS * FULL_SLICES);    // float4 per thread per tile
+    const float4 *c4 = reinterpret_cast<const float4 *>(c);
+    const int64_t c4_total = (int64_t)k * 16;
     for (unsigned int base = blockIdx.x * FULL_ROWS; base < n_full; base += gridDim.x * FULL_ROWS) {
         const unsigned int e = base + r;
         const bool live = e < n_full;
@@ -780,18 +793,32 @@ __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
         const float xn = tree16(qq);
         float bd = INFINITY;
         int best = 0x7FFFFFFF;
+        float4 pre[LD];
+        float pre_cn = INFINITY;
+#pragma unroll
+        for (int t = 0; t < LD; t++) {
+            const int64_t i4 = tid + t * (FULL_ROWS * FULL_SLICES);
+            pre[t] = i4 < c4_total ? __ldg(c4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tid < FULL_KT) pre_cn = tid < k ? cn[tid] : INFINITY;
         for (int j0 = 0; j0 < k; j0 += FULL_KT) {
-            const int kt = min(FULL_KT, k - j0);
             __syncthreads();   // the previous tile has been consumed
-            for (int i = tid; i < FULL_KT * 16; i += FULL_ROWS * FULL_SLICES) {
-                const int jj = i >> 4;
-                reinterpret_cast<float4 *>(&ctile[0][0])[i] =
-                    jj < kt ? __ldg(reinterpret_cast<const float4 *>(c + (size_t)j0 * 64) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (tid < FULL_KT) cns[tid] = tid < kt ? cn[j0 + tid] : INFINITY;
+#pragma unroll
+            for (int t = 0; t < LD; t++) reinterpret_cast<float4 *>(&ctile[0][0])[tid + t * (FULL_ROWS * FULL_SLICES)] = pre[t];
+            if (tid < FULL_KT) cns[tid] = pre_cn;
             __syncthreads();
-#pragma unroll 2
-            for (int jj = q * (FULL_KT / FULL_SLICES); jj < (q + 1) * (FULL_KT / FULL_SLICES); jj++) {
+            const int jn = j0 + FULL_KT;   // fetch the next tile while this one is scanned
+            if (jn < k) {
+#pragma unroll
+                for (int t = 0; t < LD; t++) {
+                    const int64_t i4 = (int64_t)jn * 16 + tid + t * (FULL_ROWS * FULL_SLICES);
+                    pre[t] = i4 < c4_total ? __ldg(c4 + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (tid < FULL_KT) pre_cn = jn + tid < k ? cn[jn + tid] : INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int jj = q * PER + u;
 #pragma unroll
                 for (int l = 0; l < 16; l++) {
                     const float4 cv = *reinterpret_cast<const float4 *>(&ctile[jj][4 * l]);
@@ -802,7 +829,7 @@ __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
                     qq[l] = sacc;
                 }
                 const float dj = l2_expanded(xn, cns[jj], tree16(qq));
-                if (jj < kt && dj < bd) bd = dj, best = j0 + jj;   // ascending index within the slice: strict '<'
+                if (j0 + jj < k && dj < bd) bd = dj, best = j0 + jj;   // ascending index within the slice: strict '<'
             }
         }
         s_bd[q][r] = bd, s_best[q][r] = best;
@@ -948,7 +975,7 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     k_tc_tail<<<sms * 8, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, rows->tail, rows->tail_count, l32, labels64, kdist,
                                       ix->tc_counters);
     AT_LAUNCH_OK();
-    k_tc_full<<<sms * 4, FULL_ROWS * FULL_SLICES, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
+    k_tc_full<<<sms * 8, FULL_ROWS * FULL_SLICES, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
                                             (unsigned int)rows->cap, l32, labels64, kdist);
     AT_LAUNCH_OK();
     if (dist && exact_dist) {
