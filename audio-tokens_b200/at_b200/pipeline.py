@@ -127,6 +127,79 @@ class HotPath:
         main.synchronize()
         return bufs["tokens_host"], bufs["centroids_host"], bufs["bad_host"]
 
+    def stream_tokenize(self, host_chunks, centroids, chunk_clips=296):
+        """Spectrogram -> tokens for a stream of HOST chunks with fixed centroids (the unbalanced-train shape: far more
+        clips than fit in HBM, SpectrogramGenerator.run + SpecTokenizer.run without the spectrogram files in between).
+
+        host_chunks: iterable of pinned (nb <= chunk_clips, L) tensors, fp32 waveforms or int16 PCM, same L throughout.
+        centroids: (k, d) fp32 CUDA tensor, unit-norm rows as ClusterCreator saves them.
+        Yields (tokens int64 pinned host tensor (nb * T,), bad int32 pinned host tensor (nb,)) per chunk, in order; the
+        copy of chunk i+1 and the read-back of chunk i-1 overlap the kernels of chunk i.  The yielded tensors are
+        re-used two chunks later: consume (or copy) them before advancing twice."""
+        import torch
+
+        self.index.set_centroids(centroids)
+        main = torch.cuda.current_stream()
+        copy_in, copy_out = torch.cuda.Stream(), torch.cuda.Stream()
+        st = None
+        prev = None
+        for ci, chunk in enumerate(host_chunks):
+            nb, L = chunk.shape
+            assert nb <= chunk_clips
+            pcm16 = chunk.dtype == torch.int16
+            T = self.plan.num_frames(L)
+            if st is None:
+                st = dict(
+                    L=L,
+                    stage=torch.empty((2, chunk_clips, L), dtype=torch.float32, device="cuda"),
+                    stage16=torch.empty((2, chunk_clips, L), dtype=torch.int16, device="cuda") if pcm16 else None,
+                    spec=torch.empty((2, chunk_clips, T, self.d), dtype=torch.float32, device="cuda"),
+                    tok=torch.empty((2, chunk_clips * T), dtype=torch.int64, device="cuda"),
+                    bad=torch.zeros((2, chunk_clips), dtype=torch.int32, device="cuda"),
+                    tok_h=torch.empty((2, chunk_clips * T), dtype=torch.int64, pin_memory=True),
+                    bad_h=torch.empty((2, chunk_clips), dtype=torch.int32, pin_memory=True),
+                    free=[None, None], done=[None, None])
+            assert L == st["L"], "stream_tokenize: every chunk must have the same clip length"
+            sb = ci & 1
+            with torch.cuda.stream(copy_in):
+                if st["free"][sb] is not None:
+                    copy_in.wait_event(st["free"][sb])
+                (st["stage16"] if pcm16 else st["stage"])[sb, :nb].copy_(chunk, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_in)
+            main.wait_event(ev)
+            if st["done"][sb] is not None:
+                main.wait_event(st["done"][sb])   # the read-back of this slot's previous tokens has finished
+            if pcm16:
+                _lib.check(self.plan.lib.at_pcm16_to_f32(_lib.ptr(st["stage16"][sb]), nb * L, _lib.ptr(st["stage"][sb]),
+                                                         _lib.stream_ptr()))
+            st["bad"][sb].zero_()
+            _lib.check(self.plan.lib.at_mel_forward(self.plan.h, _lib.ptr(st["stage"][sb]), None, None, L, nb,
+                                                    _lib.ptr(st["spec"][sb]), None, _lib.ptr(st["bad"][sb]),
+                                                    _lib.stream_ptr()))
+            st["free"][sb] = torch.cuda.Event()
+            st["free"][sb].record(main)
+            self.index.search(st["spec"][sb, :nb].reshape(-1, self.d), l2norm_rows=True, algo=self.algo, want_dist=False,
+                              labels_dtype=torch.int64, labels=st["tok"][sb, :nb * T])
+            ev2 = torch.cuda.Event()
+            ev2.record(main)
+            with torch.cuda.stream(copy_out):
+                copy_out.wait_event(ev2)
+                st["tok_h"][sb, :nb * T].copy_(st["tok"][sb, :nb * T], non_blocking=True)
+                st["bad_h"][sb, :nb].copy_(st["bad"][sb, :nb], non_blocking=True)
+                st["done"][sb] = torch.cuda.Event()
+                st["done"][sb].record(copy_out)
+            if prev is not None:
+                psb, pn = prev
+                st["done"][psb].synchronize()
+                yield st["tok_h"][psb, :pn * T], st["bad_h"][psb, :pn]
+            prev = (sb, nb)
+        if prev is not None:
+            psb, pn = prev
+            st["done"][psb].synchronize()
+            T = self.plan.num_frames(st["L"])
+            yield st["tok_h"][psb, :pn * T], st["bad_h"][psb, :pn]
+
     def alloc_bufs(self, B, L, host=False, chunk_clips=296, pcm16=False):
         import torch
 

@@ -3,6 +3,7 @@ processors/spectrogram_generator.py, with the per-clip torchaudio transform repl
 fused sm_100a mel kernel (at_mel_forward) per ``spectrogram_batch_size`` clips."""
 import json
 import logging
+from concurrent.futures import ThreadPoolExecutor
 import os
 import shutil
 from pathlib import Path
@@ -28,6 +29,8 @@ class SpectrogramGenerator:
         self._plan_db = self.plan if not c.normalize else MelPlan(c.common_sr, c.n_fft, c.hop_length, c.n_mels, False)
         with open(config.split_file, "r") as f:
             self.data_split = json.load(f)
+        self.writer_threads = 8
+        self._last_batch = None   # frame-major device tensor of the last populate_specs call
 
     # ------------------------------------------------------------------ driver (reference :39-61)
     def run(self):
@@ -38,12 +41,22 @@ class SpectrogramGenerator:
             output_dir.mkdir(parents=True)
             ytids = self.data_split[split]
             bs = self.config.spectrogram_batch_size
-            for i in tqdm(range(0, len(ytids), bs), total=len(ytids) // bs, position=0):
-                specs = self.populate_specs(ytids[i: i + bs])
-                for spec in specs:
-                    ytid = spec["filename"].replace(".flac", "")
-                    # (n_mels, T) view of a frame-major tile: np.save writes fortran_order=True like the reference
-                    np.save(output_dir / f"{ytid}.npy", spec["spec"].cpu())
+            pending = []
+            with ThreadPoolExecutor(max_workers=self.writer_threads) as pool:
+                for i in tqdm(range(0, len(ytids), bs), total=len(ytids) // bs, position=0):
+                    specs = self.populate_specs(ytids[i: i + bs])
+                    if not specs:
+                        continue
+                    # one device->host copy per batch (the reference pays one per clip), then the clips' .npy files are
+                    # written by a small thread pool while the next batch is decoded and transformed
+                    host = self._last_batch.to("cpu", non_blocking=False).numpy()
+                    for spec in specs:
+                        ytid = spec["filename"].replace(".flac", "")
+                        a, b = spec["rows"]
+                        # (n_mels, T) view of a frame-major tile: np.save writes fortran_order=True like the reference
+                        pending.append(pool.submit(np.save, output_dir / f"{ytid}.npy", host[a:b].T))
+                for f in pending:
+                    f.result()
             self.logger.info(f"{split.capitalize()} spectrograms saved to: {output_dir}")
 
     # ------------------------------------------------------------------ batch body (reference :63-85)
@@ -66,6 +79,7 @@ class SpectrogramGenerator:
         if not waves:
             return []
         out, fo, bad = self.plan.forward_ragged(waves)
+        self._last_batch = out
         bad = bad.cpu().tolist()
         specs = []
         for i, name in enumerate(names):
@@ -76,7 +90,8 @@ class SpectrogramGenerator:
             if bad[i]:
                 self.logger.debug(f"Bad file: {name}")
                 continue
-            specs.append({"filename": os.path.basename(str(name)), "spec": out[fo[i]:fo[i + 1]].T})
+            specs.append({"filename": os.path.basename(str(name)), "spec": out[fo[i]:fo[i + 1]].T,
+                          "rows": (int(fo[i]), int(fo[i + 1]))})
         return specs
 
     # ------------------------------------------------------------------ helpers (reference :87-146)

@@ -200,6 +200,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("AT_NCCL_DEBUG", "WARN")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from at_b200 import _lib, synth_clips
     from at_b200.pipeline import HotPath

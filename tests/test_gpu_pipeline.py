@@ -162,3 +162,52 @@ def test_pcm16_host_path_matches_fp32_host_path():
         tok, cen, bad = hp.run_host(host, bufs, chunk_clips=20)
         outs.append((tok.clone(), cen.clone(), bad.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_streaming_spectrogram_to_tokens_matches_the_staged_path():
+    """C5 shape in miniature: host chunks streamed through mel -> tokenize with fixed centroids (K = 4096) give the
+    tokens the staged path (mel of everything, then one search) gives; fp32 and int16 PCM host chunks agree."""
+    import torch
+    from at_b200 import FlatL2, MelPlan, row_l2norm, synth_clips
+    from at_b200.pipeline import HotPath
+
+    B, L, K, CH = 100, 22050, 4096, 24
+    wave = synth_clips(4242, 0, B, L)
+    plan = MelPlan(22050, 1024, 512, 64, True)
+    spec, bad, l2 = plan.forward(wave, want_l2=True)
+    rows = l2.reshape(-1, 64)
+    cents = row_l2norm(rows[torch.randperm(rows.shape[0], device="cuda", generator=torch.Generator("cuda").manual_seed(1))[:K]].contiguous())
+    ix = FlatL2(64)
+    ix.set_centroids(cents)
+    want, _ = ix.search(spec.reshape(-1, 64).contiguous(), l2norm_rows=True, want_dist=False, labels_dtype=torch.int64)
+    hp = HotPath(22050, 1024, 512, 64, True, K, 1)
+    for dtype in (torch.float32, torch.int16):
+        host = (wave if dtype == torch.float32 else (wave * 32768.0).to(torch.int16)).cpu().pin_memory()
+        chunks = [host[b0:b0 + CH] for b0 in range(0, B, CH)]
+        got, flags = [], []
+        for tok, bd in hp.stream_tokenize(iter(chunks), cents, chunk_clips=CH):
+            got.append(tok.clone()), flags.append(bd.clone())
+        got = torch.cat(got)
+        assert torch.equal(got, want.cpu())
+        assert int(torch.cat(flags).sum()) == 0
+
+
+def test_large_vocab_tensor_search_matches_exact_scan():
+    """C4 regime (K = 16384): the tcgen05 search returns the exact fp32 kernel's labels."""
+    import torch
+    from at_b200 import FlatL2, MelPlan, _lib, row_l2norm, synth_clips
+
+    wave = synth_clips(4242, 0, 400, 22050)
+    plan = MelPlan(22050, 1024, 512, 64, True)
+    _, _, l2 = plan.forward(wave, want_l2=True)
+    rows = l2.reshape(-1, 64).contiguous()          # 400 * 44 = 17,600 rows
+    K = 16384
+    g = torch.Generator("cuda").manual_seed(7)
+    cents = (rows[torch.randperm(rows.shape[0], device="cuda", generator=g)[:K]] +
+             0.01 * torch.randn(K, 64, device="cuda", generator=g)).contiguous()
+    ix = FlatL2(64)
+    ix.set_centroids(cents)
+    a, da = ix.search(rows, algo=_lib.ALGO_SIMT)
+    b, db = ix.search(rows, algo=_lib.ALGO_TENSOR)
+    assert torch.equal(a, b)
+    assert torch.equal(da, db)
