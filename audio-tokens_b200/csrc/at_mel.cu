@@ -412,7 +412,9 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                     const float *w = wt + woff[m];
                     for (int i = 0; i < 4 * cnt4; i++) acc = fmaf(__ldg(w + i), prow[i], acc);
                 }
-                dtile[f * dstride + m] = 10.0f * log10f(fmaxf(acc, 1e-10f));
+                // 10 log10(x) = (10 log10 2) log2(x): MUFU.LG2 (relative error 2^-22) instead of the ~25-instruction log10f;
+                // the result differs from torch's by < 3e-5 dB over the whole range (gate: 1e-4 of the clip's range)
+                dtile[f * dstride + m] = 3.01029995663981195f * __log2f(fmaxf(acc, 1e-10f));
             }
         }
         group_sync(grp);
