@@ -64,13 +64,22 @@ constexpr int TM = 128;          // rows per MMA tile (UMMA M)
 constexpr int TN = 128;          // centroids per tile (UMMA N)
 constexpr int RT = 3;            // row tiles per super tile
 constexpr int SROWS = RT * TM;   // 384
-constexpr int B_SLOTS = 4;       // operand tiles resident per CTA / ring depth
+// SPLIT_C (build-time experiment, off): the centroid operand as the sum of two fp16 tiles (hi + lo, ~22 significant bits)
+// multiplied in two passes (9 MMAs per accumulator instead of 5).  The certification threshold then loses its dominant term
+// (the centroids' fp16 rounding) and 4-5x fewer rows reach the tail kernels, and the scan still hides the MMAs -- but the
+// board reaches its power cap (SM clock 1,965 -> 1,837 MHz measured) and the whole step is 15 % slower: 5 MMAs it is.
+#ifndef AT_TC_SPLIT_C
+#define AT_TC_SPLIT_C 0
+#endif
+constexpr bool SPLIT_C = AT_TC_SPLIT_C != 0;
+constexpr int B_SLOTS = SPLIT_C ? 2 : 4;   // operand tiles resident per CTA / ring depth
 constexpr int ACC_SLOTS = 4;     // 128-column accumulators in TMEM, used as a ring by consecutive (centroid tile, row tile) pairs
 constexpr uint32_t A_MAIN_BYTES = TM * 128;              // 128 rows x 64 fp16
 constexpr uint32_t AUG_BYTES = TM * 32;                  // 128 rows x 16 fp16, no-swizzle core matrices
 constexpr uint32_t A_TILE_BYTES = A_MAIN_BYTES + AUG_BYTES;      // 20,480
 constexpr uint32_t A_BUF_BYTES = RT * A_TILE_BYTES;              // 61,440
-constexpr uint32_t B_TILE_BYTES = TN * 128 + TN * 32;            // main | aug = 20,480
+constexpr uint32_t B_MAIN_BYTES = (SPLIT_C ? 2 : 1) * TN * 128;   // hi [| lo]
+constexpr uint32_t B_TILE_BYTES = B_MAIN_BYTES + TN * 32;        // hi [| lo] | aug = 20,480 or 36,864
 
 // shared memory map (dynamic, 1024-B aligned base)
 constexpr uint32_t OFF_A = 0;                                    // 2 buffers
@@ -267,16 +276,21 @@ __global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, co
     unsigned char *tile = op + (size_t)(j / TN) * B_TILE_BYTES;
     const int r = j % TN;
     const int js = j < k ? j : k - 1;
-    __align__(16) __half hi[8];
+    __align__(16) __half hi[8], lo[8];
     float e2 = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const float v = -2.0f * Sc * c[(size_t)js * 64 + chunk * 8 + e];
         hi[e] = __float2half_rn(v);
-        const float err = v - __half2float(hi[e]);
+        float err = v - __half2float(hi[e]);
+        if (SPLIT_C) {
+            lo[e] = __float2half_rn(err);
+            err -= __half2float(lo[e]);
+        }
         e2 = fmaf(err, err, e2);
     }
     *reinterpret_cast<uint4 *>(tile + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(hi);
+    if (SPLIT_C) *reinterpret_cast<uint4 *>(tile + TN * 128 + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(lo);
     e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
     e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
     e2 += __shfl_xor_sync(0xffffffffu, e2, 4);
@@ -293,7 +307,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, co
         a[0] = a[1] = a[2] = w;
         split3(fmaf(cn[js], S * S * AUG_INV, (j < k ? BIAS : BIAS + PAD_BUMP) * AUG_INV), a[3], a[4], a[5]);
         a[6] = a[7] = zero;
-        unsigned char *aug = tile + TN * 128;
+        unsigned char *aug = tile + B_MAIN_BYTES;
         *reinterpret_cast<uint4 *>(aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
         *reinterpret_cast<uint4 *>(aug + aug_off(r, 1)) = make_uint4(0, 0, 0, 0);
     }
@@ -501,7 +515,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 const uint32_t slot = RESIDENT ? (uint32_t)jt : st;
                 if (!RESIDENT || i == 0) mbar_wait(BAR(BAR_B_FULL + slot), RESIDENT ? 0u : bph);
                 const uint32_t b_hi = base + OFF_B + slot * B_TILE_BYTES;
-                const uint64_t dB_hi = desc_sw128(b_hi), dB_aug = desc_nosw(b_hi + TN * 128);
+                const uint64_t dB_hi = desc_sw128(b_hi), dB_lo = desc_sw128(b_hi + TN * 128), dB_aug = desc_nosw(b_hi + B_MAIN_BYTES);
 #pragma unroll
                 for (int rt = 0; rt < RT; rt++) {
                     const uint32_t a_hi = a0 + rt * A_TILE_BYTES;
@@ -516,6 +530,10 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
 #else
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_hi + 2 * kk, IDESC, kk > 0);
+                    if (SPLIT_C) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_lo + 2 * kk, IDESC, 1);
+                    }
                     umma_f16(d, dA_aug, dB_aug, IDESC, 1);
 #endif
                     umma_commit(BAR(BAR_ACC_FULL + acc));

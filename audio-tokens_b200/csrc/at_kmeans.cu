@@ -610,7 +610,7 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
         AT_CUDA_OK(cudaMalloc(&ix->c, sizeof(float) * (size_t)k * ix->d));
         AT_CUDA_OK(cudaMalloc(&ix->cn, sizeof(float) * (size_t)k));
         if (ix->d == 64) {
-            AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 20480));
+            AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 36864)   /* room for the hi | lo | aug form */);
             if (!ix->tc_max) {
                 AT_CUDA_OK(cudaMalloc(&ix->tc_max, 2 * sizeof(unsigned int)));
                 AT_CUDA_OK(cudaMemsetAsync(ix->tc_max, 0, 2 * sizeof(unsigned int), st));
