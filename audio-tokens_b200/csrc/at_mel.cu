@@ -304,8 +304,36 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
         {
             float zr[32], zi[32];
             const int64_t tj = t0 + (int64_t)warp * FR;
+            // fast path (one frame pair per job, hop = n_fft / 2, both frames interior and staged): the second frame's samples
+            // are the first frame's shifted by half a window, so the pair needs 1.5 n_fft staged samples, not 2, and each window
+            // value is fetched once for both frames
+            bool fast_pair = false;
+            if (G == 1 && hop == NF / 2 && cur.staged) {
+                const int64_t start = tj * hop - NF / 2;
+                fast_pair = tj + 1 < T && start >= 0 && start + hop + NF <= L;
+                if (fast_pair) {
+                    const float *sp = s_stage + (start - cur.lo) + lane;
+                    float wv[N2 / 2];
+#pragma unroll
+                    for (int n2 = 0; n2 < N2 / 2; n2++) {   // first half of the window: frame a only
+                        wv[n2] = s_win[lane + 32 * n2];
+                        zr[n2] = sp[32 * n2] * wv[n2];
+                    }
+#pragma unroll
+                    for (int n2 = N2 / 2; n2 < N2; n2++) {  // shared samples: a's second half, b's first half
+                        const float r = sp[32 * n2];
+                        const float w = s_win[lane + 32 * n2];
+                        zr[n2] = r * w;
+                        zi[n2 - N2 / 2] = r * wv[n2 - N2 / 2];
+                        wv[n2 - N2 / 2] = w;
+                    }
+#pragma unroll
+                    for (int n2 = N2; n2 < N2 + N2 / 2; n2++) zi[n2 - N2 / 2] = sp[32 * n2] * wv[n2 - N2];
+                }
+            }
 #pragma unroll
             for (int g = 0; g < G; g++) {
+                if (fast_pair) break;
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
                     const int64_t f = tj + 2 * g + half;
