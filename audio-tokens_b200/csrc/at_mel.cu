@@ -160,7 +160,8 @@ struct MelCfg {
     static constexpr int FR = 2 * G;         // real frames per job
     static constexpr int BF = MEL_WARPS * FR;  // frames per batch
     static constexpr int NB = NF / 2 + 1;    // bins
-    static constexpr int P_FLOATS = BF * NB;
+    static constexpr int PS = (NB + 3) & ~3; // power-tile row stride: rows start 16-byte aligned (vector reads in the mel phase)
+    static constexpr int P_FLOATS = BF * PS;
     // per group: [exchange | power tile | staged samples] (the dB tile aliases exchange + power-tile space);
     // then, shared by the groups: [twiddles | window | filter weights | filter parameters]
     static constexpr size_t OFF_P = XCH_BYTES;
@@ -193,7 +194,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
       const float *__restrict__ wt, int wt_count, float *__restrict__ out, float *__restrict__ out_l2,
       int32_t *__restrict__ bad_flags) {
     using C = MelCfg<LOG2NF>;
-    constexpr int NF = C::NF, N2 = C::N2, G = C::G, FR = C::FR, BF = C::BF, NB = C::NB;
+    constexpr int NF = C::NF, N2 = C::N2, G = C::G, FR = C::FR, BF = C::BF, PS = C::PS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int grp = threadIdx.x / MEL_THREADS;            // group of this thread
     const int tid = threadIdx.x % MEL_THREADS, lane = tid & 31, warp = tid >> 5;   // position inside the group
@@ -220,6 +221,8 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
         for (int i = threadIdx.x; i < n_mels; i += CTA_THREADS)
             s_par[3 * i] = fstart[i], s_par[3 * i + 1] = fcnt[i], s_par[3 * i + 2] = woff[i];
     }
+    // the padding columns of the power tile are read (against zero weights) by the vector loads of the mel phase
+    for (int i = tid; i < BF * (PS - C::NB); i += MEL_THREADS) ptile[(i / (PS - C::NB)) * PS + C::NB + i % (PS - C::NB)] = 0.f;
     const uint32_t bar = smem_u32(&s_bar_all[grp]);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -390,8 +393,8 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
             // pass 2: 32-point FFT over n1; position p holds k1 = brev5(p); Z[N2*k1 + k2]
             fft_dif<32>(zr, zi);
             // separate the two real frames and store |.|^2 (the 1/4 lives in the mel weights)
-            float *pa = ptile + (size_t)(warp * FR + 2 * g2) * NB;
-            float *pb = pa + NB;
+            float *pa = ptile + (size_t)(warp * FR + 2 * g2) * PS;
+            float *pb = pa + PS;
 #pragma unroll
             for (int k1 = 0; k1 < 16; k1++) {
                 const float Zr = zr[brev(k1, 5)], Zi = zi[brev(k1, 5)];
@@ -423,7 +426,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 const int fg = item % FG, m = (item / FG) * MPW + lane / FPW;
                 const int f = fg * FPW + lane % FPW;
                 if (m >= n_mels) continue;
-                const float *prow = ptile + (size_t)f * NB + (wt_in_smem ? s_par[3 * m] : fstart[m]);
+                const float *prow = ptile + (size_t)f * PS + (wt_in_smem ? s_par[3 * m] : fstart[m]);   // first bin: a multiple of 4
                 const int cnt4 = wt_in_smem ? s_par[3 * m + 1] : fcnt[m];
                 float acc = 0.f;
                 if (wt_in_smem) {
@@ -431,10 +434,11 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
 #pragma unroll 2
                     for (int i = 0; i < cnt4; i++) {
                         const float4 w = w4[i];  // broadcast: the lanes of a filter read the same segment
-                        acc = fmaf(w.x, prow[4 * i], acc);
-                        acc = fmaf(w.y, prow[4 * i + 1], acc);
-                        acc = fmaf(w.z, prow[4 * i + 2], acc);
-                        acc = fmaf(w.w, prow[4 * i + 3], acc);
+                        const float4 pw = *reinterpret_cast<const float4 *>(prow + 4 * i);   // conflict-free: rows are 516 floats apart
+                        acc = fmaf(w.x, pw.x, acc);
+                        acc = fmaf(w.y, pw.y, acc);
+                        acc = fmaf(w.z, pw.z, acc);
+                        acc = fmaf(w.w, pw.w, acc);
                     }
                 } else {
                     const float *w = wt + woff[m];
@@ -637,8 +641,8 @@ static int upload_constants(at_mel_plan *p) {
                 if (k < lo) lo = k;
                 hi = k;
             }
-        fstart[m] = hi < 0 ? 0 : lo;
-        fcnt[m] = hi < 0 ? 0 : hi - lo + 1;
+        fstart[m] = hi < 0 ? 0 : (lo & ~3);   // segments start on a multiple of 4 bins (16-byte aligned power-tile reads)
+        fcnt[m] = hi < 0 ? 0 : hi - fstart[m] + 1;
         woff[m] = (int)wt.size();
         for (int k = fstart[m]; k < fstart[m] + fcnt[m]; k++) wt.push_back(0.25f * p->h_fb[(size_t)k * nm + m]);
         while (wt.size() % 4) wt.push_back(0.f);
