@@ -8,10 +8,11 @@ from . import _lib
 from .index import FlatL2, IndexFlatL2
 from .kmeans import ClusteringParameters, Kmeans, LloydTrainer
 from .mel import MelPlan
+from .resample import ResamplePlan
 from .synth import sine_table, synth_clips
 
 __all__ = [
-    "_lib", "MelPlan", "FlatL2", "IndexFlatL2", "Kmeans", "ClusteringParameters", "LloydTrainer",
+    "_lib", "MelPlan", "ResamplePlan", "FlatL2", "IndexFlatL2", "Kmeans", "ClusteringParameters", "LloydTrainer",
     "synth_clips", "sine_table", "get_num_gpus", "row_l2norm", "pcm16_to_f32",
 ]
 

@@ -8,10 +8,10 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /
        -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -Xptxas -v ${AT_EXTRA_FLAGS:-})
 mkdir -p "$HERE/obj"
 pids=()
-for f in at_util at_kmeans at_mel at_assign_tc; do
+for f in at_util at_kmeans at_mel at_assign_tc at_resample; do
   ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" > "$HERE/obj/$f.log" 2>&1 || { cat "$HERE/obj/$f.log"; exit 1; } ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/obj/at_util.o "$HERE"/obj/at_kmeans.o "$HERE"/obj/at_mel.o "$HERE"/obj/at_assign_tc.o -lcudart
+"$NVCC" -shared -o "$OUT" "$HERE"/obj/at_util.o "$HERE"/obj/at_kmeans.o "$HERE"/obj/at_mel.o "$HERE"/obj/at_assign_tc.o "$HERE"/obj/at_resample.o -lcudart
 echo "built $OUT"

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 from tqdm import tqdm
 
-from at_b200 import MelPlan
+from at_b200 import MelPlan, ResamplePlan
 
 
 class SpectrogramGenerator:
@@ -29,6 +29,7 @@ class SpectrogramGenerator:
         self._plan_db = self.plan if not c.normalize else MelPlan(c.common_sr, c.n_fft, c.hop_length, c.n_mels, False)
         with open(config.split_file, "r") as f:
             self.data_split = json.load(f)
+        self._resamplers = {}     # source rate -> ResamplePlan
         self.writer_threads = 8
         self._last_batch = None   # frame-major device tensor of the last populate_specs call
 
@@ -115,8 +116,17 @@ class SpectrogramGenerator:
                 return None
             raise
         waveform = waveform.to(self.device)
+        if sr != self.config.common_sr and waveform.dtype == torch.float32:
+            # channel mean + sample-rate conversion in one launch (convert_to_mono + resample below, fused)
+            return self._resample_plan(sr).forward(waveform.contiguous())
         waveform = self.convert_to_mono(waveform)
         return self.resample(waveform, sr)
+
+    def _resample_plan(self, sr):
+        plan = self._resamplers.get(int(sr))
+        if plan is None:
+            plan = self._resamplers[int(sr)] = ResamplePlan(int(sr), int(self.config.common_sr))
+        return plan
 
     @staticmethod
     def convert_to_mono(waveform):
@@ -125,10 +135,13 @@ class SpectrogramGenerator:
         return waveform
 
     def resample(self, waveform, sr):
+        """(1, L) waveform at sr -> (1, L') at common_sr: torchaudio.transforms.Resample's arithmetic, one cached filter
+        bank per source rate (the reference builds a new Resample module per clip)."""
         if sr != self.config.common_sr:
-            from torchaudio.transforms import Resample
-
-            waveform = Resample(sr, self.config.common_sr).to(self.device)(waveform)
+            w = waveform.to(self.device, torch.float32).reshape(-1, waveform.shape[-1]).contiguous()
+            if w.shape[0] != 1:   # batched input: channel by channel, like Resample does
+                return torch.cat([self._resample_plan(sr).forward(w[i:i + 1]) for i in range(w.shape[0])], dim=0)
+            waveform = self._resample_plan(sr).forward(w)
         return waveform
 
     def generate_mel_spectrogram(self, audio):

@@ -177,6 +177,20 @@ int at_rand_perm_host(int32_t *perm, int64_t n, int64_t seed);
  * ---------------------------------------------------------------------------------------------- */
 int at_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, void *stream);
 
+/* Channel mean + sample-rate conversion of one decoded clip: SpectrogramGenerator.convert_to_mono + .resample
+ * (processors/spectrogram_generator.py:109-121) = torch.mean(dim=0) then torchaudio.transforms.Resample(orig, new) with
+ * its defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99).  A plan holds the filter bank of one
+ * (orig_freq, new_freq) pair (the reference rebuilds it for every clip).  wave: device fp32 [channels][n_in]
+ * (torchaudio.load's layout); out: device fp32 [at_resample_out_len(plan, n_in)] = ceil(new * n_in / orig) samples. */
+typedef struct at_resample_plan at_resample_plan;
+int at_resample_plan_create(int orig_freq, int new_freq, at_resample_plan **plan);
+int at_resample_plan_destroy(at_resample_plan *plan);
+int64_t at_resample_out_len(const at_resample_plan *plan, int64_t n_in);
+int at_resample_mono(at_resample_plan *plan, const float *wave, int channels, int64_t n_in, float *out, void *stream);
+/* B clips of the same length in one launch: wave [B][channels][n_in] -> out [B][out_len]. */
+int at_resample_mono_batch(at_resample_plan *plan, const float *wave, int channels, int64_t n_in, int B, float *out,
+                           void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Token histogram (SpecTokenizer.analyze_tokens' Counter) and int32 -> int64 widening
  * ---------------------------------------------------------------------------------------------- */

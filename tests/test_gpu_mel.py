@@ -118,3 +118,33 @@ def test_builtin_constants_close_to_torch_constants():
     a, _ = MelPlan(22050, 1024, 512, 64, True, torch_constants=True).forward(w)
     b, _ = MelPlan(22050, 1024, 512, 64, True, torch_constants=False).forward(w)
     assert (a - b).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("orig,new,channels", [(44100, 22050, 2), (48000, 22050, 1), (16000, 22050, 1), (32000, 22050, 2), (22050, 22050, 2)])
+def test_mono_resample_matches_torchaudio(orig, new, channels):
+    """Channel mean + Resample on the device against torch.mean + torchaudio.transforms.Resample on the CPU
+    (processors/spectrogram_generator.py:109-121).  Tolerance: 2e-6 absolute on samples in [-1, 1)."""
+    import torch
+    from at_b200 import ResamplePlan
+    from oracle import resample_ref
+
+    rng = np.random.default_rng(orig + channels)
+    L = orig + 123
+    wave = (rng.integers(-20000, 20000, size=(channels, L)).astype(np.float32) / 32768.0)
+    want = resample_ref.resample_torchaudio(wave, orig, new)
+    plan = ResamplePlan(orig, new)
+    got = plan.forward(torch.from_numpy(wave).cuda()).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-6
+
+
+def test_mono_resample_batch_equals_per_clip():
+    import torch
+    from at_b200 import ResamplePlan
+
+    g = torch.Generator("cuda").manual_seed(3)
+    wave = (torch.randint(-20000, 20000, (5, 2, 48000 + 17), device="cuda", generator=g).float() / 32768.0)
+    plan = ResamplePlan(48000, 22050)
+    batch = plan.forward_batch(wave)
+    for i in range(5):
+        assert torch.equal(batch[i:i + 1], plan.forward(wave[i]))
