@@ -200,8 +200,12 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        import datetime
+
         os.environ["NCCL_DEBUG"] = os.environ.get("AT_NCCL_DEBUG", "WARN")   # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a mismatched collective should fail in minutes, not after the default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=300))
     from at_b200 import _lib, synth_clips
     from at_b200.pipeline import HotPath
 
@@ -294,21 +298,43 @@ def run_b200(args):
 
     # ---- e2e: the same step from pinned HOST buffers, tokens + centroids read back to the host.  Two host forms of the
     # same clips: fp32 waveforms (what torchaudio.load hands the reference) and the decoder's native 16-bit PCM.
+    def agree(ok):
+        """True only if every rank says so: whether the e2e leg runs is a collective decision (a rank that skipped it
+        alone would leave the others waiting in the leg's all-reduces)."""
+        if world == 1:
+            return bool(ok)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
     def measure_e2e(pcm16):
         import psutil
 
         esz = 2 if pcm16 else 4
         need = B * L * esz
-        if psutil.virtual_memory().available / max(world, 1) < 2.5 * need:
-            raise MemoryError("not enough host memory for a pinned copy of the waveforms")
-        if pcm16:
-            wave_host = torch.empty((B, L), dtype=torch.int16, pin_memory=True)
-            for b0 in range(0, B, 2000):   # exact: the synthetic clips are 16-bit-PCM valued
-                wave_host[b0:b0 + 2000].copy_((wave[b0:b0 + 2000] * 32768.0).to(torch.int16))
-        else:
-            wave_host = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
-            wave_host.copy_(wave)
-        hb = hp.alloc_bufs(B, L, host=True, pcm16=pcm16)
+        barrier()   # every rank samples the host memory before any of them allocates
+        mem_ok = psutil.virtual_memory().available / max(world, 1) >= 2.5 * need
+        if not agree(mem_ok):
+            raise MemoryError("not enough host memory for a pinned copy of the waveforms on every rank")
+        wave_host, hb, err = None, None, None
+        try:
+            if pcm16:
+                wave_host = torch.empty((B, L), dtype=torch.int16, pin_memory=True)
+                for b0 in range(0, B, 2000):   # exact: the synthetic clips are 16-bit-PCM valued
+                    wave_host[b0:b0 + 2000].copy_((wave[b0:b0 + 2000] * 32768.0).to(torch.int16))
+            else:
+                wave_host = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
+                wave_host.copy_(wave)
+            hb = hp.alloc_bufs(B, L, host=True, pcm16=pcm16)
+        except Exception as ex:
+            err = ex
+        if not agree(err is None):
+            del wave_host, hb
+            try:
+                torch._C._host_emptyCache()
+            except Exception:
+                pass
+            raise RuntimeError(f"host / device buffers for the e2e leg could not be allocated on every rank ({err!r})")
         hb["spec"], hb["l2"], hb["tokens"] = bufs["spec"], bufs["l2"], bufs["tokens"]
         hp.run_host(wave_host, hb, row_offset=row_offset, n_total=n_total)  # warm-up
         barrier()
