@@ -3,57 +3,67 @@
 // Replaces the blocked sgemm + top-1 scan of faiss::exhaustive_L2sqr_blas (reached from
 // processors/spec_tokenizer.py:77 and, inside faiss.Kmeans.train, processors/cluster_creator.py:54-56).
 //
-// Three kernels:
+// Four kernels:
 //   k_tc_rows    rows (fp32) -> optional L2 normalisation -> the fp16 operand image of the rows, laid out exactly as the
 //                tensor core reads it (128-row tiles: 128x64 K-major SWIZZLE_128B + a 128x16 tile carrying |x|^2), plus
 //                per row the norm of the fp16 rounding error |delta| and |x|^2.  K-means builds it ONCE per training set
 //                and re-uses it for every Lloyd iteration (the rows do not change); a one-off search builds it per call.
-//   k_assign_tc  distances + scan (below).  Certifies almost every row from the accumulators.
-//   k_tc_tail    the uncertified rows (a compacted list, ~1-2 %): canonical fp32 re-evaluation of the candidate
-//                columns -- or of every centroid -- by one warp per row.
+//   k_assign_tc  distances + scan (below).  Certifies 93-97 % of the rows from the accumulators.
+//   k_tc_tail    uncertified rows with a candidate list (5-7 %): canonical fp32 re-evaluation of <= 4 columns, a
+//                16-lane group per row.
+//   k_tc_full    the remaining rows (0.1-0.5 %): exact scan of every centroid.
 //
-// Arithmetic.  For a tile of 128 rows x 128 centroids the tensor core evaluates, in ONE chain of 9 tcgen05.mma
+// Arithmetic.  For a tile of 128 rows x 128 centroids the tensor core evaluates, in ONE chain of 5 tcgen05.mma
 // (kind::f16, fp32 accumulate in TMEM),
-//     acc = BIAS + P * ( |x|^2 + |c|^2 - 2 <x~, c> )          P = S^2 a power of two chosen from max |c|
-//   = x~ * c_hi  +  x~ * c_lo                       (x~ = fp16(Sx x); c_hi + c_lo = fp16 hi/lo split of -2 (P/Sx) c, ~22 bits)
-//   + [xn pieces | 2^12 2^12 2^12] * [w w w | cn pieces]              (one extra K=16 step: both norms and the bias)
-// The only first-order error is the rounding of the ROW: acc_j - P d_j = 2 P <x - x~/Sx, c_j>, the same vector
+//     acc = BIAS + P * ( |x|^2 + |c|^2 - 2 <x~, c~> )         P = S^2 a power of two chosen from max |c|
+//   = x~ * c~                                        (x~ = fp16(Sx x), c~ = fp16(-2 (P/Sx) c): four K = 16 steps)
+//   + [xn pieces | 2^12 2^12 2^12] * [w w w | cn pieces]      (one extra K = 16 step: both norms and the bias)
+// Two first-order errors.  The rounding of the ROW, acc_j - P d_j = 2 P <x - x~/Sx, c_j>, is the same vector
 // delta = x - x~/Sx for every centroid, so for two candidates j, j' the error of the DIFFERENCE is bounded by
-// 2 |delta| |c_j - c_j'| <= 2 |delta| (sqrt d_j + sqrt d_j') -- small exactly when the two are close competitors.
+// 2 |delta| |c_j - c_j'| <= 2 |delta| (sqrt d_j + sqrt d_j') -- small exactly when the two are close competitors.  The
+// rounding of the CENTROIDS, <x~, e_j> with e_j = c~_j - (-2 (P/Sx) c_j), is bounded per column by |x~| e_max
+// (Cauchy-Schwarz), e_max = the largest |e_j|, measured when the operands are built (k_tc_prep).  (The scan, not the tensor
+// pipe, bounds the kernel; a second product with the fp16 residual of c would remove the second term at no scan cost, but
+// 9 MMAs per tile push the board into its power cap -- SPLIT_C below, off.)
 //
 // BIAS = 2^14 puts every accumulator into the binades [2^13, 2^17): the low 25 bits of its fp32 pattern are then a
 // monotone fixed-point image of the distance, and  key = pattern * 128 + column  (ONE IMAD, fma pipe) is an unsigned
 // integer whose order is the order of the distances with the column riding in the low 7 bits.  Measured pipe rates
 // (tools/ubench_pipes.cu): VIMNMX / VIMNMX3 / LOP3 one warp instruction per 2 cycles per scheduler (alu pipe), IMAD
-// one per 2 cycles on the fma pipe, concurrently.  The scan keeps TWO orthogonal groupings of a tile's 128 columns:
-//     A: 16 groups of 8 adjacent columns   -> exact running top-3 over the group minima
-//     B: 8 groups of 16 columns = position mod 8  -> exact running top-2 over the group minima
-// = 1.0 fma-pipe + 1.66 alu-pipe instructions per score.  Two columns never share both an A and a B group, so the
-// second smallest COLUMN of a row is exactly min(second A minimum, second B minimum): a runner-up can hide behind the
+// one per 2 cycles on the fma pipe, concurrently.  The scan keeps TWO orthogonal groupings of the columns:
+//     A: per tile, 8 groups of 16 adjacent columns -> exact running top-3 over the group minima (with their tiles)
+//     B: 16 classes = column mod 16, kept as running minima over the WHOLE sweep -> top-3 taken once per row
+// = 1.0 fma-pipe + 1.25 alu-pipe instructions per score (fold32).  An A group and a B class share exactly one column, so
+// the second smallest COLUMN of a row is exactly min(second A minimum, second B minimum): a runner-up can hide behind the
 // winner in one grouping, never in both.
 //
-// Certification (per row, accumulator units; tau from the measured |delta|):
+// Certification (per row, accumulator units):  tau = 1.0625 (tau_abs + 4 S|delta| sqrt(ub) + 2 |x~| e_max)
 //   second smallest column further than tau from the best -> the best column is the argmin: label final.
-// Otherwise the row goes to the tail list with the columns of the best and second-best A group minima; the tail kernel
-// re-evaluates those two groups (16 columns) with the library's canonical fp32 formula (at_index.cuh, the one the exact
-// SIMT kernel uses) -- every other column is at least the third A minimum, which must be further than tau; if it is
-// not, or the row is outside the fp16 / accumulator range, the tail kernel scans all centroids exactly.
+//   else, third A minimum and third B minimum both further than tau -> every column within reach lies where one of the
+//   two best A groups meets one of the two best B classes: <= 4 columns, re-evaluated by k_tc_tail with the library's
+//   canonical fp32 formula (at_index.cuh, the one the exact SIMT kernel uses);
+//   else (or the row is outside the fp16 / accumulator range) -> k_tc_full scans all centroids exactly.
 // Labels therefore equal the exact fp32 kernel's except ties below what the fp32 formula itself resolves.
-// Distances: canonical fp32 for tail rows, accumulator read-out (|error| <= 2 |delta| |c|) for certified rows;
-// at_index_search re-evaluates them exactly in a second pass when the caller asks for distances.
+// Distances: canonical fp32 for tail rows, accumulator read-out for certified rows; at_index_search re-evaluates them
+// exactly in a second pass when the caller asks for distances (k-means does not use them: its objective comes from the
+// exact cluster sums).
 //
-// Roofline note: 2*N*K*64 algorithmic flops are executed as 2.25x that many fp16 MMA flops.
+// Roofline note: 2*N*K*64 algorithmic flops are executed as 1.25x that many fp16 MMA flops; the alu pipe of the scan binds
+// (ncu: alu 67 % of peak, tensor 50 %, profiles/r01_ncu_full_summary.txt).
 //
 // k_assign_tc: persistent CTAs (one per SM), 16 warps; the unit of work is a SUPER TILE of 384 rows (three 128-row MMA
 // tiles) so every centroid operand tile fetched from L2 is used three times and every scheduler holds three scanning
 // warps (the scan is alu-pipe work: a third warp per scheduler hides its dependent-issue latency):
-//   warp 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into a 2-slot ring (or once, when all
+//   warp 0   bulk-copies (cp.async.bulk, TMA engine) centroid operand tiles into a 4-slot ring (or once, when all
 //            tiles fit: RESIDENT)
 //   warp 1   issues tcgen05.mma, commits to mbarriers
 //   warp 2   TMEM allocation / deallocation (all 512 columns = a ring of four 128-column accumulators)
 //   warp 3   bulk-copies the row operand image, one 60 KB super tile at a time, double-buffered
-//   warps 4-15  epilogue: warps 4-7 scan row tile 0, 8-11 row tile 1, 12-15 row tile 2 (tcgen05.ld -> keys -> top-3 / top-2)
-// Producer, MMA and row-image warps run their loops converged and issue from one elected lane (uniform operands).
+//   warps 4-15  epilogue: warps 4-7 scan row tile 0, 8-11 row tile 1, 12-15 row tile 2 (tcgen05.ld -> keys -> fold32);
+//            an accumulator's TMEM slot is released as soon as its last columns are in registers (half way through
+//            the tile's scan)
+// setmaxnreg: 56 registers for warps 0-3, 152 for the scanning warps.  Producer, MMA and row-image warps run their loops
+// converged and issue from one elected lane (uniform operands).
 #include "at_index.cuh"
 #include "at_ptx.cuh"
 
