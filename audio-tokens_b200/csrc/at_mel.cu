@@ -7,21 +7,25 @@
 //   normalize_spectrogram   -> (s - min s) / (max s - min s) over the clip
 //   check_for_nan_inf       -> bad flag
 //
-// Kernel shape (one persistent CTA of 16 warps per SM, clips dealt round-robin):
-//   * the sample window of the next batch of frames (31 hops + n_fft samples, <= 67.6 KB) is fetched into shared memory
-//     by one cp.async.bulk (TMA engine) while the current batch is in its mel / write-out phases, so overlapping
-//     frames are read from HBM once and no warp ever waits on DRAM (reflected edge frames read global memory);
+// Kernel shape (one persistent CTA per SM = two independent groups of 8 warps, clips dealt round-robin to the groups; a
+// group works through its clip in batches of 8 jobs and synchronises on its own named barrier, so one group's FFT phase
+// overlaps the other's mel / write-out phases):
+//   * the sample window of the next batch of frames (15 hops + n_fft samples at n_fft 1024, 34.8 KB) is fetched into
+//     shared memory by one cp.async.bulk (TMA engine) while the current batch is in its mel / write-out phases, so
+//     overlapping frames are read from HBM once and no warp ever waits on DRAM (reflected edge frames read global memory);
 //   * a warp owns one "job": 1024 complex points = G complex FFTs of n_fft points, each packing TWO real
 //     frames (frame a -> real part, frame b -> imaginary part), so no arithmetic is spent on the redundant
-//     half of a real-input transform;
+//     half of a real-input transform; at hop = n_fft / 2 the two frames share half their staged samples and every window
+//     value is fetched once for both;
 //   * n_fft = 32 * N2 is split Cooley-Tukey style: an N2-point FFT inside each lane's registers, a twiddle
 //     multiply, one 32x32 transpose through the warp's private shared-memory tile, a 32-point FFT in registers;
 //   * the two frames are separated with one shuffle per bin (Z[k], conj Z[n_fft-k]) and their power written
-//     to a shared power tile; 16 jobs fill the tile;
+//     to a shared power tile (rows 16-byte aligned); 8 jobs fill the tile;
 //   * the mel projection runs thread-per-(frame, filter) over the tile using the filterbank's sparsity
-//     (each triangular filter touches only its own bin range), then 10*log10, a transposed shared tile and
-//     coalesced 128-bit stores; min/max are tracked on the way out;
-//   * after the clip's last frame the CTA normalises the clip's tile in place (it is still in L2).
+//     (each triangular filter touches only its own bin range, weights and powers read 128 bits at a time), then
+//     10*log10 through MUFU.LG2, a transposed shared tile and coalesced 128-bit stores; min/max are tracked on the way out;
+//   * after the clip's last frame the group normalises the clip's tile in place (it is still in L2) and writes the
+//     L2-normalised copy the k-means stage consumes.
 #include "at_common.cuh"
 #include "at_index.cuh"
 #include "at_ptx.cuh"
