@@ -148,3 +148,18 @@ def test_mono_resample_batch_equals_per_clip():
     batch = plan.forward_batch(wave)
     for i in range(5):
         assert torch.equal(batch[i:i + 1], plan.forward(wave[i]))
+
+
+@pytest.mark.parametrize("name", ["frontend_44100_stereo", "frontend_48000_mono", "frontend_16000_mono"])
+def test_mono_resample_matches_reference_goldens(golden_dir, name):
+    """Device channel mean + resampler against the outputs of the reference's own convert_to_mono + resample methods
+    (tests/golden/frontend_*.npz)."""
+    import os
+    import torch
+    from at_b200 import ResamplePlan, pcm16_to_f32
+
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    wave = pcm16_to_f32(torch.from_numpy(g["pcm"]).cuda())
+    got = ResamplePlan(int(g["source_rate"]), int(g["common_sr"])).forward(wave).cpu().numpy()
+    assert got.shape == g["out"].shape
+    assert np.abs(got - g["out"]).max() <= 2e-6

@@ -23,3 +23,19 @@ def test_kernel_known_answers():
     assert abs(float(k[0, width]) - 0.495) < 1e-7
     k2, width2, o2, n2 = resample_ref.sinc_kernel(48000, 22050)
     assert (o2, n2) == (320, 147) and width2 == 14 and k2.shape == (147, 348)
+
+
+@pytest.mark.parametrize("name", ["frontend_44100_stereo", "frontend_48000_mono", "frontend_16000_mono"])
+def test_oracle_matches_the_reference_methods_goldens(golden_dir, name):
+    """tests/golden/frontend_*.npz were produced by the reference's own convert_to_mono + resample
+    (tests/golden/make_golden_frontend.py): both oracle flavours reproduce them."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    wave = g["pcm"].astype(np.float32) / np.float32(32768.0)
+    sr, common = int(g["source_rate"]), int(g["common_sr"])
+    a = resample_ref.resample_torchaudio(wave, sr, common)
+    b = resample_ref.resample_numpy(wave, sr, common)
+    assert a.shape == g["out"].shape
+    assert np.abs(a - g["out"]).max() <= 1e-6
+    assert np.abs(b - g["out"]).max() <= 2e-6
