@@ -52,6 +52,7 @@ PROTOTYPES = {
     "at_kmeans_set_incremental": (c_int, [c_ptr, c_int]),
     "at_pcm16_to_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "at_resample_plan_create": (c_int, [c_int, c_int, c_ptr]),
+    "at_resample_bank_host": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "at_resample_plan_destroy": (c_int, [c_ptr]),
     "at_resample_out_len": (c_i64, [c_ptr, c_i64]),
     "at_resample_mono": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_ptr, c_ptr]),

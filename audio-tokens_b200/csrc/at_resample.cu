@@ -14,6 +14,7 @@
 #include "at_common.cuh"
 
 #include <math.h>
+#include <string.h>
 #include <new>
 #include <numeric>
 #include <vector>
@@ -115,20 +116,17 @@ using namespace at;
 
 extern "C" {
 
-int at_resample_plan_create(int orig_freq, int new_freq, at_resample_plan **plan) {
-    AT_REQUIRE(plan && orig_freq > 0 && new_freq > 0, "at_resample_plan_create: bad arguments");
-    int dev;
-    AT_CUDA_OK(cudaGetDevice(&dev));
-    at_resample_plan *p = new (std::nothrow) at_resample_plan();
-    if (!p) return AT_ERR_NOMEM;
+// torchaudio's filter bank for (orig_freq, new_freq), evaluated as _get_sinc_resample_kernel does (host, double).
+static void build_bank(int orig_freq, int new_freq, std::vector<float> &kern, std::vector<int2> &range, int &o, int &n,
+                       int &width, int &taps) {
     const int g = std::gcd(orig_freq, new_freq);
-    const int o = orig_freq / g, n = new_freq / g;
+    o = orig_freq / g, n = new_freq / g;
     const double base = (double)(o < n ? o : n) * 0.99;
     const bool identity = orig_freq == new_freq;   // Resample.forward returns its input unchanged: channel mean only
-    const int width = identity ? 0 : (int)ceil(6.0 * (double)o / base);
-    const int taps = 2 * width + o;
-    std::vector<float> kern((size_t)n * taps);
-    std::vector<int2> range(n);
+    width = identity ? 0 : (int)ceil(6.0 * (double)o / base);
+    taps = 2 * width + o;
+    kern.assign((size_t)n * taps, 0.f);
+    range.assign(n, make_int2(0, 0));
     const double scale = base / (double)o;
     for (int ph = 0; ph < n; ph++) {
         const double phase = (double)((float)(-ph) / (float)n);   // int64 tensor / int -> float32 in torch
@@ -151,6 +149,33 @@ int at_resample_plan_create(int orig_freq, int new_freq, at_resample_plan **plan
         }
         range[ph] = last < 0 ? make_int2(0, 0) : make_int2(first, last + 1);
     }
+}
+
+// HOST function, HOST pointers (no device needed): the filter bank a plan for (orig_freq, new_freq) uses.  bank may be
+// NULL to query the sizes: [*phases][*taps] floats.
+int at_resample_bank_host(int orig_freq, int new_freq, float *bank, int *phases, int *taps_out, int *width_out) {
+    AT_REQUIRE(orig_freq > 0 && new_freq > 0, "at_resample_bank_host: bad arguments");
+    std::vector<float> kern;
+    std::vector<int2> range;
+    int o, n, width, taps;
+    build_bank(orig_freq, new_freq, kern, range, o, n, width, taps);
+    if (phases) *phases = n;
+    if (taps_out) *taps_out = taps;
+    if (width_out) *width_out = width;
+    if (bank) memcpy(bank, kern.data(), sizeof(float) * kern.size());
+    return AT_OK;
+}
+
+int at_resample_plan_create(int orig_freq, int new_freq, at_resample_plan **plan) {
+    AT_REQUIRE(plan && orig_freq > 0 && new_freq > 0, "at_resample_plan_create: bad arguments");
+    int dev;
+    AT_CUDA_OK(cudaGetDevice(&dev));
+    at_resample_plan *p = new (std::nothrow) at_resample_plan();
+    if (!p) return AT_ERR_NOMEM;
+    std::vector<float> kern;
+    std::vector<int2> range;
+    int o, n, width, taps;
+    build_bank(orig_freq, new_freq, kern, range, o, n, width, taps);
     p->orig = o, p->neu = n, p->width = width, p->taps = taps;
     std::vector<float> ck;
     std::vector<int> coff(n);

@@ -184,6 +184,9 @@ int at_pcm16_to_f32(const int16_t *pcm, int64_t n, float *out, void *stream);
  * (torchaudio.load's layout); out: device fp32 [at_resample_out_len(plan, n_in)] = ceil(new * n_in / orig) samples. */
 typedef struct at_resample_plan at_resample_plan;
 int at_resample_plan_create(int orig_freq, int new_freq, at_resample_plan **plan);
+/* HOST function, HOST pointers, no device needed: the filter bank a plan for this rate pair uses, [*phases][*taps]
+ * floats (torchaudio's _get_sinc_resample_kernel); bank may be NULL to query the sizes. */
+int at_resample_bank_host(int orig_freq, int new_freq, float *bank, int *phases, int *taps, int *width);
 int at_resample_plan_destroy(at_resample_plan *plan);
 int64_t at_resample_out_len(const at_resample_plan *plan, int64_t n_in);
 int at_resample_mono(at_resample_plan *plan, const float *wave, int channels, int64_t n_in, float *out, void *stream);

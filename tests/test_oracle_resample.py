@@ -39,3 +39,26 @@ def test_oracle_matches_the_reference_methods_goldens(golden_dir, name):
     assert a.shape == g["out"].shape
     assert np.abs(a - g["out"]).max() <= 1e-6
     assert np.abs(b - g["out"]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("orig,new", [(44100, 22050), (48000, 22050), (16000, 22050), (32000, 22050), (8000, 22050)])
+def test_library_filter_bank_equals_torchaudio(orig, new):
+    """The filter bank the CUDA library builds on the host (at_resample_bank_host, no device needed) against
+    torchaudio's own _get_sinc_resample_kernel: same shape, values within one float32 ulp of the centre tap."""
+    import ctypes
+    import math
+
+    import torchaudio.functional.functional as AF
+    from at_b200 import _lib
+
+    lib = _lib.load()
+    ph, taps, width = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.at_resample_bank_host(orig, new, None, ctypes.byref(ph), ctypes.byref(taps), ctypes.byref(width)))
+    bank = np.empty((ph.value, taps.value), dtype=np.float32)
+    _lib.check(lib.at_resample_bank_host(orig, new, bank.ctypes.data_as(ctypes.c_void_p), None, None, None))
+    kern, w = AF._get_sinc_resample_kernel(orig, new, math.gcd(orig, new))
+    kern = kern.numpy()[:, 0, :]
+    assert w == width.value and kern.shape == bank.shape
+    assert np.abs(bank - kern).max() <= 6e-8
+    ours, _, _, _ = resample_ref.sinc_kernel(orig, new)
+    assert np.abs(ours - kern).max() <= 6e-8
