@@ -9,6 +9,7 @@ from tqdm import tqdm
 
 import at_b200
 import at_b200.faiss_compat as faiss
+from at_b200.npyio import load_spec_batch
 
 
 def _set_seed(seed=42):
@@ -66,8 +67,8 @@ class ClusterCreator:
     def _batch_generator(self, batch_size):
         files = self._files()
         for i in tqdm(range(0, len(files), batch_size)):
-            batch_data = [np.load(f).T for f in files[i:i + batch_size]]
-            yield np.concatenate(batch_data, axis=0).astype(np.float32)
+            # np.concatenate([np.load(f).T ...]).astype(float32) of the reference, with the reads on a thread pool
+            yield load_spec_batch(files[i:i + batch_size])[0]
 
     def visualize_centroids(self, centroids):
         """PCA scatter plot (cosmetic): produced only when matplotlib and scikit-learn are importable."""

@@ -11,6 +11,7 @@ from tqdm import tqdm
 import at_b200
 import at_b200.faiss_compat as faiss
 from at_b200 import _lib
+from at_b200.npyio import load_spec_batch
 
 
 class SpecTokenizer:
@@ -49,18 +50,17 @@ class SpecTokenizer:
         return all_tokens
 
     def process_batch(self, batch_files, tokenized_dir: Path):
-        batch_specs = [np.load(f).T for f in batch_files]
-        if not batch_specs:
+        if not batch_files:
             return []
-        batch_data = np.concatenate(batch_specs, axis=0).astype(np.float32)
+        batch_data, lengths = load_spec_batch(batch_files)   # the reference's per-file np.load(f).T + concatenate
         if batch_data.size == 0:
             return []
         # normalize_vectors + index.search(x, 1) in one kernel; int64 labels like faiss
         _, tokens = self.index.search(batch_data, 1, l2norm_rows=True)
         tokens = np.squeeze(tokens, 1)
         start = 0
-        for spec_file, spec in zip(batch_files, batch_specs):
-            end = start + len(spec)
+        for spec_file, n_frames in zip(batch_files, lengths):
+            end = start + n_frames
             np.save(tokenized_dir / f"{spec_file.stem}.npy", tokens[start:end])
             start = end
         return tokens.tolist()
