@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libat_b200.so")
+# AT_B200_LIB: an experiment build of the same library (tools/ only; the product path is the in-tree file)
+LIB_PATH = os.environ.get("AT_B200_LIB") or os.path.join(_HERE, "libat_b200.so")
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -26,10 +27,12 @@ PROTOTYPES = {
     "at_profile_summary": (c_int, [c_int, c_ptr, c_ptr]),
     "at_mel_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_ptr]),
     "at_mel_plan_set_constants_host": (c_int, [c_ptr, c_ptr, c_ptr]),
+    "at_mel_plan_set_output": (c_int, [c_ptr, c_int]),
     "at_mel_plan_destroy": (c_int, [c_ptr]),
     "at_mel_num_frames": (c_i64, [c_ptr, c_i64]),
     "at_mel_forward": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "at_mel_forward_host": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "at_amplitude_to_db": (c_int, [c_ptr, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr]),
     "at_row_l2norm": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     "at_index_create": (c_int, [c_int, c_ptr]),
     "at_index_destroy": (c_int, [c_ptr]),
@@ -78,6 +81,8 @@ def load():
             )
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
+            if os.environ.get("AT_B200_LIB") and not hasattr(lib, name):
+                continue  # an older experiment build (tools/ only)
             fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

@@ -214,9 +214,20 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
+// blocking wait of the pipeline roles (build-time AT_TC_WAIT_NS: 0 = the default polling form)
+#ifndef AT_TC_WAIT_NS
+#define AT_TC_WAIT_NS 0
+#endif
+__device__ __forceinline__ void mbar_waitx(uint32_t bar, uint32_t parity) {
+    if (AT_TC_WAIT_NS > 0) mbar_wait_hint(bar, parity, (uint32_t)AT_TC_WAIT_NS);
+    else mbar_wait(bar, parity);
+}
+
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }  // VIMNMX3.U32
-// accumulator value of a key (exact): the 7 dropped pattern bits are the same for every binade in range
-__device__ __forceinline__ float acc_of(uint32_t key) { return __uint_as_float(BIAS_HI | (key >> 7)); }
+// accumulator value of an A key (pattern * 8 + group) / a B key (pattern * 16 + class), exact: the pattern bits pushed out
+// by the multiplication are the same for every binade in range (BIAS_HI); an all-ones key (nothing seen) maps above the range
+__device__ __forceinline__ float acc_a(uint32_t key) { return __uint_as_float(BIAS_HI | (key >> 3)); }
+__device__ __forceinline__ float acc_b(uint32_t key) { return __uint_as_float(BIAS_HI | (key >> 4)); }
 
 // value split into three fp16 pieces (p1 + p2 + p3 ~ v to ~33 bits)
 __device__ __forceinline__ void split3(float v, __half &p1, __half &p2, __half &p3) {
@@ -415,27 +426,28 @@ __device__ __forceinline__ uint32_t umin16(const uint32_t *k) {
     return min(umin3(a, b, c), umin3(d, e, k[15]));
 }
 
-// 32 accumulator columns (two 16-column loads, column base cb a multiple of 32) -> keys.  Two orthogonal groupings:
-//   A: the tile's 8 groups of 16 adjacent columns -> exact running top-3 over the group minima of the tile;
-//   B: 16 classes = column mod 16, running over ALL tiles of the row's sweep -> bp[h], the minimum of class h.
+// 32 accumulator columns (two 16-column loads = two A groups, ga the index of the first one inside its tile).  The raw
+// fp32 patterns are scanned as unsigned integers (every accumulator lies in [2^13, 2^17), where the pattern order is the
+// value order); NO per-score key is built.  Two orthogonal groupings:
+//   A: the tile's 8 groups of 16 adjacent columns -> the group minimum gets its group index appended
+//      (pattern * 8 + group: one IMAD per 16 scores; the three pattern bits pushed out are the same for the whole range)
+//      -> exact running top-3 over the group minima of the tile;
+//   B: 16 classes = column mod 16, running over ALL tiles of the row's sweep -> bp[h], the minimum pattern of class h
+//      (the class is the register index; it is appended once per row, after the sweep).
 // A group (tile, columns 16a .. 16a+15) and a B class share exactly one column, so two columns never share both: the
 // second smallest COLUMN of a row is exactly min(second smallest A-group minimum, second smallest B-class minimum) -- a
-// runner-up can hide behind the winner in one grouping, never in both.
-// alu: 16 (A minima) + 8 (A top-3) + 16 (B) per 32 columns = 1.25 per score; fma pipe: 32 IMAD.
-__device__ __forceinline__ void fold32(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const int cb, const uint32_t mul,
+// runner-up can hide behind the winner in one grouping, never in both -- and the arg-min COLUMN is where the best A
+// group meets the best B class.
+// alu pipe: 16 (A minima) + 8 (A top-3) + 16 (B) per 32 columns = 1.25 per score; fma pipe: 2 IMAD per 32 columns.
+__device__ __forceinline__ void fold32(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const uint32_t ga, const uint32_t mul8,
                                        uint32_t &t1, uint32_t &t2, uint32_t &t3, uint32_t (&bp)[16]) {
-    uint32_t ka[16], kb[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) ka[i] = ra[i] * mul + (uint32_t)(cb + i);        // IMAD R, R, Rmul, imm
-#pragma unroll
-    for (int i = 0; i < 16; i++) kb[i] = rb[i] * mul + (uint32_t)(cb + 16 + i);
-    const uint32_t ga0 = umin16(ka), ga1 = umin16(kb);
+    const uint32_t ga0 = umin16(ra) * mul8 + ga, ga1 = umin16(rb) * mul8 + (ga + 1u);
     const uint32_t lo = min(ga0, ga1), hi = max(ga0, ga1);
     t3 = umin3(t3, max(t2, lo), max(t1, hi));
     t2 = umin3(t2, hi, max(t1, lo));
     t1 = min(t1, lo);
 #pragma unroll
-    for (int h = 0; h < 16; h++) bp[h] = umin3(bp[h], ka[h], kb[h]);
+    for (int h = 0; h < 16; h++) bp[h] = umin3(bp[h], ra[h], rb[h]);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -494,7 +506,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 uint32_t st = 0, ph = 0;
                 for (int64_t i = 0; i < my_tiles; i++) {
                     for (int jt = 0; jt < ktiles; jt++) {
-                        mbar_wait(BAR(BAR_B_EMPTY + st), ph ^ 1);
+                        mbar_waitx(BAR(BAR_B_EMPTY + st), ph ^ 1);
                         bulk_g2s_elect(base + OFF_B + st * B_TILE_BYTES, op + (size_t)jt * B_TILE_BYTES, B_TILE_BYTES,
                                        BAR(BAR_B_FULL + st));
                         if (++st == B_SLOTS) st = 0, ph ^= 1;
@@ -507,7 +519,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
         // ================================================================== row-image producer
         for (int64_t i = 0; i < my_tiles; i++) {
             const uint32_t ab = (uint32_t)(i & 1);
-            mbar_wait(BAR(BAR_A_EMPTY + ab), (uint32_t)(((i >> 1) & 1) ^ 1));
+            mbar_waitx(BAR(BAR_A_EMPTY + ab), (uint32_t)(((i >> 1) & 1) ^ 1));
             bulk_g2s_elect(base + OFF_A + ab * A_BUF_BYTES, img + (size_t)(worker + i * workers) * A_BUF_BYTES, A_BUF_BYTES,
                            BAR(BAR_A_FULL + ab));
         }
@@ -519,11 +531,11 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
         uint32_t st = 0, bph = 0, u = 0;
         for (int64_t i = 0; i < my_tiles; i++) {
             const uint32_t ab = (uint32_t)(i & 1);
-            mbar_wait(BAR(BAR_A_FULL + ab), (uint32_t)((i >> 1) & 1));
+            mbar_waitx(BAR(BAR_A_FULL + ab), (uint32_t)((i >> 1) & 1));
             const uint32_t a0 = base + OFF_A + ab * A_BUF_BYTES;
             for (int jt = 0; jt < ktiles; jt++, u++) {
                 const uint32_t slot = RESIDENT ? (uint32_t)jt : st;
-                if (!RESIDENT || i == 0) mbar_wait(BAR(BAR_B_FULL + slot), RESIDENT ? 0u : bph);
+                if (!RESIDENT || i == 0) mbar_waitx(BAR(BAR_B_FULL + slot), RESIDENT ? 0u : bph);
                 const uint32_t b_hi = base + OFF_B + slot * B_TILE_BYTES;
                 const uint64_t dB_hi = desc_sw128(b_hi), dB_lo = desc_sw128(b_hi + TN * 128), dB_aug = desc_nosw(b_hi + B_MAIN_BYTES);
 #pragma unroll
@@ -531,7 +543,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                     const uint32_t a_hi = a0 + rt * A_TILE_BYTES;
                     const uint64_t dA = desc_sw128(a_hi), dA_aug = desc_nosw(a_hi + A_MAIN_BYTES);
                     const uint32_t v = u * RT + rt, acc = v % ACC_SLOTS, aph = (v / ACC_SLOTS) & 1;
-                    mbar_wait(BAR(BAR_ACC_EMPTY + acc), aph ^ 1);
+                    mbar_waitx(BAR(BAR_ACC_EMPTY + acc), aph ^ 1);
                     tc_fence_after();
                     const uint32_t d = tmem + acc * TN;
                     // descriptor start addresses are in 16-byte units: a K step of 16 fp16 = 32 bytes = +2
@@ -578,7 +590,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             // behind a fold of two, and the first two loads of the NEXT tile are issued before the last fold of this one.
             if (!primed) {   // very first tile of this warp
                 const uint32_t v0 = u * RT + rt;
-                mbar_wait(BAR(BAR_ACC_FULL + v0 % ACC_SLOTS), (v0 / ACC_SLOTS) & 1);
+                mbar_waitx(BAR(BAR_ACC_FULL + v0 % ACC_SLOTS), (v0 / ACC_SLOTS) & 1);
                 tc_fence_after();
                 const uint32_t ta = tmem + lane_addr + (v0 % ACC_SLOTS) * TN;
                 tmem_ld16(ta, c0);
@@ -592,11 +604,11 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 tmem_ld_wait();                       // c0, c1 (issued during the previous tile)
                 tmem_ld16(ta + 32, c2);
                 tmem_ld16(ta + 48, c3);
-                fold32(c0, c1, 0, key_mul, t1, t2, t3, bp);
+                fold32(c0, c1, 0u, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tmem_ld16(ta + 64, c0);
                 tmem_ld16(ta + 80, c1);
-                fold32(c2, c3, 32, key_mul, t1, t2, t3, bp);
+                fold32(c2, c3, 2u, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tmem_ld16(ta + 96, c2);
                 tmem_ld16(ta + 112, c3);
@@ -608,7 +620,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 tc_fence_before();
                 __syncwarp();
                 mbar_arrive_elect(BAR(BAR_ACC_EMPTY + acc));
-                fold32(c0, c1, 64, key_mul, t1, t2, t3, bp);
+                fold32(c0, c1, 4u, key_mul, t1, t2, t3, bp);
                 // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
                 const bool more = (jt + 1 < ktiles) || (i + 1 < my_tiles);
                 const uint32_t vn = (u + 1) * RT + rt;
@@ -621,9 +633,9 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                     tmem_ld16(tn + 16, c1);
                     started = true;
                 }
-                fold32(c2, c3, 96, key_mul, t1, t2, t3, bp);
+                fold32(c2, c3, 6u, key_mul, t1, t2, t3, bp);
                 if (more && !started) {
-                    mbar_wait(nbar, nph);
+                    mbar_waitx(nbar, nph);
                     tc_fence_after();
                     tmem_ld16(tn, c0);
                     tmem_ld16(tn + 16, c1);
@@ -640,7 +652,10 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 j1 = p ? jt : j1;
                 g3 = n3;
             }
-            // B grouping: top-3 of the 16 class minima (h1 == g1: the row minimum is the same in both groupings)
+            // B grouping: the class index is appended now (pattern * 16 + class), then the top-3 of the 16 class minima
+            // (the row minimum is the same value in both groupings: acc_b(h1) == acc_a(g1))
+#pragma unroll
+            for (int h = 0; h < 16; h++) bp[h] = bp[h] * (2u * key_mul) + (uint32_t)h;
             uint32_t h1 = min(bp[0], bp[1]), h2 = max(bp[0], bp[1]), h3 = 0xFFFFFFFFu;
 #pragma unroll
             for (int pr = 1; pr < 8; pr++) {
@@ -657,8 +672,8 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             const float xnP = R * R * xnS;                   // S^2 |x|^2
             const bool fallback = !(xnP <= X_LIMIT * X_LIMIT);   // outside the accumulator range, Inf, NaN
             // ---- certification (accumulator units)
-            const float A1 = acc_of(g1), A2 = acc_of(min(g2, h2)), A3 = acc_of(min(g3, h3));
-            const int ca = j1 * TN + (int)(g1 & 127u);
+            const float A1 = acc_a(g1), A2 = fminf(acc_a(g2), acc_b(h2)), A3 = fminf(acc_a(g3), acc_b(h3));
+            const int ca = j1 * TN + (int)((g1 & 7u) << 4) + (int)(h1 & 15u);   // best A group x best B class
             const float v1 = fmaxf(A1 - BIAS, 0.f);
             const float cterm = sqrtf(xnS) * 1.001f * emax;                          // >= |<x~, e_j>| for every column j
             const float ub = v1 + 2.0f * e * cmax + tau_abs + cterm;                 // >= S^2 d_best
@@ -692,7 +707,7 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 sc = __shfl_sync(0xffffffffu, sc, 0), sf = __shfl_sync(0xffffffffu, sf, 0);
                 const unsigned lt = (1u << lane) - 1u;
                 if (want_cand) {
-                    const int a1 = (int)(g1 & 112u), b1 = (int)(g1 & 15u), a2 = (int)(g2 & 112u), b2 = (int)(h2 & 15u);
+                    const int a1 = (int)((g1 & 7u) << 4), b1 = (int)(h1 & 15u), a2 = (int)((g2 & 7u) << 4), b2 = (int)(h2 & 15u);
                     int c1 = j1 * TN + a1 + b2, c2 = j2 * TN + a2 + b1, c3 = j2 * TN + a2 + b2;
                     c1 = c1 < k ? c1 : ca, c2 = c2 < k ? c2 : ca, c3 = c3 < k ? c3 : ca;
                     tail[sc + __popc(mc & lt)] = make_uint4((uint32_t)row, (uint32_t)ca | ((uint32_t)c1 << 16),
@@ -957,11 +972,12 @@ int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const fl
 // rows: a prepared image of exactly these rows (k-means), or nullptr to build one in the index's own workspace.
 int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32, int64_t *labels64,
                      float *dist, int exact_dist, at_tc_rows *rows, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {};   // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
         AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        configured = true;
+        configured[dev] = true;
     }
     if (!rows) {
         rows = &ix->rows;
@@ -993,11 +1009,11 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     AT_CUDA_OK(cudaMemsetAsync(rows->tail_count, 0, 2 * sizeof(unsigned int), st));
     if (resident)
         k_assign_tc<true><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
-                                                            ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
+                                                            ix->tc_scale, 8u, l32, labels64, kdist, rows->tail,
                                                             rows->tail_count, (unsigned int)rows->cap);
     else
         k_assign_tc<false><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
-                                                             ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
+                                                             ix->tc_scale, 8u, l32, labels64, kdist, rows->tail,
                                                              rows->tail_count, (unsigned int)rows->cap);
     AT_LAUNCH_OK();
     k_tc_tail<<<sms * 8, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, rows->tail, rows->tail_count, l32, labels64, kdist,

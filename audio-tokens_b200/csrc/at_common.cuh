@@ -40,7 +40,9 @@ void set_error(const char *fmt, ...);
         }                                                                                      \
     } while (0)
 
-int sm_count();  // cached; 0 when no device
+constexpr int MAX_DEVICES = 64;
+int current_device();  // cudaGetDevice clamped to [0, MAX_DEVICES)
+int sm_count();  // of the current device (cached per device); 0 when no device
 extern int64_t g_launches;
 
 // Event-pair profiling (at_profile_*): ProfScope brackets the launches issued while it is alive.

@@ -36,6 +36,7 @@
 
 struct at_mel_plan {
     int sample_rate = 0, n_fft = 0, hop = 0, n_mels = 0, normalize = 0;
+    int power_out = 0;        // 1: write the mel POWER (MelSpectrogram alone), 0: dB (MelSpectrogram + AmplitudeToDB)
     int log2nf = 0;
     // device constants
     float *win = nullptr;     // n_fft
@@ -193,7 +194,7 @@ template <int LOG2NF>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets,
       const int64_t *__restrict__ frame_offsets, int64_t uniform_samples, int B, int hop, int n_mels,
-      int normalize, const float *__restrict__ g_win, const float2 *__restrict__ g_tw,
+      int normalize, int power_out, const float *__restrict__ g_win, const float2 *__restrict__ g_tw,
       const int *__restrict__ fstart, const int *__restrict__ fcnt, const int *__restrict__ woff,
       const float *__restrict__ wt, int wt_count, float *__restrict__ out, float *__restrict__ out_l2,
       int32_t *__restrict__ bad_flags) {
@@ -450,7 +451,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 }
                 // 10 log10(x) = (10 log10 2) log2(x): MUFU.LG2 (relative error 2^-22) instead of the ~25-instruction log10f;
                 // the result differs from torch's by < 3e-5 dB over the whole range (gate: 1e-4 of the clip's range)
-                dtile[f * dstride + m] = 3.01029995663981195f * __log2f(fmaxf(acc, 1e-10f));
+                dtile[f * dstride + m] = power_out ? acc : 3.01029995663981195f * __log2f(fmaxf(acc, 1e-10f));
             }
         }
         group_sync(grp);
@@ -683,16 +684,17 @@ template <int LOG2NF>
 static int launch_mel(at_mel_plan *p, const float *wave, const int64_t *so, const int64_t *fo, int64_t us, int B,
                       float *out, float *out_l2, int32_t *bad, cudaStream_t st) {
     using C = MelCfg<LOG2NF>;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {};   // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
         AT_CUDA_OK(cudaFuncSetAttribute(k_mel<LOG2NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
+        configured[dev] = true;
     }
     int grid = sm_count();
     if (grid > (B + MEL_GROUPS - 1) / MEL_GROUPS) grid = (B + MEL_GROUPS - 1) / MEL_GROUPS;
     if (grid < 1) grid = 1;
     ProfScope prof(PROF_MEL, st);
-    k_mel<LOG2NF><<<grid, CTA_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->win,
+    k_mel<LOG2NF><<<grid, CTA_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->power_out, p->win,
                                                      p->tw, p->fstart, p->fcnt, p->woff, p->wt, p->wt_count, out, out_l2,
                                                      bad);
     AT_LAUNCH_OK();
@@ -742,6 +744,13 @@ int at_mel_plan_set_constants_host(at_mel_plan *p, const float *window, const fl
     if (fb) p->h_fb.assign(fb, fb + (size_t)(p->n_fft / 2 + 1) * p->n_mels);
     AT_CUDA_OK(cudaDeviceSynchronize());
     return upload_constants(p);
+}
+
+int at_mel_plan_set_output(at_mel_plan *p, int kind) {
+    AT_REQUIRE(p && (kind == AT_MEL_OUT_DB || kind == AT_MEL_OUT_POWER), "at_mel_plan_set_output: bad arguments");
+    AT_REQUIRE(!(kind == AT_MEL_OUT_POWER && p->normalize), "at_mel_plan_set_output: the power output is not min-max normalised");
+    p->power_out = kind == AT_MEL_OUT_POWER;
+    return AT_OK;
 }
 
 int at_mel_plan_destroy(at_mel_plan *p) {

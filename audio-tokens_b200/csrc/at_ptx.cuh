@@ -26,6 +26,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// same, with an explicit suspend-time hint (ns): a waiting warp is parked by the hardware until the phase completes (or
+// the hint expires) instead of re-issuing the probe every few cycles -- the polling loop of the default form took 9 % of
+// the issue slots of the tensor search (round-1 ncu, profiles/r01_hot_lines_k_assign_tc.txt)
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITH_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONEH_%=;\n\t"
+        "bra WAITH_%=;\n\t"
+        "DONEH_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

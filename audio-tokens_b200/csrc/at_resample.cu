@@ -230,13 +230,14 @@ int at_resample_mono_batch(at_resample_plan *p, const float *wave, int channels,
     // input span of one tile: ((RS_TILE - 1) / n + 1) * o + (kmax - kmin) samples
     const int64_t span = ((int64_t)(RS_TILE - 1) / p->neu + 1) * p->orig + (p->kmax - p->kmin);
     if (span <= RS_SPAN_MAX && p->ctotal <= RS_CK_MAX) {
-        static bool configured = false;
+        static bool configured[MAX_DEVICES] = {};   // the attribute is per device
+        const int dev = current_device();
         const int span_cap = (int)((span + 3) & ~(int64_t)3);
         const size_t smem = sizeof(float) * (size_t)(span_cap + p->ctotal);
-        if (!configured) {
+        if (!configured[dev]) {
             AT_CUDA_OK(cudaFuncSetAttribute(k_resample_mono_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(sizeof(float) * (RS_SPAN_MAX + RS_CK_MAX))));
-            configured = true;
+            configured[dev] = true;
         }
         int64_t tiles = ceil_div(out_len, RS_TILE);
         const int64_t capt = ceil_div((int64_t)(sm_count() > 0 ? sm_count() : 1) * 8, B);

@@ -34,18 +34,29 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-int sm_count() {
-    static int cached = -1;
-    if (cached < 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-        cached = n;
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
     }
-    return cached;
+    return dev < 0 ? 0 : (dev >= MAX_DEVICES ? MAX_DEVICES - 1 : dev);
+}
+
+int sm_count() {
+    static int cached[MAX_DEVICES] = {};   // 0 = not asked yet
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (dev >= 0 && dev < MAX_DEVICES && cached[dev] > 0) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (dev >= 0 && dev < MAX_DEVICES) cached[dev] = n;
+    return n;
 }
 
 __global__ void k_absmax(const float *__restrict__ x, int64_t n, float *__restrict__ out) {
@@ -161,9 +172,38 @@ __global__ void __launch_bounds__(256) k_pcm16_to_f32(const int16_t *__restrict_
     for (int64_t i = (n8 << 3) + tid; i < n; i += nth) out[i] = (float)pcm[i] * (1.0f / 32768.0f);
 }
 
+// AmplitudeToDB.forward (torchaudio functional.amplitude_to_DB): multiplier * log10(max(x, amin)) - multiplier * db_multiplier,
+// through MUFU.LG2 like the fused mel kernel; optional top_db clamp against a device-resident maximum.
+__global__ void __launch_bounds__(256) k_amp_to_db(const float *__restrict__ x, int64_t n, float mul_log2, float amin,
+                                                   float sub, float *__restrict__ out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t n4 = vec ? n >> 2 : 0;
+    for (int64_t i = tid; i < n4; i += nth) {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        v.x = mul_log2 * __log2f(fmaxf(v.x, amin)) - sub, v.y = mul_log2 * __log2f(fmaxf(v.y, amin)) - sub;
+        v.z = mul_log2 * __log2f(fmaxf(v.z, amin)) - sub, v.w = mul_log2 * __log2f(fmaxf(v.w, amin)) - sub;
+        reinterpret_cast<float4 *>(out)[i] = v;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += nth) out[i] = mul_log2 * __log2f(fmaxf(x[i], amin)) - sub;
+}
+
 extern "C" {
 
 int at_version(void) { return AT_B200_VERSION; }
+
+int at_amplitude_to_db(const float *x, int64_t n, float multiplier, float amin, float db_multiplier, float *out, void *stream) {
+    AT_REQUIRE(x && out && n >= 0 && amin > 0.f, "at_amplitude_to_db: bad arguments");
+    if (n == 0) return AT_OK;
+    int64_t want = ceil_div(n, 256 * 8);
+    int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+    if (blocks < 1) blocks = 1;
+    // multiplier * log10(v) = multiplier * log10(2) * log2(v)
+    k_amp_to_db<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, multiplier * 0.301029995663981195f, amin,
+                                                         multiplier * db_multiplier, out);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
 
 const char *at_last_error(void) { return g_err; }
 

@@ -2,16 +2,17 @@
 # Builds libat_b200.so for sm_100a, in-tree (audio-tokens_b200/at_b200/libat_b200.so).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="$HERE/../at_b200/libat_b200.so"
+OUT="${AT_OUT:-$HERE/../at_b200/libat_b200.so}"   # AT_OUT / AT_OBJ / AT_EXTRA_FLAGS: experiment builds beside the product library
+OBJ="${AT_OBJ:-$HERE/obj}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /usr/bin/g++
        -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -Xptxas -v ${AT_EXTRA_FLAGS:-})
-mkdir -p "$HERE/obj"
+mkdir -p "$OBJ"
 pids=()
 for f in at_util at_kmeans at_mel at_assign_tc at_resample; do
-  ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/obj/$f.o" > "$HERE/obj/$f.log" 2>&1 || { cat "$HERE/obj/$f.log"; exit 1; } ) &
+  ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$OBJ/$f.o" > "$OBJ/$f.log" 2>&1 || { cat "$OBJ/$f.log"; exit 1; } ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/obj/at_util.o "$HERE"/obj/at_kmeans.o "$HERE"/obj/at_mel.o "$HERE"/obj/at_assign_tc.o "$HERE"/obj/at_resample.o -lcudart
+"$NVCC" -shared -o "$OUT" "$OBJ"/at_util.o "$OBJ"/at_kmeans.o "$OBJ"/at_mel.o "$OBJ"/at_assign_tc.o "$OBJ"/at_resample.o -lcudart
 echo "built $OUT"

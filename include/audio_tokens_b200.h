@@ -73,6 +73,12 @@ int at_mel_plan_create(int sample_rate, int n_fft, int hop_length, int n_mels, i
 /* Optional: replace the built-in constants by the caller's (HOST pointers): window[n_fft] and the dense
  * filterbank fb[(n_fft/2+1) * n_mels] (row = frequency bin), e.g. the tensors torchaudio itself builds. */
 int at_mel_plan_set_constants_host(at_mel_plan *plan, const float *window, const float *fb);
+/* What at_mel_forward writes: AT_MEL_OUT_DB (default) = MelSpectrogram followed by AmplitudeToDB, the fused form of
+ * generate_mel_spectrogram (processors/spectrogram_generator.py:123-126); AT_MEL_OUT_POWER = the mel power spectrogram,
+ * i.e. torchaudio.transforms.MelSpectrogram alone (processors/spectrogram_generator.py:28-33,124), for callers that
+ * keep AmplitudeToDB as a separate operator (at_amplitude_to_db).  The power output cannot be min-max normalised. */
+enum { AT_MEL_OUT_DB = 0, AT_MEL_OUT_POWER = 1 };
+int at_mel_plan_set_output(at_mel_plan *plan, int kind);
 int at_mel_plan_destroy(at_mel_plan *plan);
 /* 1 + n_samples / hop_length (center=True). */
 int64_t at_mel_num_frames(const at_mel_plan *plan, int64_t n_samples);
@@ -92,6 +98,13 @@ int at_mel_forward(at_mel_plan *plan, const float *wave, const int64_t *sample_o
  * and copied back D2H on two streams so copies overlap compute.  Blocks until the result is in out. */
 int at_mel_forward_host(at_mel_plan *plan, const float *wave, int64_t uniform_samples, int B, float *out,
                         int32_t *bad_flags);
+
+/* torchaudio.transforms.AmplitudeToDB.forward (processors/spectrogram_generator.py:34,125; torchaudio
+ * functional.amplitude_to_DB with top_db=None): out = multiplier * log10(max(x, amin)) - multiplier * db_multiplier.
+ * AmplitudeToDB() defaults: multiplier 10 (stype "power"), amin 1e-10, db_multiplier log10(max(amin, 1)) = 0.
+ * Device pointers; in place (out == x) allowed. */
+int at_amplitude_to_db(const float *x, int64_t n, float multiplier, float amin, float db_multiplier, float *out,
+                       void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * normalize_vectors
