@@ -224,9 +224,9 @@ __device__ __forceinline__ void mbar_waitx(uint32_t bar, uint32_t parity) {
 }
 
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }  // VIMNMX3.U32
-// accumulator value of an A key (pattern * 8 + group) / a B key (pattern * 16 + class), exact: the pattern bits pushed out
+// accumulator value of an A key (pattern * 128 + id) / a B key (pattern * 16 + class), exact: the pattern bits pushed out
 // by the multiplication are the same for every binade in range (BIAS_HI); an all-ones key (nothing seen) maps above the range
-__device__ __forceinline__ float acc_a(uint32_t key) { return __uint_as_float(BIAS_HI | (key >> 3)); }
+__device__ __forceinline__ float acc_a(uint32_t key) { return __uint_as_float(BIAS_HI | (key >> 7)); }
 __device__ __forceinline__ float acc_b(uint32_t key) { return __uint_as_float(BIAS_HI | (key >> 4)); }
 
 // value split into three fp16 pieces (p1 + p2 + p3 ~ v to ~33 bits)
@@ -429,9 +429,10 @@ __device__ __forceinline__ uint32_t umin16(const uint32_t *k) {
 // 32 accumulator columns (two 16-column loads = two A groups, ga the index of the first one inside its tile).  The raw
 // fp32 patterns are scanned as unsigned integers (every accumulator lies in [2^13, 2^17), where the pattern order is the
 // value order); NO per-score key is built.  Two orthogonal groupings:
-//   A: the tile's 8 groups of 16 adjacent columns -> the group minimum gets its group index appended
-//      (pattern * 8 + group: one IMAD per 16 scores; the three pattern bits pushed out are the same for the whole range)
-//      -> exact running top-3 over the group minima of the tile;
+//   A: the tile's 8 groups of 16 adjacent columns -> the group minimum gets (tile mod 16, group) appended
+//      (pattern * 128 + id: one IMAD per 16 scores; the seven pattern bits pushed out are the same for the whole range)
+//      -> exact running top-3 over the group minima of a BLOCK of 16 tiles (2,048 centroids), merged into the row's
+//      top-3 once per block;
 //   B: 16 classes = column mod 16, running over ALL tiles of the row's sweep -> bp[h], the minimum pattern of class h
 //      (the class is the register index; it is appended once per row, after the sweep).
 // A group (tile, columns 16a .. 16a+15) and a B class share exactly one column, so two columns never share both: the
@@ -439,9 +440,9 @@ __device__ __forceinline__ uint32_t umin16(const uint32_t *k) {
 // runner-up can hide behind the winner in one grouping, never in both -- and the arg-min COLUMN is where the best A
 // group meets the best B class.
 // alu pipe: 16 (A minima) + 8 (A top-3) + 16 (B) per 32 columns = 1.25 per score; fma pipe: 2 IMAD per 32 columns.
-__device__ __forceinline__ void fold32(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const uint32_t ga, const uint32_t mul8,
+__device__ __forceinline__ void fold32(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const uint32_t ga, const uint32_t mul,
                                        uint32_t &t1, uint32_t &t2, uint32_t &t3, uint32_t (&bp)[16]) {
-    const uint32_t ga0 = umin16(ra) * mul8 + ga, ga1 = umin16(rb) * mul8 + (ga + 1u);
+    const uint32_t ga0 = umin16(ra) * mul + ga, ga1 = umin16(rb) * mul + (ga + 1u);
     const uint32_t lo = min(ga0, ga1), hi = max(ga0, ga1);
     t3 = umin3(t3, max(t2, lo), max(t1, hi));
     t2 = umin3(t2, hi, max(t1, lo));
@@ -574,16 +575,18 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
         const int ew = warp & 3;          // the TMEM lane quadrant this warp may read
         const int row_in_super = rt * TM + ew * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        const int ntiles = (int)my_tiles;
         uint32_t u = 0;
         bool primed = false;
         uint32_t c0[16], c1[16], c2[16], c3[16];
-        for (int64_t i = 0; i < my_tiles; i++) {
+        for (int i = 0; i < ntiles; i++) {
             uint32_t g1 = 0xFFFFFFFFu, g2 = 0xFFFFFFFFu, g3 = 0xFFFFFFFFu;   // A grouping: best three group minima of the row
+            uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;   // ... of the current block of 16 tiles
             uint32_t bp[16];                               // B grouping: class minima over the whole sweep
 #pragma unroll
             for (int h = 0; h < 16; h++) bp[h] = 0xFFFFFFFFu;
-            int j1 = 0, j2 = 0;                            // centroid tiles of g1, g2
-            const int64_t row = (worker + i * workers) * SROWS + row_in_super;
+            int j1 = 0, j2 = 0;                            // 16-tile blocks of g1, g2
+            const int64_t row = ((int64_t)worker + (int64_t)i * workers) * SROWS + row_in_super;
             const float erow_r = __ldg(erow + row);          // Sx |delta|
             const float xnS = __ldg(xns + row);              // Sx^2 |x|^2
             // Accumulator read-out in eight 16-column loads through four register buffers: two loads are always in flight
@@ -600,15 +603,15 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             for (int jt = 0; jt < ktiles; jt++, u++) {
                 const uint32_t acc = (u * RT + rt) % ACC_SLOTS;
                 const uint32_t ta = tmem + lane_addr + acc * TN;
-                uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;
+                const uint32_t idb = (uint32_t)(jt & 15) << 3;   // (tile mod 16, group) rides in the low 7 bits of an A key
                 tmem_ld_wait();                       // c0, c1 (issued during the previous tile)
                 tmem_ld16(ta + 32, c2);
                 tmem_ld16(ta + 48, c3);
-                fold32(c0, c1, 0u, key_mul, t1, t2, t3, bp);
+                fold32(c0, c1, idb, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tmem_ld16(ta + 64, c0);
                 tmem_ld16(ta + 80, c1);
-                fold32(c2, c3, 2u, key_mul, t1, t2, t3, bp);
+                fold32(c2, c3, idb + 2u, key_mul, t1, t2, t3, bp);
                 tmem_ld_wait();
                 tmem_ld16(ta + 96, c2);
                 tmem_ld16(ta + 112, c3);
@@ -620,9 +623,9 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 tc_fence_before();
                 __syncwarp();
                 mbar_arrive_elect(BAR(BAR_ACC_EMPTY + acc));
-                fold32(c0, c1, 4u, key_mul, t1, t2, t3, bp);
+                fold32(c0, c1, idb + 4u, key_mul, t1, t2, t3, bp);
                 // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
-                const bool more = (jt + 1 < ktiles) || (i + 1 < my_tiles);
+                const bool more = (jt + 1 < ktiles) || (i + 1 < ntiles);
                 const uint32_t vn = (u + 1) * RT + rt;
                 const uint32_t nbar = BAR(BAR_ACC_FULL + vn % ACC_SLOTS), nph = (vn / ACC_SLOTS) & 1;
                 const uint32_t tn = tmem + lane_addr + (vn % ACC_SLOTS) * TN;
@@ -633,29 +636,36 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                     tmem_ld16(tn + 16, c1);
                     started = true;
                 }
-                fold32(c2, c3, 6u, key_mul, t1, t2, t3, bp);
+                fold32(c2, c3, idb + 6u, key_mul, t1, t2, t3, bp);
                 if (more && !started) {
                     mbar_waitx(nbar, nph);
                     tc_fence_after();
                     tmem_ld16(tn, c0);
                     tmem_ld16(tn + 16, c1);
                 }
-                // A grouping: merge the tile's sorted triple into the row's (equal keys keep the earlier tile)
-                const bool p = t1 < g1;
-                const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
-                const uint32_t xa = p ? g1 : g2, ya = p ? t2 : t1;
-                const int xt = p ? j1 : j2;
-                const bool qn = ya < xa;
-                g2 = min(xa, ya);
-                j2 = qn ? jt : xt;
-                g1 = min(g1, t1);
-                j1 = p ? jt : j1;
-                g3 = n3;
+                if ((jt & 15) == 15 || jt + 1 == ktiles) {
+                    // A grouping: merge the block's sorted triple into the row's (equal keys keep the earlier block); once per
+                    // sweep up to 2,048 centroids
+                    const int jb = jt >> 4;
+                    const bool p = t1 < g1;
+                    const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
+                    const uint32_t xa = p ? g1 : g2, ya = p ? t2 : t1;
+                    const int xt = p ? j1 : j2;
+                    const bool qn = ya < xa;
+                    g2 = min(xa, ya);
+                    j2 = qn ? jb : xt;
+                    g1 = min(g1, t1);
+                    j1 = p ? jb : j1;
+                    g3 = n3;
+                    t1 = t2 = t3 = 0xFFFFFFFFu;
+                }
             }
+            // column tiles of the two best A groups
+            j1 = j1 * 16 + (int)((g1 >> 3) & 15u), j2 = j2 * 16 + (int)((g2 >> 3) & 15u);
             // B grouping: the class index is appended now (pattern * 16 + class), then the top-3 of the 16 class minima
             // (the row minimum is the same value in both groupings: acc_b(h1) == acc_a(g1))
 #pragma unroll
-            for (int h = 0; h < 16; h++) bp[h] = bp[h] * (2u * key_mul) + (uint32_t)h;
+            for (int h = 0; h < 16; h++) bp[h] = bp[h] * (key_mul >> 3) + (uint32_t)h;
             uint32_t h1 = min(bp[0], bp[1]), h2 = max(bp[0], bp[1]), h3 = 0xFFFFFFFFu;
 #pragma unroll
             for (int pr = 1; pr < 8; pr++) {
@@ -1009,19 +1019,32 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     AT_CUDA_OK(cudaMemsetAsync(rows->tail_count, 0, 2 * sizeof(unsigned int), st));
     if (resident)
         k_assign_tc<true><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
-                                                            ix->tc_scale, 8u, l32, labels64, kdist, rows->tail,
+                                                            ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
                                                             rows->tail_count, (unsigned int)rows->cap);
     else
         k_assign_tc<false><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
-                                                             ix->tc_scale, 8u, l32, labels64, kdist, rows->tail,
+                                                             ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
                                                              rows->tail_count, (unsigned int)rows->cap);
     AT_LAUNCH_OK();
+    // The two tail kernels touch disjoint rows: the exact scans (few rows, FMA-bound) run on the index's side stream while
+    // the candidate re-checks (many rows, latency-bound) run on the caller's, joined again before anything reads the labels.
+#ifndef AT_TC_TAIL_FORK
+#define AT_TC_TAIL_FORK 1
+#endif
+    const bool fork = AT_TC_TAIL_FORK && ix->side_ok();
+    cudaStream_t fs = fork ? ix->side : st;
+    if (fork) {
+        AT_CUDA_OK(cudaEventRecord(ix->ev_fork, st));
+        AT_CUDA_OK(cudaStreamWaitEvent(ix->side, ix->ev_fork, 0));
+    }
+    k_tc_full<<<sms * 8, FULL_ROWS * FULL_SLICES, 0, fs>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
+                                            (unsigned int)rows->cap, l32, labels64, kdist);
+    AT_LAUNCH_OK();
+    if (fork) AT_CUDA_OK(cudaEventRecord(ix->ev_join, ix->side));
     k_tc_tail<<<sms * 8, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, rows->tail, rows->tail_count, l32, labels64, kdist,
                                       ix->tc_counters);
     AT_LAUNCH_OK();
-    k_tc_full<<<sms * 8, FULL_ROWS * FULL_SLICES, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
-                                            (unsigned int)rows->cap, l32, labels64, kdist);
-    AT_LAUNCH_OK();
+    if (fork) AT_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_join, 0));
     if (dist && exact_dist) {
         k_exact_dist<<<sms * 8, 256, 0, st>>>(x, n, l2norm_rows, ix->c, ix->cn, l32, l32 ? nullptr : labels64, dist);
         AT_LAUNCH_OK();

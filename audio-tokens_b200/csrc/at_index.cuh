@@ -35,6 +35,22 @@ struct at_index {
     int32_t *part_lab = nullptr;  // scratch labels for a distance-only request
     int64_t part_cap = 0;
     int ktiles = 0;
+    // side stream + fork / join events of the tensor search's two tail kernels (created on first use)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool side_failed = false;
+    bool side_ok() {
+        if (side) return true;
+        if (side_failed) return false;
+        if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            side = nullptr, side_failed = true;
+            return false;
+        }
+        return true;
+    }
 };
 
 struct at_kmeans {

@@ -584,6 +584,9 @@ int at_index_destroy(at_index *ix) {
     cudaFree(ix->tc_counters);
     cudaFree(ix->part_lab);
     tc_rows_free(&ix->rows);
+    if (ix->side) cudaStreamDestroy(ix->side);
+    if (ix->ev_fork) cudaEventDestroy(ix->ev_fork);
+    if (ix->ev_join) cudaEventDestroy(ix->ev_join);
     delete ix;
     return AT_OK;
 }
