@@ -53,6 +53,7 @@ PROTOTYPES = {
     "at_kmeans_accumulate": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "at_kmeans_finalize": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "at_kmeans_set_incremental": (c_int, [c_ptr, c_int]),
+    "at_kmeans_invalidate": (c_int, [c_ptr]),
     "at_pcm16_to_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "at_resample_plan_create": (c_int, [c_int, c_int, c_ptr]),
     "at_resample_bank_host": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),

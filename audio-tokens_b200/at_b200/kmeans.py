@@ -71,6 +71,7 @@ class LloydTrainer:
         self.accum = torch.zeros(words, dtype=torch.int64, device="cuda")
         self._absmax = torch.zeros(1, dtype=torch.float32, device="cuda")
         self.n_total = 0
+        self._rows_key = None   # identity of the rows the library's caches (row image, previous labels) were built from
 
     def __del__(self):
         try:
@@ -85,7 +86,11 @@ class LloydTrainer:
         import torch
 
         dist, _, world = _world(self.group)
-        _lib.check(self.lib.at_absmax(_lib.ptr(x_local), x_local.numel(), _lib.ptr(self._absmax), _lib.stream_ptr()))
+        self._rows_key = self._key(x_local)
+        if x_local.numel() == 0:   # a shard left empty by the subsample: nothing to scan (at_absmax rejects a null pointer)
+            self._absmax.zero_()
+        else:
+            _lib.check(self.lib.at_absmax(_lib.ptr(x_local), x_local.numel(), _lib.ptr(self._absmax), _lib.stream_ptr()))
         if world > 1:
             dist.all_reduce(self._absmax, op=dist.ReduceOp.MAX, group=self.group or None)
             if n_total is None:
@@ -96,6 +101,17 @@ class LloydTrainer:
             n_total = x_local.shape[0]
         self.n_total = int(n_total)
         _lib.check(self.lib.at_kmeans_begin(self.h, float(self._absmax.item()), self.n_total))
+
+    @staticmethod
+    def _key(x):
+        # data pointer + shape + torch's in-place version counter: a different tensor at a recycled address, or the same
+        # tensor modified in place, changes the key
+        return (x.data_ptr(), tuple(x.shape), getattr(x, "_version", 0))
+
+    def invalidate(self):
+        """Drop the library's per-training-set caches (at_kmeans_invalidate)."""
+        _lib.check(self.lib.at_kmeans_invalidate(self.h))
+        self._rows_key = None
 
     def set_centroids(self, c):
         import torch
@@ -118,6 +134,12 @@ class LloydTrainer:
         """One Lloyd iteration over this rank's rows.  stats_out: CUDA float32[4] (objective, nsplit,
         imbalance factor, empty clusters) or None.  No host synchronisation."""
         dist, _, world = _world(self.group)
+        key = self._key(x_local)
+        if key != self._rows_key:
+            # not the rows begin() / the previous step saw (another tensor, possibly at a recycled address, or an in-place
+            # update): the cached fp16 image and the incremental sums would be stale
+            _lib.check(self.lib.at_kmeans_invalidate(self.h))
+            self._rows_key = key
         _lib.check(self.lib.at_kmeans_accumulate(self.h, _lib.ptr(x_local), x_local.shape[0], 0, self.algo,
                                                  _lib.ptr(self.accum), _lib.ptr(labels), _lib.stream_ptr()))
         if world > 1:
@@ -238,7 +260,18 @@ class Kmeans:
         stats = None
         t0 = time.time()
         if nx == k:
-            self._final = cent
+            # faiss::Clustering::train_encoded: with exactly k training points the centroids ARE the training set, in input
+            # order (init_centroids and the permutation are ignored), and one all-zero iteration stat is pushed
+            full = torch.zeros((k, d), dtype=torch.float32, device=x.device)
+            if perm is None:
+                full[off:off + n_local] = x
+            else:   # (unreachable with FAISS's parameters: subsampling to exactly k rows needs max_points_per_centroid = 1)
+                pos = torch.from_numpy(np.nonzero(mine)[0]).to(x.device)
+                full.index_copy_(0, pos, x_train)
+            if world > 1:
+                dist.all_reduce(full, group=self.group or None)
+            self._final = full
+            stats = torch.zeros((1, 4), dtype=torch.float32, device=x.device)
         else:
             backend.begin(x_train, nx)
             backend.set_centroids(cent)
@@ -247,7 +280,7 @@ class Kmeans:
                 backend.step(x_train, stats[it])
             self._final = backend.get_centroids()
         self.centroids = self._final.cpu().numpy()
-        st = stats[: cp.niter].cpu().numpy() if stats is not None else np.zeros((0, 4), dtype=np.float32)
+        st = stats[: (1 if nx == k else cp.niter)].cpu().numpy() if stats is not None else np.zeros((0, 4), dtype=np.float32)
         elapsed = time.time() - t0
         self.iteration_stats = [
             dict(obj=float(r[0]), time=elapsed * (i + 1) / max(len(st), 1), time_search=0.0,

@@ -69,10 +69,13 @@
 
 namespace at {
 
-constexpr int TC_THREADS = 512;
+#ifndef AT_TC_RT
+#define AT_TC_RT 3
+#endif
 constexpr int TM = 128;          // rows per MMA tile (UMMA M)
 constexpr int TN = 128;          // centroids per tile (UMMA N)
-constexpr int RT = 3;            // row tiles per super tile
+constexpr int RT = AT_TC_RT;     // row tiles per super tile
+constexpr int TC_THREADS = 128 + RT * 128;   // 4 service warps + 4 scanning warps per row tile
 constexpr int SROWS = RT * TM;   // 384
 // SPLIT_C (build-time experiment, off): the centroid operand as the sum of two fp16 tiles (hi + lo, ~22 significant bits)
 // multiplied in two passes (9 MMAs per accumulator instead of 5).  The certification threshold then loses its dominant term
@@ -557,7 +560,9 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
 #pragma unroll
                         for (int kk = 0; kk < 4; kk++) umma_f16(d, dA + 2 * kk, dB_lo + 2 * kk, IDESC, 1);
                     }
+#ifndef AT_TC_NO_AUG   // timing experiment only (wrong results): the cost of the K step that carries the norms
                     umma_f16(d, dA_aug, dB_aug, IDESC, 1);
+#endif
 #endif
                     umma_commit(BAR(BAR_ACC_FULL + acc));
                 }
@@ -569,7 +574,11 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             umma_commit(BAR(BAR_A_EMPTY + ab));
         }
     } else if (warp >= 4) {
+        #if AT_TC_RT == 3
         asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+#else
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+#endif
         // ================================================================== epilogue: accumulator scan
         const int rt = (warp - 4) >> 2;   // row tile of the super tile
         const int ew = warp & 3;          // the TMEM lane quadrant this warp may read

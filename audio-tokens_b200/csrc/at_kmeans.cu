@@ -706,6 +706,13 @@ int at_kmeans_set_incremental(at_kmeans *km, int on) {
     return AT_OK;
 }
 
+int at_kmeans_invalidate(at_kmeans *km) {
+    AT_REQUIRE(km, "at_kmeans_invalidate: bad arguments");
+    km->rows_valid = false;   // the next accumulate rebuilds the fp16 row image ...
+    km->prev_valid = false;   // ... and regroups every row
+    return AT_OK;
+}
+
 int at_kmeans_set_centroids(at_kmeans *km, const float *centroids, void *stream) {
     AT_REQUIRE(km && centroids, "at_kmeans_set_centroids: bad arguments");
     km->prev_valid = false;   // new centroids from outside: the next accumulate regroups every row

@@ -88,6 +88,6 @@ class ClusterCreator:
 
 
 if __name__ == "__main__":
-    from audio_tokens_config import AudioTokensConfig
+    from audio_tokens_config import AudioTokensConfig   # the reference's own config (resolved from its checkout)
 
     ClusterCreator(AudioTokensConfig()).run()

@@ -100,6 +100,6 @@ class SpecTokenizer:
 
 
 if __name__ == "__main__":
-    from audio_tokens_config import AudioTokensConfig
+    from audio_tokens_config import AudioTokensConfig   # the reference's own config (resolved from its checkout)
 
     SpecTokenizer(AudioTokensConfig()).run()

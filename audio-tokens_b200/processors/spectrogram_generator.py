@@ -166,6 +166,6 @@ class SpectrogramGenerator:
 
 
 if __name__ == "__main__":
-    from audio_tokens_config import AudioTokensConfig
+    from audio_tokens_config import AudioTokensConfig   # the reference's own config (resolved from its checkout)
 
     SpectrogramGenerator(AudioTokensConfig()).run()

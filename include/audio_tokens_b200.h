@@ -177,6 +177,13 @@ int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, flo
  * the old cluster's exact integer sum and added to the new one, which gives bit-identical sums to regrouping every
  * row.  on = 0 switches this off (every accumulate regroups every row); default on. */
 int at_kmeans_set_incremental(at_kmeans *km, int on);
+/* CONTRACT of the two caches behind at_kmeans_accumulate (the fp16 operand image of the rows, and the incremental
+ * update's previous labels and local sums): they are keyed on (x pointer, n_local) only, so the CONTENTS of x must not
+ * change between at_kmeans_begin and the last accumulate of that training set.  A caller that re-uses a buffer for new
+ * rows (or mutates it in place) without calling at_kmeans_begin again must call at_kmeans_invalidate first: the next
+ * accumulate then rebuilds the image and regroups every row.  (faiss.Kmeans.train has no such state: every train() call
+ * of the look-alike goes through at_kmeans_begin.) */
+int at_kmeans_invalidate(at_kmeans *km);
 
 /* faiss::rand_perm(perm, n, seed) (faiss/utils/random.cpp): forward Fisher-Yates driven by std::mt19937(seed),
  * i2 = i + mt() % (n - i).  HOST function, HOST pointer.  Used for FAISS's training-set subsample (seed 1234)

@@ -23,6 +23,9 @@
 #include <stddef.h>
 #include <string.h>
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* ------------------------------------------------------------------ mt19937 */
 typedef struct {
@@ -157,18 +160,57 @@ void ref_compute_centroids(int64_t d, int64_t k, int64_t n, const float *x,
                            const int64_t *assign, float *hassign, float *centroids) {
     memset(centroids, 0, sizeof(float) * (size_t)(d * k));
     memset(hassign, 0, sizeof(float) * (size_t)k);
-    for (int64_t i = 0; i < n; i++) {
-        int64_t ci = assign[i];
-        float *c = centroids + ci * d;
-        const float *xi = x + i * d;
-        hassign[ci] += 1.0f;
-        for (int64_t j = 0; j < d; j++) c[j] += xi[j];
+    /* like upstream: every thread walks all points and accumulates the clusters of its own slice
+     * [k rank / nt, k (rank+1) / nt), so each cluster is summed by one thread in point-index order and the result
+     * does not depend on the thread count */
+#pragma omp parallel
+    {
+        int nt = 1, rank = 0;
+#ifdef _OPENMP
+        nt = omp_get_num_threads();
+        rank = omp_get_thread_num();
+#endif
+        const int64_t c0 = (k * rank) / nt, c1 = (k * (rank + 1)) / nt;
+        for (int64_t i = 0; i < n; i++) {
+            int64_t ci = assign[i];
+            if (ci >= c0 && ci < c1) {
+                float *c = centroids + ci * d;
+                const float *xi = x + i * d;
+                hassign[ci] += 1.0f;
+                for (int64_t j = 0; j < d; j++) c[j] += xi[j];
+            }
+        }
     }
+#pragma omp parallel for schedule(static)
     for (int64_t ci = 0; ci < k; ci++) {
         if (hassign[ci] == 0) continue;
         float norm = 1 / hassign[ci];
         float *c = centroids + ci * d;
         for (int64_t j = 0; j < d; j++) c[j] *= norm;
+    }
+}
+
+/* exhaustive_L2sqr_blas' epilogue for one (nx x ny) block of inner products ip (row stride ldip, produced by an sgemm):
+ * dis = x_norm + y_norm - 2 ip, negative -> 0, strict '<' against the running best (the lowest index wins ties, blocks are
+ * visited in ascending j0).  faiss/utils/distances.cpp. */
+void ref_l2_block_argmin(const float *ip, int64_t nx, int64_t ny, int64_t ldip, const float *x_norms,
+                         const float *y_norms, int64_t j0, float *best, int64_t *labels) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < nx; i++) {
+        const float *row = ip + i * ldip;
+        const float xn = x_norms[i];
+        float b = best[i];
+        int64_t bj = labels[i];
+        for (int64_t j = 0; j < ny; j++) {
+            float dis = xn + y_norms[j] - 2 * row[j];
+            if (dis < 0) dis = 0;
+            if (dis < b) {
+                b = dis;
+                bj = j0 + j;
+            }
+        }
+        best[i] = b;
+        labels[i] = bj;
     }
 }
 

@@ -56,6 +56,7 @@ def _lib():
         lib.ref_assign_l2.argtypes = [f32p, i64, f32p, i64, i64, i64p, f32p, f32p]
         lib.ref_assign_l2_f64.argtypes = [f32p, i64, f32p, i64, i64, i64p, ctypes.c_void_p, ctypes.c_void_p]
         lib.ref_compute_centroids.argtypes = [i64, i64, i64, f32p, i64p, f32p, f32p]
+        lib.ref_l2_block_argmin.argtypes = [f32p, i64, i64, i64, f32p, f32p, i64, f32p, i64p]
         lib.ref_split_clusters.argtypes = [i64, i64, i64, f32p, f32p]
         lib.ref_split_clusters.restype = ctypes.c_int
         _LIB = lib
@@ -127,22 +128,22 @@ def knn_l2sqr_blas(x, c, bs_x=4096, bs_y=1024):
         import torch
 
         xt, ct = torch.from_numpy(x), torch.from_numpy(c)
-        x_norms = (xt * xt).sum(1)
-        c_norms = (ct * ct).sum(1)
-        best = torch.full((n,), float("inf"), dtype=torch.float32)
-        labels = torch.zeros(n, dtype=torch.int64)
+        x_norms = (xt * xt).sum(1).numpy()
+        c_norms = (ct * ct).sum(1).numpy()
+        best = np.full(n, np.inf, dtype=np.float32)
+        labels = np.zeros(n, dtype=np.int64)
+        lib = _lib()
+        ip = torch.empty((min(bs_x, n), min(bs_y, k)), dtype=torch.float32)
         for i0 in range(0, n, bs_x):
             i1 = min(n, i0 + bs_x)
             for j0 in range(0, k, bs_y):
                 j1 = min(k, j0 + bs_y)
-                ip = xt[i0:i1] @ ct[j0:j1].T
-                dis = x_norms[i0:i1, None] + c_norms[None, j0:j1] - 2 * ip
-                dis.clamp_(min=0)
-                bmin, bidx = dis.min(1)  # first minimal index, like the strict '<' scan
-                upd = bmin < best[i0:i1]
-                best[i0:i1] = torch.where(upd, bmin, best[i0:i1])
-                labels[i0:i1] = torch.where(upd, bidx + j0, labels[i0:i1])
-        return best.numpy(), labels.numpy()
+                blk = ip[: i1 - i0, : j1 - j0]
+                torch.mm(xt[i0:i1], ct[j0:j1].T, out=blk)   # the sgemm of the block (MKL, all host threads)
+                # fused epilogue in C (OpenMP): distances, clamp, strict '<' top-1 -- what FAISS does after its sgemm
+                lib.ref_l2_block_argmin(blk.data_ptr(), i1 - i0, j1 - j0, ip.stride(0), _p(x_norms[i0:i1]),
+                                        _p(c_norms[j0:j1]), j0, _p(best[i0:i1]), _p(labels[i0:i1]))
+        return best, labels
     except ImportError:  # pragma: no cover
         x_norms = (x * x).sum(1)
         c_norms = (c * c).sum(1)
@@ -334,7 +335,10 @@ class Kmeans:
             if n_input < k:
                 centroids[n_input:] = x[perm[n_input:k]]
             if n == k:
-                best_centroids = centroids
+                # train_encoded's corner case: the training set IS the centroids, in input order (init_centroids and the
+                # permutation are ignored), and one all-zero iteration stat is pushed
+                best_centroids = x.copy()
+                stats.append(dict(obj=0.0, time=0.0, time_search=0.0, imbalance_factor=0.0, nsplit=0))
                 break
             t0 = time.time()
             for it in range(cp.niter):

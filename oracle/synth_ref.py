@@ -97,3 +97,32 @@ def make_clips(seed: int, first: int, count: int, n_samples: int) -> np.ndarray:
     for i in range(count):
         out[i] = make_clip(seed, first + i, n_samples, table)
     return out
+
+
+_CLIB = None
+
+
+def make_clips_c(seed: int, first: int, count: int, n_samples: int, pcm16: bool = False) -> np.ndarray:
+    """Same clips through the C twin (oracle/synth_ref.c, OpenMP over clips): what bench.py's CPU arm uses to build its
+    input in seconds.  Bit-identical to make_clips (tests/test_oracle_synth.py).  pcm16=True returns the int16 samples."""
+    import ctypes
+    import os
+
+    global _CLIB
+    if _CLIB is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        path = os.path.join(here, "_ref", "libsynth_ref.so")
+        if not os.path.exists(path):
+            import subprocess
+
+            subprocess.check_call(["make", "-C", here], stdout=subprocess.DEVNULL)
+        _CLIB = ctypes.CDLL(path)
+        _CLIB.ref_synth_clips.argtypes = [ctypes.c_uint32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _CLIB.ref_synth_clips.restype = None
+    table = np.ascontiguousarray(sine_table())
+    out = np.empty((count, n_samples), dtype=np.int16 if pcm16 else np.float32)
+    ptr = out.ctypes.data_as(ctypes.c_void_p)
+    _CLIB.ref_synth_clips(seed & 0xFFFFFFFF, first, count, n_samples, table.ctypes.data_as(ctypes.c_void_p),
+                          None if pcm16 else ptr, ptr if pcm16 else None)
+    return out

@@ -1,10 +1,8 @@
-"""Configuration object of the hot-path stages.
-
-The drop-in processors read a config by attribute name, so the reference's own ``AudioTokensConfig``
-(audio_tokens_config.py:14-81 of danavery/audio-tokens) can be passed unchanged.  This class carries the same
-field names and defaults for the three preprocessing stages, so tests and benchmarks run without the reference
-checkout, plus the knobs that only exist here (all defaulting to the reference's behaviour and always read with
-``getattr(config, name, default)``).
+"""TEST FIXTURE: a stand-in for the reference's ``AudioTokensConfig`` (audio_tokens_config.py:14-81 of
+danavery/audio-tokens) carrying the fields the three hot-path stages read, with the reference's defaults, plus the knobs
+that only exist in the B200 stages (read there with ``getattr(config, name, default)``).  The product never ships a config
+class: the drop-in stages take the reference's own object (at_b200.dropin leaves ``audio_tokens_config`` to the reference
+checkout).  /root/reference does not exist on the GPU box, hence this fixture.
 """
 from __future__ import annotations
 
@@ -21,7 +19,7 @@ def _here(*parts) -> str:
 
 
 @dataclass
-class AudioTokensConfig:
+class StageConfig:
     # shared
     random_seed: int = 4242
 

@@ -329,3 +329,49 @@ def test_lloyd_incremental_update_bit_identical_to_full_regroup(k):
     assert torch.equal(outs[0][1], outs[1][1])
     changed = (outs[1][2][1:] != outs[1][2][:-1]).sum(dim=1)
     assert int(changed[0]) > 0   # the incremental path had rows to move
+
+
+def test_kmeans_with_exactly_k_points_copies_the_training_set():
+    """faiss::Clustering::train_encoded's corner case nx == k: centroids = the training set in input order, whatever
+    init_centroids says, one all-zero iteration stat."""
+    from at_b200 import Kmeans
+    from oracle import faiss_ref
+
+    _, l2 = _frames(4)
+    x = l2.cpu().numpy()[:48]
+    km = Kmeans(64, 48, niter=5)
+    obj = km.train(x, init_centroids=x[::-1][:7].copy())
+    ref = faiss_ref.Kmeans(64, 48, niter=5)
+    robj = ref.train(x, init_centroids=x[::-1][:7].copy())
+    assert np.array_equal(km.centroids, x) and np.array_equal(ref.centroids, x)
+    assert len(km.iteration_stats) == 1 == len(ref.iteration_stats) and obj == 0.0 == robj
+
+
+def test_lloyd_trainer_notices_new_rows_at_the_same_address():
+    """The row image and the incremental sums are cached per training set; a different batch in the same buffer (or an
+    in-place update) must not be searched through the stale image (at_kmeans_invalidate)."""
+    import torch
+    from at_b200 import LloydTrainer
+    from oracle import faiss_ref
+
+    _, l2 = _frames(30)
+    a, b = l2[:1200].clone(), l2[1200:2400].clone()
+    k = 64
+    cents = a[torch.from_numpy(faiss_ref.rand_perm(1200, 1235)[:k].astype("int64")).cuda()].contiguous()
+
+    def one_step(tr, x):
+        tr.set_centroids(cents)
+        tr.step(x, None)
+        return tr.get_centroids()
+
+    fresh = LloydTrainer(64, k)
+    fresh.begin(b)
+    want = one_step(fresh, b)
+    tr = LloydTrainer(64, k)
+    buf = a.clone()
+    tr.begin(buf)
+    one_step(tr, buf)
+    tr.step(buf, None)                 # incremental state now describes batch a
+    buf.copy_(b)                       # same pointer, same shape, new contents
+    got = one_step(tr, buf)
+    assert torch.equal(got, want)

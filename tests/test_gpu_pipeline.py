@@ -12,9 +12,9 @@ SR, L = 22050, 22050 * 3
 
 
 def _config(tmp_path, **over):
-    from audio_tokens_config import AudioTokensConfig
+    from stage_config import StageConfig
 
-    cfg = AudioTokensConfig()
+    cfg = StageConfig()
     cfg.split_file = str(tmp_path / "split.json")
     cfg.dest_spec_path = tmp_path / "spectrograms"
     cfg.source_spec_path = tmp_path / "spectrograms"
