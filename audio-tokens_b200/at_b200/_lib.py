@@ -54,6 +54,15 @@ PROTOTYPES = {
     "at_kmeans_finalize": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "at_kmeans_set_incremental": (c_int, [c_ptr, c_int]),
     "at_kmeans_invalidate": (c_int, [c_ptr]),
+    "at_peer_create": (c_int, [c_int, c_int, c_i64, c_ptr]),
+    "at_peer_export": (c_int, [c_ptr, c_ptr]),
+    "at_peer_import": (c_int, [c_ptr, c_int, c_ptr]),
+    "at_peer_connect": (c_int, [c_ptr]),
+    "at_peer_destroy": (c_int, [c_ptr]),
+    "at_peer_local_buffer": (c_ptr, [c_ptr]),
+    "at_peer_total": (c_ptr, [c_ptr]),
+    "at_peer_reduce": (c_int, [c_ptr, c_ptr]),
+    "at_peer_status": (c_int, [c_ptr, c_ptr]),
     "at_pcm16_to_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "at_resample_plan_create": (c_int, [c_int, c_int, c_ptr]),
     "at_resample_bank_host": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -102,6 +111,11 @@ def stream_ptr():
     import torch
 
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ctypes_stream(stream):
+    """A torch.cuda.Stream as a void* for the C ABI."""
+    return ctypes.c_void_p(stream.cuda_stream)
 
 
 def ptr(t):

@@ -54,10 +54,84 @@ def _world(group):
     return dist, dist.get_rank(group), dist.get_world_size(group)
 
 
-class LloydTrainer:
-    """Device-level Lloyd loop state for (k, d).  All tensors are CUDA tensors on the current device."""
+class PeerReducer:
+    """The per-iteration exchange over peer memory (at_peer_*): every rank's accumulator window is mapped by all the
+    others through CUDA IPC and one kernel signals, waits and sums them over NVLink.  torch.distributed is used once, to
+    exchange the 64-byte handles."""
 
-    def __init__(self, d: int, k: int, group=False, algo: int = _lib.ALGO_AUTO):
+    def __init__(self, group, words: int):
+        import torch
+        import torch.distributed as dist
+
+        self.lib = _lib.load()
+        g = group or None
+        self.rank, self.world = dist.get_rank(g), dist.get_world_size(g)
+        self.h = None
+        h = ctypes.c_void_p()
+        ok = self.world <= 16 and self.lib.at_peer_create(self.rank, self.world, words, ctypes.byref(h)) == 0
+        handle = torch.zeros(64, dtype=torch.uint8)
+        if ok:
+            ok = self.lib.at_peer_export(h, _lib.ptr(handle)) == 0
+        # a collective decision at every step: a rank must never be alone in (or out of) the peer protocol
+        ok = self._all_ok(ok, g)
+        handles = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
+        dist.all_gather(handles, handle.cuda(), group=g)
+        if ok:
+            for r, hd in enumerate(handles):
+                hb = hd.cpu().contiguous()
+                if r != self.rank and self.lib.at_peer_import(h, r, _lib.ptr(hb)) != 0:
+                    ok = False
+                    break
+        ok = self._all_ok(ok, g)   # doubles as the barrier at_peer_connect asks for
+        if ok:
+            ok = self.lib.at_peer_connect(h) == 0
+        ok = self._all_ok(ok, g)
+        if not ok:
+            if h:
+                self.lib.at_peer_destroy(h)
+            raise RuntimeError("peer-memory reduction unavailable: " + self.lib.at_last_error().decode("utf-8", "replace"))
+        self.h = h
+
+    @staticmethod
+    def _all_ok(ok, g):
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=g)
+        return bool(t.item())
+
+    def local_buffer(self):
+        return ctypes.c_void_p(self.lib.at_peer_local_buffer(self.h))
+
+    def total(self):
+        return ctypes.c_void_p(self.lib.at_peer_total(self.h))
+
+    def reduce(self):
+        _lib.check(self.lib.at_peer_reduce(self.h, _lib.stream_ptr()))
+
+    def status(self):
+        _lib.check(self.lib.at_peer_status(self.h, _lib.stream_ptr()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.at_peer_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class LloydTrainer:
+    """Device-level Lloyd loop state for (k, d).  All tensors are CUDA tensors on the current device.
+
+    reduce: how the ranks' accumulators are summed each iteration when ``group`` spans several ranks -- "peer" (one kernel
+    over CUDA-IPC-mapped peer memory, at_peer_*), "nccl" (torch.distributed all_reduce) or "auto" (peer when it can be set
+    up on every rank, else nccl; AT_B200_REDUCE overrides)."""
+
+    def __init__(self, d: int, k: int, group=False, algo: int = _lib.ALGO_AUTO, reduce: str = "auto"):
+        import os
+
         import torch
 
         _lib.require_cuda()
@@ -72,6 +146,19 @@ class LloydTrainer:
         self._absmax = torch.zeros(1, dtype=torch.float32, device="cuda")
         self.n_total = 0
         self._rows_key = None   # identity of the rows the library's caches (row image, previous labels) were built from
+        self.peer = None
+        self.reduce = "none"
+        dist, _, world = _world(self.group)
+        if world > 1:
+            reduce = os.environ.get("AT_B200_REDUCE", reduce)
+            self.reduce = "nccl"
+            if reduce in ("auto", "peer"):
+                try:
+                    self.peer = PeerReducer(self.group, words)
+                    self.reduce = "peer"
+                except RuntimeError:
+                    if reduce == "peer":
+                        raise
 
     def __del__(self):
         try:
@@ -140,6 +227,14 @@ class LloydTrainer:
             # update): the cached fp16 image and the incremental sums would be stale
             _lib.check(self.lib.at_kmeans_invalidate(self.h))
             self._rows_key = key
+        if self.peer is not None:
+            # accumulate straight into this rank's window; one kernel signals, waits and adds the windows over NVLink
+            _lib.check(self.lib.at_kmeans_accumulate(self.h, _lib.ptr(x_local), x_local.shape[0], 0, self.algo,
+                                                     self.peer.local_buffer(), _lib.ptr(labels), _lib.stream_ptr()))
+            self.peer.reduce()
+            _lib.check(self.lib.at_kmeans_finalize(self.h, self.peer.total(), self.n_total, _lib.ptr(stats_out),
+                                                   _lib.stream_ptr()))
+            return
         _lib.check(self.lib.at_kmeans_accumulate(self.h, _lib.ptr(x_local), x_local.shape[0], 0, self.algo,
                                                  _lib.ptr(self.accum), _lib.ptr(labels), _lib.stream_ptr()))
         if world > 1:

@@ -84,24 +84,20 @@ class HotPath:
         tok, cents = self.cluster_and_tokenize(spec, l2, row_offset, n_total, stats, bufs.get("tokens"))
         return tok, cents, bad
 
-    def run_host(self, wave_host, bufs, chunk_clips=296, row_offset=0, n_total=None):
-        """End to end from HOST memory: wave_host (B, L) pinned tensor, fp32 waveforms or the decoder's int16 PCM (half
-        the PCIe bytes; widened on the device with at_pcm16_to_f32, bufs from alloc_bufs(..., pcm16=True)).  Chunks are
-        copied H2D on a copy stream while the mel kernel works on the previous chunk; tokens (int64) and centroids are
-        copied back into the pinned host tensors bufs["tokens_host"], bufs["centroids_host"].  Blocks until they are
-        there."""
+    def _ingest(self, wave_host, bufs, bad, chunk_clips, mel_stream):
+        """H2D copy of one batch in chunks on bufs["copy_stream"], widening (int16 PCM) + mel on ``mel_stream`` into
+        bufs["spec"] / bufs["l2"]; chunk i+1 is copied while chunk i is transformed.  Returns an event recorded on
+        ``mel_stream`` after the last mel launch."""
         import torch
 
         pcm16 = wave_host.dtype == torch.int16
         B, L = wave_host.shape
-        T = self.plan.num_frames(L)
         spec, l2 = bufs["spec"], bufs["l2"]
         stage = bufs["stage"]  # (2, chunk_clips, L) device
-        main = torch.cuda.current_stream()
         copy = bufs["copy_stream"]
-        bad = torch.zeros(B, dtype=torch.int32, device="cuda")
-        copy.wait_stream(main)
+        copy.wait_stream(mel_stream)
         ev_free = [None, None]
+        sp = _lib.ctypes_stream(mel_stream)
         for ci, b0 in enumerate(range(0, B, chunk_clips)):
             nb = min(chunk_clips, B - b0)
             sb = ci & 1
@@ -111,21 +107,80 @@ class HotPath:
                 (bufs["stage16"] if pcm16 else stage)[sb, :nb].copy_(wave_host[b0:b0 + nb], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
-            main.wait_event(ev)
+            mel_stream.wait_event(ev)
             if pcm16:
-                _lib.check(self.plan.lib.at_pcm16_to_f32(_lib.ptr(bufs["stage16"][sb]), nb * L, _lib.ptr(stage[sb]),
-                                                         _lib.stream_ptr()))
+                _lib.check(self.plan.lib.at_pcm16_to_f32(_lib.ptr(bufs["stage16"][sb]), nb * L, _lib.ptr(stage[sb]), sp))
             _lib.check(self.plan.lib.at_mel_forward(self.plan.h, _lib.ptr(stage[sb]), None, None, L, nb,
-                                                    _lib.ptr(spec[b0:]), _lib.ptr(l2[b0:]), _lib.ptr(bad[b0:]),
-                                                    _lib.stream_ptr()))
+                                                    _lib.ptr(spec[b0:]), _lib.ptr(l2[b0:]), _lib.ptr(bad[b0:]), sp))
             ev_free[sb] = torch.cuda.Event()
-            ev_free[sb].record(main)
-        tok, cents = self.cluster_and_tokenize(spec, l2, row_offset, n_total, None, bufs.get("tokens"))
+            ev_free[sb].record(mel_stream)
+        done = torch.cuda.Event()
+        done.record(mel_stream)
+        return done
+
+    def run_host(self, wave_host, bufs, chunk_clips=296, row_offset=0, n_total=None):
+        """End to end from HOST memory: wave_host (B, L) pinned tensor, fp32 waveforms or the decoder's int16 PCM (half
+        the PCIe bytes; widened on the device with at_pcm16_to_f32, bufs from alloc_bufs(..., pcm16=True)).  Chunks are
+        copied H2D on a copy stream while the mel kernel works on the previous chunk; tokens (int64) and centroids are
+        copied back into the pinned host tensors bufs["tokens_host"], bufs["centroids_host"].  Blocks until they are
+        there."""
+        import torch
+
+        B = wave_host.shape[0]
+        main = torch.cuda.current_stream()
+        bad = torch.zeros(B, dtype=torch.int32, device="cuda")
+        self._ingest(wave_host, bufs, bad, chunk_clips, main)
+        tok, cents = self.cluster_and_tokenize(bufs["spec"], bufs["l2"], row_offset, n_total, None, bufs.get("tokens"))
         bufs["tokens_host"].copy_(tok, non_blocking=True)
         bufs["centroids_host"].copy_(cents, non_blocking=True)
         bufs["bad_host"].copy_(bad, non_blocking=True)
         main.synchronize()
         return bufs["tokens_host"], bufs["centroids_host"], bufs["bad_host"]
+
+    def run_host_stream(self, batches, bufs_pair, chunk_clips=296, row_offset=0, n_total=None):
+        """The same end-to-end step for a SEQUENCE of host batches (each one a full k-means + tokenize job, e.g. one split
+        or one day's clips): the H2D copy and the mel transform of batch i+1 run on side streams while batch i goes through
+        k-means and tokenization, so in steady state a step costs max(PCIe time, device time) instead of their sum.
+
+        batches: iterable of pinned (B, L) tensors (fp32 or int16 PCM), same shape throughout; bufs_pair: two buffer sets
+        from alloc_bufs(B, L, host=True, ...).  Yields (tokens_host, centroids_host, bad_host) per batch, in order; the
+        pinned tensors belong to the buffer set and are overwritten two batches later."""
+        import torch
+
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_mel_stream"):
+            self._mel_stream = torch.cuda.Stream()
+        mel_stream = self._mel_stream
+        it = iter(batches)
+        pend = None    # (bufs, bad, event) of the batch whose ingest is in flight
+
+        def start(batch, slot):
+            bufs = bufs_pair[slot]
+            bad = torch.zeros(batch.shape[0], dtype=torch.int32, device="cuda")
+            # everything queued on the main stream so far is older than this batch: the previous occupant of the slot has
+            # been read back (its result event was synchronised before it was yielded), `bad` has been zeroed
+            mel_stream.wait_stream(main)
+            return bufs, bad, self._ingest(batch, bufs, bad, chunk_clips, mel_stream)
+
+        slot = 0
+        first = next(it, None)
+        if first is None:
+            return
+        pend = start(first, slot)
+        while pend is not None:
+            bufs, bad, ev = pend
+            nxt = next(it, None)
+            slot ^= 1
+            pend = start(nxt, slot) if nxt is not None else None
+            main.wait_event(ev)
+            tok, cents = self.cluster_and_tokenize(bufs["spec"], bufs["l2"], row_offset, n_total, None, bufs.get("tokens"))
+            bufs["tokens_host"].copy_(tok, non_blocking=True)
+            bufs["centroids_host"].copy_(cents, non_blocking=True)
+            bufs["bad_host"].copy_(bad, non_blocking=True)
+            bufs["result_event"] = torch.cuda.Event()
+            bufs["result_event"].record(main)
+            bufs["result_event"].synchronize()
+            yield bufs["tokens_host"], bufs["centroids_host"], bufs["bad_host"]
 
     def stream_tokenize(self, host_chunks, centroids, chunk_clips=296):
         """Spectrogram -> tokens for a stream of HOST chunks with fixed centroids (the unbalanced-train shape: far more

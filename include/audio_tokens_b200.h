@@ -185,6 +185,36 @@ int at_kmeans_set_incremental(at_kmeans *km, int on);
  * of the look-alike goes through at_kmeans_begin.) */
 int at_kmeans_invalidate(at_kmeans *km);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange step of a Lloyd iteration over peer memory (one process per GPU, one node).
+ * The reference has no counterpart (faiss.Kmeans(gpu=True) shards inside one process); in this library the per-iteration
+ * exchange is the sum over ranks of the exact int64 accumulator.  An at_peer owns a window of
+ * device memory that the other ranks map through CUDA IPC; at_peer_reduce is ONE kernel that signals, waits for every
+ * rank's window and adds them up over NVLink in rank order (integers: the total is identical on every rank and for every
+ * rank count).  Protocol per iteration:
+ *     at_kmeans_accumulate(km, x, n, 0, algo, at_peer_local_buffer(peer), labels, stream);
+ *     at_peer_reduce(peer, stream);
+ *     at_kmeans_finalize(km, at_peer_total(peer), n_total, stats, stream);
+ * Set-up (host, once): every rank creates its at_peer, exports a 64-byte handle, the caller exchanges the handles (any
+ * transport: torch.distributed all_gather in the Python layer), every rank imports the others' and calls at_peer_connect
+ * after a barrier.  A missing rank makes the kernel give up after ~4 s of SM clock; at_peer_status then reports it.
+ * ---------------------------------------------------------------------------------------------- */
+#define AT_PEER_MAX 16
+#define AT_PEER_HANDLE_BYTES 64
+typedef struct at_peer at_peer;
+int at_peer_create(int rank, int world, int64_t words, at_peer **peer);
+int at_peer_export(const at_peer *peer, void *handle64);
+int at_peer_import(at_peer *peer, int peer_rank, const void *handle64);
+int at_peer_connect(at_peer *peer);
+int at_peer_destroy(at_peer *peer);
+/* Device pointer of the window buffer the NEXT at_peer_reduce will read (words int64). */
+int64_t *at_peer_local_buffer(at_peer *peer);
+/* Device pointer of the all-rank total written by the last at_peer_reduce (words int64). */
+const int64_t *at_peer_total(const at_peer *peer);
+int at_peer_reduce(at_peer *peer, void *stream);
+/* Synchronises the stream and returns AT_ERR_CUDA if a wait timed out since creation. */
+int at_peer_status(at_peer *peer, void *stream);
+
 /* faiss::rand_perm(perm, n, seed) (faiss/utils/random.cpp): forward Fisher-Yates driven by std::mt19937(seed),
  * i2 = i + mt() % (n - i).  HOST function, HOST pointer.  Used for FAISS's training-set subsample (seed 1234)
  * and random-point initialisation (seed 1235). */
