@@ -19,10 +19,10 @@ from .mel import MelPlan
 
 class HotPath:
     def __init__(self, sample_rate=22050, n_fft=1024, hop_length=512, n_mels=64, normalize=True, vocab_size=1024,
-                 niter=20, group=False, seed=1234, algo=_lib.ALGO_AUTO):
+                 niter=20, group=False, seed=1234, algo=_lib.ALGO_AUTO, reduce="auto"):
         self.plan = MelPlan(sample_rate, n_fft, hop_length, n_mels, normalize)
         self.k, self.d, self.niter, self.group, self.seed = vocab_size, n_mels, niter, group, seed
-        self.trainer = LloydTrainer(n_mels, vocab_size, group=group, algo=algo)
+        self.trainer = LloydTrainer(n_mels, vocab_size, group=group, algo=algo, reduce=reduce)
         self.index = FlatL2(n_mels)
         self.algo = algo
         self._init_rows = {}
@@ -255,15 +255,18 @@ class HotPath:
             T = self.plan.num_frames(st["L"])
             yield st["tok_h"][psb, :pn * T], st["bad_h"][psb, :pn]
 
-    def alloc_bufs(self, B, L, host=False, chunk_clips=296, pcm16=False):
+    def alloc_bufs(self, B, L, host=False, chunk_clips=296, pcm16=False, device_outputs=True):
+        """device_outputs=False leaves out spec / l2 / tokens (the caller plugs in buffers it already owns)."""
         import torch
 
         T = self.plan.num_frames(L)
-        bufs = dict(
-            spec=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
-            l2=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
-            tokens=torch.empty(B * T, dtype=torch.int64, device="cuda"),
-        )
+        bufs = {}
+        if device_outputs:
+            bufs.update(
+                spec=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
+                l2=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
+                tokens=torch.empty(B * T, dtype=torch.int64, device="cuda"),
+            )
         if host:
             bufs.update(
                 stage=torch.empty((2, chunk_clips, L), dtype=torch.float32, device="cuda"),

