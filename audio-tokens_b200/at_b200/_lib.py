@@ -49,6 +49,7 @@ PROTOTYPES = {
     "at_kmeans_get_centroids": (c_int, [c_ptr, c_ptr, c_ptr]),
     "at_absmax": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "at_kmeans_begin": (c_int, [c_ptr, c_f32, c_i64]),
+    "at_kmeans_begin_on": (c_int, [c_ptr, c_f32, c_i64, c_ptr]),
     "at_kmeans_accum_words": (c_i64, [c_ptr]),
     "at_kmeans_accumulate": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "at_kmeans_finalize": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),

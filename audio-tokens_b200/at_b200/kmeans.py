@@ -187,7 +187,8 @@ class LloydTrainer:
         elif n_total is None:
             n_total = x_local.shape[0]
         self.n_total = int(n_total)
-        _lib.check(self.lib.at_kmeans_begin(self.h, float(self._absmax.item()), self.n_total))
+        # (.item() waits for the current stream only; the stream-ordered begin keeps other streams' work in flight)
+        _lib.check(self.lib.at_kmeans_begin_on(self.h, float(self._absmax.item()), self.n_total, _lib.stream_ptr()))
 
     @staticmethod
     def _key(x):

@@ -735,8 +735,13 @@ static int ceil_log2_d(double v) {
     return e;      // v < 2^e
 }
 
-int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total) {
+__global__ void k_set_float(float *p, float v) { *p = v; }
+
+// Stream-ordered form: nothing here waits for the device, so a caller can keep copies / kernels of the NEXT training set in
+// flight on other streams while this one starts (HotPath.run_host_stream).
+int at_kmeans_begin_on(at_kmeans *km, float max_abs, int64_t n_total, void *stream) {
     AT_REQUIRE(km && n_total > 0 && max_abs >= 0 && isfinite(max_abs), "at_kmeans_begin: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
     int nb = ceil_log2_d((double)n_total + 1.0);
     int mb = ceil_log2_d((double)max_abs);
     km->e_sum = 61 - nb - mb;  // |x * 2^e| < 2^(61-nb); n_total rows sum below 2^61
@@ -760,16 +765,24 @@ int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total) {
             if (e < -60) e = -60;
             sx = ldexpf(1.0f, e);
         }
-        AT_CUDA_OK(cudaDeviceSynchronize());
         if (!km->rows_sx) AT_CUDA_OK(cudaMalloc(&km->rows_sx, sizeof(float)));
-        AT_CUDA_OK(cudaMemcpy(km->rows_sx, &sx, sizeof(float), cudaMemcpyHostToDevice));
+        k_set_float<<<1, 1, 0, st>>>(km->rows_sx, sx);
+        AT_LAUNCH_OK();
         km->index->ext_sx = km->rows_sx;
         if (km->index->k > 0 && assign_tc_supported(km->index)) {
-            int rc = index_refresh(km->index, nullptr);
+            int rc = index_refresh(km->index, st);
             if (rc != AT_OK) return rc;
-            AT_CUDA_OK(cudaDeviceSynchronize());
         }
     }
+    return AT_OK;
+}
+
+int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total) {
+    // legacy form: ordered against everything on the device (callers on the legacy default stream)
+    AT_CUDA_OK(cudaDeviceSynchronize());
+    int rc = at_kmeans_begin_on(km, max_abs, n_total, nullptr);
+    if (rc != AT_OK) return rc;
+    AT_CUDA_OK(cudaDeviceSynchronize());
     return AT_OK;
 }
 

@@ -234,7 +234,7 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------------------- parity (outside the timed region)
-def parity_block(hp, bufs, wave, args, world, oracle_ok):
+def parity_block(hp, bufs, wave, args, world, cents, oracle_ok):
     """What the timed step produced, checked: (1) the tensor search's tokens against the exact fp32 kernel on EVERY local
     frame (mismatches are only tolerated inside north_star's 1e-6 near-tie carve-out, evaluated in fp64); (2) the same tokens
     against the CPU oracle's scalar FAISS formula on an evenly spread sample; (3) one teacher-forced Lloyd step at the
@@ -248,8 +248,7 @@ def parity_block(hp, bufs, wave, args, world, oracle_ok):
     out = {}
     spec_rows = bufs["spec"].reshape(-1, N_MELS)
     n = spec_rows.shape[0]
-    cents = row_l2norm(hp.trainer.get_centroids())
-    tok = bufs["tokens"]
+    tok = bufs["tokens"]   # written by the last timed step with `cents` (the step's unit-norm centroids)
     ix = FlatL2(N_MELS)
     ix.set_centroids(cents)
     lab_ex, _ = ix.search(spec_rows, l2norm_rows=True, algo=_lib.ALGO_SIMT, want_dist=False, labels_dtype=torch.int64)
@@ -562,6 +561,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    last = {}
+
     def step(ev=None):
         if ev:
             ev[0].record()
@@ -572,6 +573,7 @@ def run_b200(args):
         from at_b200 import row_l2norm
 
         cents = row_l2norm(cents)
+        last["centroids"] = cents
         if ev:
             ev[2].record()
         hp.tokenize(spec.reshape(-1, N_MELS), cents, bufs["tokens"])
@@ -636,7 +638,7 @@ def run_b200(args):
     parity = None
     if not args.no_parity:
         try:
-            parity = parity_block(hp, bufs, wave, args, world, oracle_ok=(world == 1))
+            parity = parity_block(hp, bufs, wave, args, world, last["centroids"], oracle_ok=(world == 1))
         except Exception as ex:  # report, never fake
             parity = {"error": repr(ex)[:300]}
 

@@ -159,6 +159,9 @@ int at_kmeans_get_centroids(const at_kmeans *km, float *out, void *stream);
  * ALL ranks' rows (at_absmax computes the local one). */
 int at_absmax(const float *x, int64_t n_elems, float *out_dev, void *stream);
 int at_kmeans_begin(at_kmeans *km, float max_abs, int64_t n_total);
+/* Same, ordered on `stream` only (at_kmeans_begin synchronises the whole device before and after): lets copies / kernels
+ * of the next training set stay in flight on other streams. */
+int at_kmeans_begin_on(at_kmeans *km, float max_abs, int64_t n_total, void *stream);
 /* Number of int64 words in the accumulator buffer: k*d sums + k counts + 1 (the sum of |x_i|^2, from which finalize
  * derives the objective). */
 int64_t at_kmeans_accum_words(const at_kmeans *km);
