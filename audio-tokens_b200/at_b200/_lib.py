@@ -72,6 +72,9 @@ PROTOTYPES = {
     "at_resample_mono": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_ptr, c_ptr]),
     "at_resample_mono_batch": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr]),
     "at_bincount": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "at_tokens_collate": (c_int, [c_ptr, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "at_tokens_multihot": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),
+    "at_tokens_batch_max_len": (c_int, [c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
     "at_synth_clips": (c_int, [ctypes.c_uint32, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "at_rand_perm_host": (c_int, [c_ptr, c_i64, c_i64]),
 }

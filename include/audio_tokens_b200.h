@@ -253,6 +253,23 @@ int at_resample_mono_batch(at_resample_plan *plan, const float *wave, int channe
 int at_bincount(const int32_t *labels, int64_t n, int k, int64_t *counts, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Token consumer (the step after the path): batch assembly of TokenizedSpecDataset.__getitem__ + collate_fn
+ * (datasets/tokenized_spec_dataset.py:52-76, datasets/data_loader_creator.py:17-34) from a device-resident token store.
+ * tokens: flat int32 / int64 array (token_bytes 4 / 8) of all clips, clip c at [offsets[c], offsets[c+1]); idx[B]: the clips
+ * of the batch.  out (B, t_max) int64 = pad_sequence(..., batch_first=True, padding_value=0); mask (B, t_max) float (may
+ * be NULL): 1 on tokens / 0 on padding, or all ones when mask_all_ones != 0 -- which is what the reference's collate_fn
+ * produces, because it builds the masks from the already padded matrix (:70-74).  Device pointers.
+ * ---------------------------------------------------------------------------------------------- */
+int at_tokens_collate(const void *tokens, int token_bytes, const int64_t *offsets, const int64_t *idx, int B, int t_max,
+                      int mask_all_ones, int64_t *out, float *mask, void *stream);
+/* labels (B, num_classes) float: multi-hot of label_ids[label_offsets[c] .. label_offsets[c+1]) for each clip of the batch
+ * (__getitem__'s labels[label_indices] = 1.0 + collate_fn's torch.stack). */
+int at_tokens_multihot(const int32_t *label_ids, const int64_t *label_offsets, const int64_t *idx, int B, int num_classes,
+                       float *labels, void *stream);
+/* Longest sequence of the batch -> device int32 (sizes the padded matrix). */
+int at_tokens_batch_max_len(const int64_t *offsets, const int64_t *idx, int B, int32_t *out_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Synthetic clips (bit-identical to oracle/synth_ref.py given the same sine table)
  * ---------------------------------------------------------------------------------------------- */
 int at_synth_clips(uint32_t seed, int64_t first_index, int64_t count, int64_t n_samples,
