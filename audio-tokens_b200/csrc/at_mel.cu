@@ -132,6 +132,45 @@ __device__ __forceinline__ void fft_dif(float *re, float *im) {
     }
 }
 
+// Packed form of the same transform: a register pair holds (real, imaginary) of one point, so the butterfly's two complex
+// additions are two FADD2 (fp32x2, sm_100) instead of four FADD, and the window multiply of a frame pair is one FMUL2; the
+// twiddle products stay scalar on the halves of the pairs.  Same arithmetic, same rounding, fewer issue slots -- the kernel
+// is bound by instruction issue, not by the FMA lanes.
+typedef float2 f2;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
+template <int N>
+__device__ __forceinline__ void fft_dif_ri(f2 *z) {
+    constexpr float R = 0.70710678118654752440f;
+#pragma unroll
+    for (int h = N / 2; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int b = 0; b < N; b += 2 * h) {
+#pragma unroll
+            for (int j = 0; j < h; j++) {
+                const int m = j * (16 / h);  // W_{2h}^j = W_32^m
+                const f2 a = z[b + j], c2 = z[b + j + h];
+                z[b + j] = add2(a, c2);
+                const f2 t = sub2(a, c2);
+                const float tr = t.x, ti = t.y;
+                if (m == 0) {
+                    z[b + j + h] = t;
+                } else if (m == 8) {  // -i
+                    z[b + j + h] = make_float2(ti, -tr);
+                } else if (m == 4) {  // (1 - i)/sqrt2
+                    z[b + j + h] = make_float2((tr + ti) * R, (ti - tr) * R);
+                } else if (m == 12) {  // (-1 - i)/sqrt2
+                    z[b + j + h] = make_float2((ti - tr) * R, -(tr + ti) * R);
+                } else {  // (tr + i ti)(c - i s)
+                    const float c = c32(m), s = s32(m);
+                    z[b + j + h] = make_float2(fmaf(tr, c, ti * s), fmaf(ti, c, -(tr * s)));
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ int64_t reflect_index(int64_t s, int64_t L) {
     if (s < 0) s = -s;
     if (s >= L) s = 2 * (L - 1) - s;
@@ -309,34 +348,24 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
             stage_phase ^= 1;
         }
         // ------------------------------------------------------------ phase A: FFT -> power tile
+        // z[p] = (real, imaginary) = (frame a, frame b) samples of point p: packed fp32x2 additions (fft_dif_ri)
         {
-            float zr[32], zi[32];
+            f2 z[32];
             const int64_t tj = t0 + (int64_t)warp * FR;
             // fast path (one frame pair per job, hop = n_fft / 2, both frames interior and staged): the second frame's samples
-            // are the first frame's shifted by half a window, so the pair needs 1.5 n_fft staged samples, not 2, and each window
-            // value is fetched once for both frames
+            // are the first frame's shifted by half a window, so the pair needs 1.5 n_fft staged samples, not 2, and each
+            // window value is fetched once for both frames (one FMUL2 per point)
             bool fast_pair = false;
             if (G == 1 && hop == NF / 2 && cur.staged) {
                 const int64_t start = tj * hop - NF / 2;
                 fast_pair = tj + 1 < T && start >= 0 && start + hop + NF <= L;
                 if (fast_pair) {
                     const float *sp = s_stage + (start - cur.lo) + lane;
-                    float wv[N2 / 2];
 #pragma unroll
-                    for (int n2 = 0; n2 < N2 / 2; n2++) {   // first half of the window: frame a only
-                        wv[n2] = s_win[lane + 32 * n2];
-                        zr[n2] = sp[32 * n2] * wv[n2];
-                    }
-#pragma unroll
-                    for (int n2 = N2 / 2; n2 < N2; n2++) {  // shared samples: a's second half, b's first half
-                        const float r = sp[32 * n2];
+                    for (int n2 = 0; n2 < N2; n2++) {
                         const float w = s_win[lane + 32 * n2];
-                        zr[n2] = r * w;
-                        zi[n2 - N2 / 2] = r * wv[n2 - N2 / 2];
-                        wv[n2 - N2 / 2] = w;
+                        z[n2] = __fmul2_rn(make_float2(sp[32 * n2], sp[32 * (n2 + N2 / 2)]), make_float2(w, w));
                     }
-#pragma unroll
-                    for (int n2 = N2; n2 < N2 + N2 / 2; n2++) zi[n2 - N2 / 2] = sp[32 * n2] * wv[n2 - N2];
                 }
             }
 #pragma unroll
@@ -345,66 +374,71 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
                     const int64_t f = tj + 2 * g + half;
-                    float *dstv = half ? zi : zr;
                     const int64_t start = f * hop - NF / 2;
+                    float v[N2];
                     if (f < T && start >= 0 && start + NF <= L) {
                         if (cur.staged) {
                             const float *sp = s_stage + (start - cur.lo) + lane;
 #pragma unroll
-                            for (int n2 = 0; n2 < N2; n2++) dstv[g * N2 + n2] = sp[32 * n2] * s_win[lane + 32 * n2];
+                            for (int n2 = 0; n2 < N2; n2++) v[n2] = sp[32 * n2] * s_win[lane + 32 * n2];
                         } else {
 #pragma unroll
-                            for (int n2 = 0; n2 < N2; n2++)
-                                dstv[g * N2 + n2] = __ldg(x + start + lane + 32 * n2) * s_win[lane + 32 * n2];
+                            for (int n2 = 0; n2 < N2; n2++) v[n2] = __ldg(x + start + lane + 32 * n2) * s_win[lane + 32 * n2];
                         }
                     } else if (f < T) {
 #pragma unroll
                         for (int n2 = 0; n2 < N2; n2++)
-                            dstv[g * N2 + n2] =
-                                __ldg(x + reflect_index(start + lane + 32 * n2, L)) * s_win[lane + 32 * n2];
+                            v[n2] = __ldg(x + reflect_index(start + lane + 32 * n2, L)) * s_win[lane + 32 * n2];
                     } else {
 #pragma unroll
-                        for (int n2 = 0; n2 < N2; n2++) dstv[g * N2 + n2] = 0.f;
+                        for (int n2 = 0; n2 < N2; n2++) v[n2] = 0.f;
+                    }
+#pragma unroll
+                    for (int n2 = 0; n2 < N2; n2++) {
+                        if (half == 0) z[g * N2 + n2].x = v[n2];
+                        else z[g * N2 + n2].y = v[n2];
                     }
                 }
             }
             // pass 1: N2-point FFTs over n2, then twiddle W_NF^(n1*k2)
 #pragma unroll
-            for (int g = 0; g < G; g++) fft_dif<N2>(zr + g * N2, zi + g * N2);
+            for (int g = 0; g < G; g++) fft_dif_ri<N2>(z + g * N2);
 #pragma unroll
             for (int g = 0; g < G; g++) {
 #pragma unroll
                 for (int p = 0; p < N2; p++) {
                     const int kk = brev(p, C::LOG2N2);
                     const float2 w = s_tw[kk * 32 + lane];
-                    const float a = zr[g * N2 + p], b = zi[g * N2 + p];
-                    zr[g * N2 + p] = fmaf(a, w.x, -(b * w.y));
-                    zi[g * N2 + p] = fmaf(a, w.y, b * w.x);
+                    const float a = z[g * N2 + p].x, b = z[g * N2 + p].y;
+                    z[g * N2 + p] = make_float2(fmaf(a, w.x, -(b * w.y)), fmaf(a, w.y, b * w.x));
                 }
             }
             // 32x32 transpose through the warp's exchange tile, real parts then imaginary parts
 #pragma unroll
             for (int part = 0; part < 2; part++) {
-                float *z = part ? zi : zr;
 #pragma unroll
                 for (int g = 0; g < G; g++)
 #pragma unroll
-                    for (int p = 0; p < N2; p++) xch[(g * N2 + brev(p, C::LOG2N2)) * XCH_STRIDE + lane] = z[g * N2 + p];
+                    for (int p = 0; p < N2; p++)
+                        xch[(g * N2 + brev(p, C::LOG2N2)) * XCH_STRIDE + lane] = part ? z[g * N2 + p].y : z[g * N2 + p].x;
                 __syncwarp();
 #pragma unroll
-                for (int n1 = 0; n1 < 32; n1++) z[n1] = xch[lane * XCH_STRIDE + n1];
+                for (int n1 = 0; n1 < 32; n1++) {
+                    if (part) z[n1].y = xch[lane * XCH_STRIDE + n1];
+                    else z[n1].x = xch[lane * XCH_STRIDE + n1];
+                }
                 __syncwarp();
             }
             // pass 2: 32-point FFT over n1; position p holds k1 = brev5(p); Z[N2*k1 + k2]
-            fft_dif<32>(zr, zi);
+            fft_dif_ri<32>(z);
             // separate the two real frames and store |.|^2 (the 1/4 lives in the mel weights)
             float *pa = ptile + (size_t)(warp * FR + 2 * g2) * PS;
             float *pb = pa + PS;
 #pragma unroll
             for (int k1 = 0; k1 < 16; k1++) {
-                const float Zr = zr[brev(k1, 5)], Zi = zi[brev(k1, 5)];
-                const float qr = k2 == 0 ? zr[brev((32 - k1) & 31, 5)] : zr[brev(31 - k1, 5)];
-                const float qi = k2 == 0 ? zi[brev((32 - k1) & 31, 5)] : zi[brev(31 - k1, 5)];
+                const float Zr = z[brev(k1, 5)].x, Zi = z[brev(k1, 5)].y;
+                const float qr = k2 == 0 ? z[brev((32 - k1) & 31, 5)].x : z[brev(31 - k1, 5)].x;
+                const float qi = k2 == 0 ? z[brev((32 - k1) & 31, 5)].y : z[brev(31 - k1, 5)].y;
                 const float pr = __shfl_sync(0xffffffffu, qr, partner);
                 const float pi = __shfl_sync(0xffffffffu, qi, partner);
                 const float ar = Zr + pr, ai = Zi - pi, br = Zi + pi, bi = pr - Zr;
@@ -412,7 +446,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 pb[N2 * k1 + k2] = fmaf(br, br, bi * bi);
             }
             if (k2 == 0) {  // Nyquist bin: Z[NF/2] is its own partner
-                const float Zr = zr[brev(16, 5)], Zi = zi[brev(16, 5)];
+                const float Zr = z[brev(16, 5)].x, Zi = z[brev(16, 5)].y;
                 pa[NF / 2] = 4.f * Zr * Zr;
                 pb[NF / 2] = 4.f * Zi * Zi;
             }
