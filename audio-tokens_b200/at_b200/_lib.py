@@ -55,6 +55,7 @@ PROTOTYPES = {
     "at_kmeans_finalize": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "at_kmeans_set_incremental": (c_int, [c_ptr, c_int]),
     "at_kmeans_invalidate": (c_int, [c_ptr]),
+    "at_index_search_trained_rows": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "at_peer_create": (c_int, [c_int, c_int, c_i64, c_ptr]),
     "at_peer_export": (c_int, [c_ptr, c_ptr]),
     "at_peer_import": (c_int, [c_ptr, c_int, c_ptr]),

@@ -66,6 +66,27 @@ class FlatL2:
         return labels, dist
 
 
+    def search_trained_rows(self, trainer, x, l2norm_rows: bool = False, want_dist: bool = False, labels_dtype=None,
+                            labels=None, dist=None):
+        """search(x, 1) for the rows ``trainer`` (a LloydTrainer) was just trained on, re-using the operand image its Lloyd
+        iterations built (at_index_search_trained_rows).  Same results as search(..., algo=ALGO_TENSOR)."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == self.d and x.is_contiguous()
+        n = x.shape[0]
+        labels_dtype = labels_dtype or (labels.dtype if labels is not None else torch.int32)
+        if labels is None:
+            labels = torch.empty(n, dtype=labels_dtype, device=x.device)
+        if want_dist and dist is None:
+            dist = torch.empty(n, dtype=torch.float32, device=x.device)
+        l32 = labels if labels_dtype == torch.int32 else None
+        l64 = labels if labels_dtype == torch.int64 else None
+        _lib.check(self.lib.at_index_search_trained_rows(self.h, trainer.h, _lib.ptr(x), n, int(l2norm_rows), _lib.ptr(l32),
+                                                         _lib.ptr(l64), _lib.ptr(dist if want_dist else None),
+                                                         _lib.stream_ptr()))
+        return labels, dist
+
+
 class IndexFlatL2:
     """faiss.IndexFlatL2(d) subset: add / reset / search(x, 1) / ntotal, numpy in, numpy out
     ((n, 1) float32 distances, (n, 1) int64 labels -- spec_tokenizer.py:77-78 squeezes axis 1)."""

@@ -59,10 +59,19 @@ class HotPath:
             self.trainer.step(l2_rows, None if stats is None else stats[it])
         return self.trainer.get_centroids()
 
-    def tokenize(self, spec_rows, centroids, tokens=None):
+    def tokenize(self, spec_rows, centroids, tokens=None, trained_rows: bool = False):
+        """Nearest-centroid tokens of the (un-normalised) spectrogram rows.  trained_rows=True: these are the rows the trainer
+        has just clustered (their L2-normalised copy), so the fp16 operand image of the Lloyd iterations is re-used instead
+        of being rebuilt from the fp32 rows (at_index_search_trained_rows)."""
         import torch
 
         self.index.set_centroids(centroids)
+        if (trained_rows and self.algo != _lib.ALGO_SIMT and self.d == 64 and self.k >= 64
+                and getattr(self.trainer, "_rows_key", None) is not None
+                and self.trainer._rows_key[1][0] == spec_rows.shape[0]):
+            lab, _ = self.index.search_trained_rows(self.trainer, spec_rows, l2norm_rows=True, labels_dtype=torch.int64,
+                                                    labels=tokens)
+            return lab
         lab, _ = self.index.search(spec_rows, l2norm_rows=True, algo=self.algo, want_dist=False,
                                    labels_dtype=torch.int64, labels=tokens)
         return lab
@@ -74,7 +83,7 @@ class HotPath:
 
         cents = self.kmeans(l2.reshape(-1, self.d), row_offset, n_total, stats)
         cents = row_l2norm(cents)  # ClusterCreator saves normalize_vectors(kmeans.centroids) (cluster_creator.py:58-61)
-        tok = self.tokenize(spec.reshape(-1, self.d), cents, tokens)
+        tok = self.tokenize(spec.reshape(-1, self.d), cents, tokens, trained_rows=True)   # l2 is spec's normalised copy
         return tok, cents
 
     def run_device(self, wave, bufs=None, row_offset=0, n_total=None, stats=None):

@@ -892,6 +892,25 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     return AT_OK;
 }
 
+int at_index_search_trained_rows(at_index *ix, at_kmeans *km, const float *x, int64_t n, int l2norm_rows, int32_t *labels32,
+                                 int64_t *labels64, float *dist, void *stream) {
+    AT_REQUIRE(ix && km && x && n > 0, "at_index_search_trained_rows: bad arguments");
+    AT_REQUIRE(ix->k > 0 && assign_tc_supported(ix), "at_index_search_trained_rows: needs d == 64 and 16 <= k <= 65536");
+    AT_REQUIRE(km->rows_valid && km->rows.n == n && km->rows_sx && km->d == ix->d,
+               "at_index_search_trained_rows: the k-means object holds no operand image of %lld rows", (long long)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the image carries its own scale: re-derive this index's operands for it, search, and put the index back
+    ix->ext_sx = km->rows_sx;
+    int rc = index_refresh(ix, st);
+    if (rc == AT_OK) {
+        ProfScope prof(PROF_SEARCH, st);
+        rc = assign_tc_search(ix, x, n, l2norm_rows, labels32, labels64, dist, 1, &km->rows, st);
+    }
+    ix->ext_sx = nullptr;
+    const int rc2 = index_refresh(ix, st);
+    return rc != AT_OK ? rc : rc2;
+}
+
 int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, float *stats, void *stream) {
     AT_REQUIRE(km && accum && n_total > 0, "at_kmeans_finalize: bad arguments");
     AT_REQUIRE(km->begun, "at_kmeans_finalize: call at_kmeans_begin first");

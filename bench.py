@@ -576,7 +576,7 @@ def run_b200(args):
         last["centroids"] = cents
         if ev:
             ev[2].record()
-        hp.tokenize(spec.reshape(-1, N_MELS), cents, bufs["tokens"])
+        hp.tokenize(spec.reshape(-1, N_MELS), cents, bufs["tokens"], trained_rows=True)   # the frames that were just clustered
         if ev:
             ev[3].record()
         return bad

@@ -180,6 +180,14 @@ int at_kmeans_finalize(at_kmeans *km, const int64_t *accum, int64_t n_total, flo
  * the old cluster's exact integer sum and added to the new one, which gives bit-identical sums to regrouping every
  * row.  on = 0 switches this off (every accumulate regroups every row); default on. */
 int at_kmeans_set_incremental(at_kmeans *km, int on);
+/* Tokenizing the rows that were just clustered (run_pipeline.py:12-13: ClusterCreator, then SpecTokenizer over the same
+ * spectrograms): search(x, 1) against `index`, re-using the fp16 operand image that at_kmeans_accumulate built for km's
+ * current training set instead of converting the rows a second time.  x must be those n rows -- either the very array km
+ * was trained on (l2norm_rows = 0), or the un-normalised rows it was derived from with normalize_vectors (l2norm_rows != 0:
+ * the candidate re-checks and exact scans normalise x canonically; a last-bit difference between the two normalisations is
+ * inside the certification threshold).  Same results as at_index_search(..., AT_ALGO_TENSOR, ...).  d == 64 only. */
+int at_index_search_trained_rows(at_index *index, at_kmeans *km, const float *x, int64_t n, int l2norm_rows,
+                                 int32_t *labels32, int64_t *labels64, float *dist, void *stream);
 /* CONTRACT of the two caches behind at_kmeans_accumulate (the fp16 operand image of the rows, and the incremental
  * update's previous labels and local sums): they are keyed on (x pointer, n_local) only, so the CONTENTS of x must not
  * change between at_kmeans_begin and the last accumulate of that training set.  A caller that re-uses a buffer for new

@@ -159,7 +159,11 @@ def test_launcher_runs_the_whole_pipeline(tmp_path, monkeypatch):
         return _wave(y), (44100 if y == "clip0006" else SR)
 
     monkeypatch.setattr(torchaudio, "load", fake_load)
-    saved_path, saved_argv, saved_mods = list(sys.path), list(sys.argv), dict(sys.modules)
+    saved_path, saved_argv = list(sys.path), list(sys.argv)
+    # a fresh interpreter as far as the checkout's module names are concerned (other tests import this repo's
+    # ``processors`` package directly); put everything back afterwards
+    ours = {m: sys.modules.pop(m) for m in list(sys.modules)
+            if m == "audio_tokens_config" or m == "processors" or m.startswith("processors.")}
     monkeypatch.chdir(ck)
     try:
         run_pipeline.main(["--reference", ck])
@@ -168,8 +172,9 @@ def test_launcher_runs_the_whole_pipeline(tmp_path, monkeypatch):
         sys.path[:] = saved_path
         sys.argv[:] = saved_argv
         for m in list(sys.modules):
-            if m not in saved_mods and (m == "audio_tokens_config" or m.startswith("processors")):
+            if m == "audio_tokens_config" or m == "processors" or m.startswith("processors."):
                 del sys.modules[m]
+        sys.modules.update(ours)
 
     # the checkout's trainer ran last, with the checkout's config
     tr = json.load(open(os.path.join(ck, "output", "trainer.json")))

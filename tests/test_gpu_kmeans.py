@@ -375,3 +375,32 @@ def test_lloyd_trainer_notices_new_rows_at_the_same_address():
     buf.copy_(b)                       # same pointer, same shape, new contents
     got = one_step(tr, buf)
     assert torch.equal(got, want)
+
+
+def test_search_reusing_the_trainers_row_image_equals_the_plain_search():
+    """Tokenizing the rows that were just clustered (at_index_search_trained_rows) = the ordinary search of the
+    un-normalised rows with l2norm_rows, tensor and exact kernels alike."""
+    import torch
+    from at_b200 import FlatL2, LloydTrainer, _lib, row_l2norm
+
+    spec, l2 = _frames(120)                      # 120 * 87 = 10,440 rows
+    k = 256
+    tr = LloydTrainer(64, k, algo=_lib.ALGO_TENSOR)
+    tr.begin(l2)
+    tr.set_centroids(l2[torch.randperm(l2.shape[0], device="cuda", generator=torch.Generator("cuda").manual_seed(3))[:k]].contiguous())
+    for _ in range(3):
+        tr.step(l2, None)
+    cents = row_l2norm(tr.get_centroids())
+    ix = FlatL2(64)
+    ix.set_centroids(cents)
+    a, da = ix.search_trained_rows(tr, spec, l2norm_rows=True, want_dist=True)
+    b, db = ix.search(spec, l2norm_rows=True, algo=_lib.ALGO_TENSOR)
+    c, dc = ix.search(spec, l2norm_rows=True, algo=_lib.ALGO_SIMT)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert torch.equal(da, db) and torch.equal(da, dc)
+    a2, _ = ix.search_trained_rows(tr, l2, l2norm_rows=False)          # the very array the trainer saw
+    assert torch.equal(a2, ix.search(l2, algo=_lib.ALGO_SIMT)[0])
+    d, _ = ix.search(spec, l2norm_rows=True, algo=_lib.ALGO_TENSOR)    # the index is back on its own scale afterwards
+    assert torch.equal(d, c)
+    with pytest.raises(RuntimeError):
+        ix.search_trained_rows(tr, spec[:100].contiguous(), l2norm_rows=True)
