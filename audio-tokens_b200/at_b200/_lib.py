@@ -34,6 +34,7 @@ PROTOTYPES = {
     "at_mel_forward_host": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     "at_amplitude_to_db": (c_int, [c_ptr, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr]),
     "at_row_l2norm": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "at_conv_expand": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr]),
     "at_index_create": (c_int, [c_int, c_ptr]),
     "at_index_destroy": (c_int, [c_ptr]),
     "at_index_set_centroids": (c_int, [c_ptr, c_ptr, c_int, c_ptr]),

@@ -120,15 +120,22 @@ class IndexFlatL2:
             raise NotImplementedError("only k=1 (the value the reference uses) is implemented")
         if self.ntotal == 0:
             raise RuntimeError("search on an empty index")
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        on_device = torch.is_tensor(x)   # rows already in HBM (e.g. the conv-expanded batch): no host round trip
+        if not on_device:
+            x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2 and x.shape[1] == self.d
         n = x.shape[0]
         D = np.empty((n, 1), dtype=np.float32)
         I = np.empty((n, 1), dtype=np.int64)
         for a in range(0, n, chunk_rows):
             b = min(n, a + chunk_rows)
-            xd = torch.from_numpy(x[a:b]).cuda()
-            lab, dist = self._ix.search(xd, l2norm_rows=l2norm_rows, labels_dtype=torch.int64)
+            xd = x[a:b].contiguous() if on_device else torch.from_numpy(x[a:b]).cuda()
+            fused = l2norm_rows and self.d <= 128   # the fused normalisation covers the register-resident kernels
+            if l2norm_rows and not fused:
+                from . import row_l2norm
+
+                xd = row_l2norm(xd)
+            lab, dist = self._ix.search(xd, l2norm_rows=fused, labels_dtype=torch.int64)
             I[a:b, 0] = lab.cpu().numpy()
             D[a:b, 0] = dist.cpu().numpy()
         return D, I

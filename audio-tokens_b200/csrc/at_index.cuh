@@ -124,5 +124,7 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
 int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, cudaStream_t st);
 void tc_rows_free(at_tc_rows *r);
 bool assign_tc_supported(const at_index *ix);
+// at_conv.cu: exact fp32 search for rows wider than 128 values (pre-normalised rows)
+int launch_assign_gemm(const at_index *ix, const float *x, int64_t n, int32_t *l32, int64_t *l64, float *dist, cudaStream_t st);
 
 }  // namespace at

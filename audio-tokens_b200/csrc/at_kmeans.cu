@@ -285,7 +285,7 @@ __global__ void k_place(const int32_t *__restrict__ labels, int64_t n, unsigned 
 // fixed point (x * 2^e_sum), flushing to sums[c] with 64-bit atomics whenever the cluster changes.
 // Delta form (items != nullptr): order[] indexes items[], an item is a row with bit 31 set when the row LEAVES the
 // cluster (its value is subtracted); the item count is 2 * *n_dev.
-template <int DPL>  // dims per lane = ceil(d / 32)
+template <int DPL, int U = 8>  // dims per lane = ceil(d / 32); rows fetched ahead per warp (fewer for wide rows: registers)
 __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x, int d,
                                                     const int32_t *__restrict__ order,
                                                     const int64_t *__restrict__ off, int k, int64_t n,
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(256) k_gather_sum(const float *__restrict__ x,
     for (int u = 0; u < DPL; u++) acc[u] = 0;
     long long sq = 0;   // sum of x^2 over this warp's rows (fixed point), the constant term of the objective
 
-    constexpr int U = 8;
     for (int64_t p = p0; p < p1; p += U) {
         int32_t rows[U];
         float v[U][DPL];
@@ -520,8 +519,12 @@ static int launch_simt(const at_index *ix, const float *x, int64_t n, int l2norm
     else if (ix->d <= 128)
         k_assign_simt<128><<<blocks, 128, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l2norm, l32, l64, dist);
     else {
-        set_error("search: d=%d > 128 is not covered by this build", ix->d);
-        return AT_ERR_UNSUPPORTED;
+        // wide rows (the use_convolution branch: d = n_mels * num_kernels): tiled exact fp32 kernel, rows pre-normalised
+        if (l2norm) {
+            set_error("search: l2norm_rows is fused for d <= 128 only; normalise wider rows with at_row_l2norm first (d=%d)", ix->d);
+            return AT_ERR_UNSUPPORTED;
+        }
+        return launch_assign_gemm(ix, x, n, l32, l64, dist, st);
     }
     AT_LAUNCH_OK();
     return AT_OK;
@@ -564,7 +567,7 @@ int at_row_l2norm(const float *x, int64_t n, int d, float *out, void *stream) {
 // ----------------------------------------------------------------------------------- index
 int at_index_create(int d, at_index **index) {
     AT_REQUIRE(index && d > 0, "at_index_create: bad arguments");
-    AT_REQUIRE(d <= 128, "at_index_create: d=%d > 128 is not covered by this build", d);
+    AT_REQUIRE(d <= 1024, "at_index_create: d=%d > 1024 is not covered by this build", d);
     int dev;
     AT_CUDA_OK(cudaGetDevice(&dev));
     at_index *ix = new (std::nothrow) at_index();
@@ -862,9 +865,18 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
         else if (dpl == 2)
             k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
                                                          lacc + kd + k, obj_scale);
-        else
+        else if (dpl <= 4)
             k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
                                                          lacc + kd + k, obj_scale);
+        else if (dpl <= 8)
+            k_gather_sum<8, 2><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
+                                                            lacc + kd + k, obj_scale);
+        else if (dpl <= 20)
+            k_gather_sum<20, 1><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
+                                                             lacc + kd + k, obj_scale);
+        else
+            k_gather_sum<32, 1><<<gblocks, 256, 0, st>>>(x, d, km->order, km->off, k, n_local, scale, lacc, nullptr, nullptr,
+                                                             lacc + kd + k, obj_scale);
         AT_LAUNCH_OK();
         AT_CUDA_OK(cudaMemcpyAsync(km->prev, labels, sizeof(int32_t) * (size_t)n_local, cudaMemcpyDeviceToDevice, st));
         km->prev_valid = true, km->prev_x = x, km->prev_n = n_local;
@@ -884,8 +896,14 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
             k_gather_sum<1><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
         else if (dpl == 2)
             k_gather_sum<2><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
-        else
+        else if (dpl <= 4)
             k_gather_sum<4><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
+        else if (dpl <= 8)
+            k_gather_sum<8, 2><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
+        else if (dpl <= 20)
+            k_gather_sum<20, 1><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
+        else
+            k_gather_sum<32, 1><<<gblocks, 256, 0, st>>>(x, d, km->d_order, km->off, k, 0, scale, lacc, km->d_row, km->d_count);
         AT_LAUNCH_OK();
     }
     AT_CUDA_OK(cudaMemcpyAsync(acc, lacc, sizeof(int64_t) * (size_t)(kd + k + 1), cudaMemcpyDeviceToDevice, st));

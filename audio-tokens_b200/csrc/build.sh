@@ -9,10 +9,10 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -ccbin /
        -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr -Xptxas -v ${AT_EXTRA_FLAGS:-})
 mkdir -p "$OBJ"
 pids=()
-for f in at_util at_kmeans at_mel at_assign_tc at_resample at_peer at_tokens; do
+for f in at_util at_kmeans at_mel at_assign_tc at_resample at_peer at_tokens at_conv; do
   ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$OBJ/$f.o" > "$OBJ/$f.log" 2>&1 || { cat "$OBJ/$f.log"; exit 1; } ) &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$OBJ"/at_util.o "$OBJ"/at_kmeans.o "$OBJ"/at_mel.o "$OBJ"/at_assign_tc.o "$OBJ"/at_resample.o "$OBJ"/at_peer.o "$OBJ"/at_tokens.o -lcudart
+"$NVCC" -shared -o "$OUT" "$OBJ"/at_util.o "$OBJ"/at_kmeans.o "$OBJ"/at_mel.o "$OBJ"/at_assign_tc.o "$OBJ"/at_resample.o "$OBJ"/at_peer.o "$OBJ"/at_tokens.o "$OBJ"/at_conv.o -lcudart
 echo "built $OUT"

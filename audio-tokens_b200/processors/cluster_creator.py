@@ -32,10 +32,13 @@ class ClusterCreator:
             raise RuntimeError("ClusterCreator (B200 build) needs a CUDA device; there is no CPU fallback")
         self.device = torch.device("cuda")
         if self.config.use_convolution:
-            raise NotImplementedError("use_convolution is outside the accelerated hot path (SURVEY.md section 8f)")
+            # same seeded default initialisation as the reference's nn.Conv1d (:28-34); applied by at_conv_expand
+            self.conv_weight, self.conv_bias = at_b200.make_conv_layer(self.config)
 
     def run(self):
         n_freq_bins = self.config.n_mels
+        if self.config.use_convolution:
+            n_freq_bins *= self.config.num_kernels
         self.logger.info("starting clustering")
         extra = {}
         mppc = getattr(self.config, "max_points_per_centroid", None)
@@ -44,7 +47,10 @@ class ClusterCreator:
         kmeans = faiss.Kmeans(n_freq_bins, self.config.vocab_size, niter=self.config.niter, verbose=True,
                               gpu=self.gpu, **extra)
         for i, batch in enumerate(self._batch_generator(self.config.clustering_batch_size)):
-            batch = at_b200.row_l2norm(torch.from_numpy(batch).to(self.device))  # normalize_vectors on the device
+            batch = torch.from_numpy(batch).to(self.device)
+            if self.config.use_convolution:
+                batch = self.apply_convolution(batch)
+            batch = at_b200.row_l2norm(batch)  # normalize_vectors on the device
             if i == 0:
                 kmeans.train(batch)
             else:
@@ -58,6 +64,13 @@ class ClusterCreator:
         """v / (||v|| + 1e-10) per row (reference :64-66), computed by at_row_l2norm."""
         v = torch.from_numpy(np.ascontiguousarray(vectors, dtype=np.float32)).to(self.device)
         return at_b200.row_l2norm(v).cpu().numpy()
+
+    def apply_convolution(self, time_slice_batch):
+        """(n, n_mels) -> (n, n_mels * num_kernels) like the reference (:68-81); CUDA tensor in, CUDA tensor out (numpy is
+        uploaded first)."""
+        if isinstance(time_slice_batch, np.ndarray) or not torch.is_tensor(time_slice_batch):
+            time_slice_batch = torch.from_numpy(np.ascontiguousarray(time_slice_batch, dtype=np.float32)).to(self.device)
+        return at_b200.conv_expand(time_slice_batch.contiguous(), self.conv_weight, self.conv_bias)
 
     def _files(self):
         spec_dir = Path(self.config.source_spec_path) / "train"

@@ -14,9 +14,20 @@ from at_b200 import _lib
 from at_b200.npyio import load_spec_batch
 
 
+def _set_seed(seed=42):
+    """utils/set_seed.py of the reference (the conv layer's default initialisation draws from torch's CPU generator)."""
+    import random
+
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+
+
 class SpecTokenizer:
     def __init__(self, config):
         self.config = config
+        _set_seed(self.config.random_seed)
         self.logger = logging.getLogger()
         if not torch.cuda.is_available():
             raise RuntimeError("SpecTokenizer (B200 build) needs a CUDA device; there is no CPU fallback")
@@ -27,7 +38,7 @@ class SpecTokenizer:
         self.index = self.load_centroid_index()
         self.token_counts = None
         if self.config.use_convolution:
-            raise NotImplementedError("use_convolution is outside the accelerated hot path (SURVEY.md section 8f)")
+            self.conv_weight, self.conv_bias = self.create_convolution_layer()
 
     def run(self):
         for split in ["train", "validation"]:
@@ -55,8 +66,13 @@ class SpecTokenizer:
         batch_data, lengths = load_spec_batch(batch_files)   # the reference's per-file np.load(f).T + concatenate
         if batch_data.size == 0:
             return []
-        # normalize_vectors + index.search(x, 1) in one kernel; int64 labels like faiss
-        _, tokens = self.index.search(batch_data, 1, l2norm_rows=True)
+        if self.config.use_convolution:
+            # conv expansion + normalize_vectors on the device, then the wide-row exact search
+            wide = at_b200.row_l2norm(self.apply_convolution(batch_data))
+            _, tokens = self.index.search(wide, 1)
+        else:
+            # normalize_vectors + index.search(x, 1) in one kernel; int64 labels like faiss
+            _, tokens = self.index.search(batch_data, 1, l2norm_rows=True)
         tokens = np.squeeze(tokens, 1)
         start = 0
         for spec_file, n_frames in zip(batch_files, lengths):
@@ -64,6 +80,20 @@ class SpecTokenizer:
             np.save(tokenized_dir / f"{spec_file.stem}.npy", tokens[start:end])
             start = end
         return tokens.tolist()
+
+    def apply_convolution(self, batch):
+        """(n, n_mels) numpy / CUDA tensor -> (n, n_mels * num_kernels) CUDA tensor (reference :92-104); None for an empty
+        batch like the reference."""
+        if len(batch) == 0:
+            self.logger.warning("Received empty batch for convolution")
+            return None
+        if not torch.is_tensor(batch):
+            batch = torch.from_numpy(np.ascontiguousarray(batch, dtype=np.float32)).to(self.device)
+        return at_b200.conv_expand(batch.contiguous(), self.conv_weight, self.conv_bias)
+
+    def create_convolution_layer(self):
+        """(weight, bias) of the reference's seeded, never-trained nn.Conv1d (:115-121) as device tensors."""
+        return at_b200.make_conv_layer(self.config)
 
     @staticmethod
     def normalize_vectors(vectors):

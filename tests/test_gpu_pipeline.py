@@ -211,3 +211,119 @@ def test_large_vocab_tensor_search_matches_exact_scan():
     b, db = ix.search(rows, algo=_lib.ALGO_TENSOR)
     assert torch.equal(a, b)
     assert torch.equal(da, db)
+
+
+def test_use_convolution_branch_matches_the_reference_expressions(tmp_path, monkeypatch):
+    """config.use_convolution = True (cluster_creator.py:28-34,68-81; spec_tokenizer.py:92-104,115-121): the seeded,
+    never-trained Conv1d expansion 64 -> 640 values per frame, k-means and tokenization over the wide rows, against the
+    reference's own torch expressions for the expansion and the FAISS restatement for stages 2-3."""
+    import torch
+    import at_b200
+    from oracle import faiss_ref, mel_ref
+    from processors.cluster_creator import ClusterCreator
+    from processors.spec_tokenizer import SpecTokenizer
+    from processors.spectrogram_generator import SpectrogramGenerator
+
+    cfg, ytids = _config(tmp_path, use_convolution=True, num_kernels=10, kernel_size=3, vocab_size=48, niter=5)
+    gen = SpectrogramGenerator(cfg)
+    monkeypatch.setattr(gen, "find_audio_file", lambda y: f"/audio/{y}.flac")
+    monkeypatch.setattr(gen, "preprocess_waveform", lambda p: _wave(os.path.basename(p)[:-5]).cuda())
+    gen.run()
+    train_files = sorted((tmp_path / "spectrograms" / "train").glob("*.npy"))
+
+    # the reference's layer, built the reference's way (seed, then the default initialisation on the CPU)
+    def ref_layer():
+        torch.manual_seed(cfg.random_seed)
+        return torch.nn.Conv1d(1, cfg.num_kernels, cfg.kernel_size, padding=cfg.kernel_size // 2)
+
+    def ref_apply(conv, rows):   # cluster_creator.py:68-81
+        t = torch.tensor(np.array(rows)).float().unsqueeze(1)
+        return conv(t).transpose(1, 2).reshape(-1, cfg.num_kernels * cfg.n_mels).detach().numpy()
+
+    cc = ClusterCreator(cfg)
+    conv = ref_layer()
+    assert torch.equal(cc.conv_weight.cpu(), conv.weight.detach().reshape(10, 3)) and torch.equal(cc.conv_bias.cpu(), conv.bias.detach())
+    x = np.concatenate([np.load(f).T for f in train_files], axis=0).astype(np.float32)
+    wide_ref = ref_apply(conv, x)
+    wide = cc.apply_convolution(x)
+    assert tuple(wide.shape) == (x.shape[0], 640)
+    assert np.abs(wide.cpu().numpy() - wide_ref).max() <= 2e-6
+    # other kernel shapes of the same operator (odd sizes keep the width, like padding = kernel_size // 2)
+    for kc, ks in ((4, 5), (1, 1), (16, 7)):
+        c2 = torch.nn.Conv1d(1, kc, ks, padding=ks // 2)
+        got = at_b200.conv_expand(torch.from_numpy(x[:777]).cuda(), c2.weight.detach().reshape(kc, ks).cuda().contiguous(),
+                                  c2.bias.detach().cuda())
+        want = c2(torch.from_numpy(x[:777]).unsqueeze(1)).transpose(1, 2).reshape(-1, kc * 64).detach().numpy()
+        assert np.abs(got.cpu().numpy() - want).max() <= 5e-6
+
+    # ---- stage 2 over the wide rows
+    cc.run()
+    cents = np.load(cfg.centroids_path)
+    assert cents.shape == (48, 640) and cents.dtype == np.float32
+    np.testing.assert_allclose(np.linalg.norm(cents, axis=1), 1.0, rtol=1e-5)
+    km = faiss_ref.Kmeans(640, 48, niter=5)
+    km.exact_search = True
+    km.train(mel_ref.normalize_rows(wide_ref))
+    ref_c = mel_ref.normalize_rows(km.centroids)
+    rel = np.linalg.norm(cents - ref_c, axis=1) / np.linalg.norm(ref_c, axis=1)
+    print("wide centroids within 1e-4 of the oracle's:", float((rel <= 1e-4).mean()), "max", float(rel.max()))
+    assert (rel <= 1e-4).mean() >= 0.9
+
+    # ---- stage 3 over the wide rows
+    tok = SpecTokenizer(cfg)
+    assert torch.equal(tok.conv_weight, cc.conv_weight) and torch.equal(tok.conv_bias, cc.conv_bias)
+    tok.run()
+    checked = flips = 0
+    for split in ("train", "validation"):
+        for f in sorted((tmp_path / "spectrograms" / split).glob("*.npy")):
+            t = np.load(tmp_path / "tokenized_audio" / split / f"{f.stem}.npy")
+            s = np.load(f).T.astype(np.float32)
+            assert t.dtype == np.int64 and t.shape == (s.shape[0],)
+            xn = mel_ref.normalize_rows(ref_apply(conv, s))
+            lab, d1, d2 = faiss_ref.assign_l2_scalar(xn, cents)
+            mism = t != lab
+            gap = (d2 - d1) / np.maximum(d1, 1e-30)
+            assert (gap[mism] < 1e-4).all()
+            checked += len(t)
+            flips += int(mism.sum())
+    print("wide tokens checked:", checked, "near-tie flips:", flips)
+    assert checked > 0 and flips <= checked * 1e-3
+
+
+def test_wide_row_search_and_update_match_the_oracle():
+    """d > 128 (the use_convolution regime): exact tiled fp32 search vs the scalar FAISS restatement, ragged sizes, and one
+    teacher-forced Lloyd step at d = 640 (k_gather_sum's wide instantiations)."""
+    import torch
+    from at_b200 import FlatL2, LloydTrainer, row_l2norm
+    from oracle import faiss_ref
+
+    g = torch.Generator("cuda").manual_seed(11)
+    for n, d, k in ((1000, 640, 50), (777, 132, 129), (4099, 320, 64), (65, 1024, 3)):
+        x = row_l2norm(torch.rand(n, d, device="cuda", generator=g))
+        c = x[torch.randperm(n, device="cuda", generator=g)[:k]].contiguous() + 0.01
+        ix = FlatL2(d)
+        ix.set_centroids(c)
+        lab, dist = ix.search(x, labels_dtype=torch.int64)
+        ref, d1, d2 = faiss_ref.assign_l2_scalar(x.cpu().numpy(), c.cpu().numpy())
+        mism = lab.cpu().numpy() != ref
+        gap = (d2 - d1) / np.maximum(d1, 1e-30)
+        assert (gap[mism] < 1e-4).all() and mism.mean() <= 1e-2
+        np.testing.assert_allclose(dist.cpu().numpy()[~mism], d1[~mism], rtol=1e-3, atol=1e-5)
+    n, d, k = 6000, 640, 40
+    x = row_l2norm(torch.rand(n, d, device="cuda", generator=g))
+    c0 = x[:k].contiguous()
+    tr = LloydTrainer(d, k)
+    tr.begin(x)
+    tr.set_centroids(c0)
+    stats = torch.zeros(4, device="cuda")
+    labels = torch.empty(n, dtype=torch.int32, device="cuda")
+    tr.step(x, stats, labels)
+    ref = faiss_ref.lloyd_step(x.cpu().numpy(), c0.cpu().numpy(), exact=True)
+    got, lab = tr.get_centroids().cpu().numpy(), labels.cpu().numpy()
+    mism = lab != ref["labels"]
+    touched = np.zeros(k, dtype=bool)
+    touched[lab[mism]] = True
+    touched[ref["labels"][mism]] = True
+    rel = np.linalg.norm(got - ref["centroids"], axis=1) / np.maximum(np.linalg.norm(ref["centroids"], axis=1), 1e-30)
+    assert int(stats.cpu().numpy()[1]) == ref["nsplit"] and mism.mean() < 1e-3
+    assert (rel[~touched] <= 1e-4).all()
