@@ -66,6 +66,7 @@
 // converged and issue from one elected lane (uniform operands).
 #include "at_index.cuh"
 #include "at_ptx.cuh"
+#include <stdlib.h>
 
 namespace at {
 
@@ -443,15 +444,29 @@ __device__ __forceinline__ uint32_t umin16(const uint32_t *k) {
 // runner-up can hide behind the winner in one grouping, never in both -- and the arg-min COLUMN is where the best A
 // group meets the best B class.
 // alu pipe: 16 (A minima) + 8 (A top-3) + 16 (B) per 32 columns = 1.25 per score; fma pipe: 2 IMAD per 32 columns.
-__device__ __forceinline__ void fold32(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const uint32_t ga, const uint32_t mul,
-                                       uint32_t &t1, uint32_t &t2, uint32_t &t3, uint32_t (&bp)[16]) {
-    const uint32_t ga0 = umin16(ra) * mul + ga, ga1 = umin16(rb) * mul + (ga + 1u);
+template <int G>   // G: index of the first of the two groups inside its tile (compile time: 0, 2, 4, 6)
+__device__ __forceinline__ void fold32(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const uint32_t tk, const uint32_t m16,
+                                       const uint32_t m8, uint32_t &t1, uint32_t &t2, uint32_t &t3, uint32_t (&bp)[16]) {
+    // key = pattern * 128 + (tile mod 16) * 8 + group as two chained IMADs (fma pipe, idle here) with the group as an
+    // immediate: a register addend (tile * 8 + group) costs one alu-pipe VIADD per group, and the alu pipe is the one the
+    // scan saturates (m16 = 16, m8 = 8 are kernel parameters so that the multiplications stay IMADs)
+    const uint32_t ga0 = (umin16(ra) * m16 + tk) * m8 + (uint32_t)G, ga1 = (umin16(rb) * m16 + tk) * m8 + (uint32_t)(G + 1);
     const uint32_t lo = min(ga0, ga1), hi = max(ga0, ga1);
     t3 = umin3(t3, max(t2, lo), max(t1, hi));
     t2 = umin3(t2, hi, max(t1, lo));
     t1 = min(t1, lo);
 #pragma unroll
     for (int h = 0; h < 16; h++) bp[h] = umin3(bp[h], ra[h], rb[h]);
+}
+
+// Candidate queue of scanning warp `sw` (0 .. 4 RT - 1) of CTA `worker`: the CTA scans super tiles worker, worker + workers,
+// ... so the warp sees 32 rows of each of the CTA's my_tiles super tiles; the queues tile the n_pad-entry array in (CTA,
+// warp) order.  Returns the first entry; the capacity is my_tiles * 32.
+__device__ __host__ __forceinline__ int64_t tc_queue_base(int64_t nsuper, int workers, int worker, int sw) {
+    const int64_t qd = nsuper / workers, rem = nsuper % workers;
+    const int64_t before = worker * qd + (worker < rem ? worker : rem);   // super tiles of the CTAs in front
+    const int64_t mine = qd + (worker < rem ? 1 : 0);
+    return (before * (RT * 4) + mine * sw) * 32;
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
@@ -461,7 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ erow, const float *__restrict__ xns, int64_t n,
             const unsigned char *__restrict__ op, int ktiles, int k, const float *__restrict__ scale, uint32_t key_mul,
             int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist,
-            uint4 *__restrict__ tail, unsigned int *__restrict__ tail_count, unsigned int tail_cap) {
+            uint4 *__restrict__ tail, uint32_t *__restrict__ full, unsigned int *__restrict__ tail_count) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ uint32_t s_tmem_base;
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -583,9 +598,22 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
         const int rt = (warp - 4) >> 2;   // row tile of the super tile
         const int ew = warp & 3;          // the TMEM lane quadrant this warp may read
         const int row_in_super = rt * TM + ew * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        // Loop-invariant addresses, pinned in registers (the compiler otherwise re-derives them from %tid every tile, on
+        // the alu pipe the scan saturates).  v = (centroid tile counter) * RT + rt numbers this warp's accumulators: slot
+        // v & 3 of the TMEM ring, barrier phase (v >> 2) & 1.
+        uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16);
+        uint32_t bar_full = BAR(BAR_ACC_FULL), bar_empty = BAR(BAR_ACC_EMPTY);
+        asm volatile("" : "+r"(tbase), "+r"(bar_full), "+r"(bar_empty));
+        const uint32_t m16 = key_mul >> 3, m8 = key_mul >> 4;   // 16, 8
         const int ntiles = (int)my_tiles;
-        uint32_t u = 0;
+        // This warp's private queue of uncertified rows with a candidate list (tc_queue_base): a shared global counter
+        // costs one contended atomic round trip per warp and super tile in the middle of the lock-stepped scan (measured:
+        // 0.18 ms of a 1.1 ms launch); a private queue needs none.
+        const int sw = warp - 4;
+        uint4 *const queue = tail + tc_queue_base(nsuper, workers, worker, sw);
+        uint32_t qn = 0;
+        uint32_t v = (uint32_t)rt;
+        uint32_t left = (uint32_t)ntiles * (uint32_t)ktiles;   // accumulators this warp still has to scan
         bool primed = false;
         uint32_t c0[16], c1[16], c2[16], c3[16];
         for (int i = 0; i < ntiles; i++) {
@@ -601,73 +629,73 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             // Accumulator read-out in eight 16-column loads through four register buffers: two loads are always in flight
             // behind a fold of two, and the first two loads of the NEXT tile are issued before the last fold of this one.
             if (!primed) {   // very first tile of this warp
-                const uint32_t v0 = u * RT + rt;
-                mbar_waitx(BAR(BAR_ACC_FULL + v0 % ACC_SLOTS), (v0 / ACC_SLOTS) & 1);
+                mbar_waitx(bar_full + 8u * (v & 3u), (v >> 2) & 1u);
                 tc_fence_after();
-                const uint32_t ta = tmem + lane_addr + (v0 % ACC_SLOTS) * TN;
+                const uint32_t ta = tbase + (v & 3u) * TN;
                 tmem_ld16(ta, c0);
                 tmem_ld16(ta + 16, c1);
                 primed = true;
             }
-            for (int jt = 0; jt < ktiles; jt++, u++) {
-                const uint32_t acc = (u * RT + rt) % ACC_SLOTS;
-                const uint32_t ta = tmem + lane_addr + acc * TN;
-                const uint32_t idb = (uint32_t)(jt & 15) << 3;   // (tile mod 16, group) rides in the low 7 bits of an A key
-                tmem_ld_wait();                       // c0, c1 (issued during the previous tile)
-                tmem_ld16(ta + 32, c2);
-                tmem_ld16(ta + 48, c3);
-                fold32(c0, c1, idb, key_mul, t1, t2, t3, bp);
-                tmem_ld_wait();
-                tmem_ld16(ta + 64, c0);
-                tmem_ld16(ta + 80, c1);
-                fold32(c2, c3, idb + 2u, key_mul, t1, t2, t3, bp);
-                tmem_ld_wait();
-                tmem_ld16(ta + 96, c2);
-                tmem_ld16(ta + 112, c3);
-                // Release the accumulator as soon as its last columns are in registers, i.e. half way through the tile's
-                // scan (a short stall on the load latency, covered by the scheduler's other scanning warps): the three
-                // scanning groups of a CTA run in lockstep and share ONE spare TMEM slot, so a slot released after the
-                // third fold would have the next round of MMAs finish after the groups need them.
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                mbar_arrive_elect(BAR(BAR_ACC_EMPTY + acc));
-                fold32(c0, c1, idb + 4u, key_mul, t1, t2, t3, bp);
-                // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
-                const bool more = (jt + 1 < ktiles) || (i + 1 < ntiles);
-                const uint32_t vn = (u + 1) * RT + rt;
-                const uint32_t nbar = BAR(BAR_ACC_FULL + vn % ACC_SLOTS), nph = (vn / ACC_SLOTS) & 1;
-                const uint32_t tn = tmem + lane_addr + (vn % ACC_SLOTS) * TN;
-                bool started = false;
-                if (more && mbar_test(nbar, nph)) {   // warp-uniform: every lane probes the same barrier
-                    tc_fence_after();
-                    tmem_ld16(tn, c0);
-                    tmem_ld16(tn + 16, c1);
-                    started = true;
+            // centroid tiles in blocks of 16 (2,048 centroids): the running top-3 of a block is merged into the row's once
+            // per block, outside the tile loop
+            for (int jb = 0; jb * 16 < ktiles; jb++) {
+                const uint32_t nt = (uint32_t)min(16, ktiles - jb * 16);
+                for (uint32_t tk = 0; tk < nt; tk++) {   // (tile mod 16, group) rides in the low 7 bits of an A key
+                    const uint32_t slot = v & 3u;
+                    const uint32_t ta = tbase + slot * TN;
+                    tmem_ld_wait();                       // c0, c1 (issued during the previous tile)
+                    tmem_ld16(ta + 32, c2);
+                    tmem_ld16(ta + 48, c3);
+                    fold32<0>(c0, c1, tk, m16, m8, t1, t2, t3, bp);
+                    tmem_ld_wait();
+                    tmem_ld16(ta + 64, c0);
+                    tmem_ld16(ta + 80, c1);
+                    fold32<2>(c2, c3, tk, m16, m8, t1, t2, t3, bp);
+                    tmem_ld_wait();
+                    tmem_ld16(ta + 96, c2);
+                    tmem_ld16(ta + 112, c3);
+                    // Release the accumulator as soon as its last columns are in registers, i.e. half way through the
+                    // tile's scan (a short stall on the load latency, covered by the scheduler's other scanning warps): the
+                    // three scanning groups of a CTA run in lockstep and share ONE spare TMEM slot, so a slot released after
+                    // the third fold would have the next round of MMAs finish after the groups need them.
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    mbar_arrive_elect(bar_empty + 8u * slot);
+                    fold32<4>(c0, c1, tk, m16, m8, t1, t2, t3, bp);
+                    // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
+                    v += RT;
+                    left--;
+                    const bool more = left != 0u;
+                    const uint32_t nbar = bar_full + 8u * (v & 3u), nph = (v >> 2) & 1u;
+                    const uint32_t tn = tbase + (v & 3u) * TN;
+                    bool started = false;
+                    if (more && mbar_test(nbar, nph)) {   // warp-uniform: every lane probes the same barrier
+                        tc_fence_after();
+                        tmem_ld16(tn, c0);
+                        tmem_ld16(tn + 16, c1);
+                        started = true;
+                    }
+                    fold32<6>(c2, c3, tk, m16, m8, t1, t2, t3, bp);
+                    if (more && !started) {
+                        mbar_waitx(nbar, nph);
+                        tc_fence_after();
+                        tmem_ld16(tn, c0);
+                        tmem_ld16(tn + 16, c1);
+                    }
                 }
-                fold32(c2, c3, idb + 6u, key_mul, t1, t2, t3, bp);
-                if (more && !started) {
-                    mbar_waitx(nbar, nph);
-                    tc_fence_after();
-                    tmem_ld16(tn, c0);
-                    tmem_ld16(tn + 16, c1);
-                }
-                if ((jt & 15) == 15 || jt + 1 == ktiles) {
-                    // A grouping: merge the block's sorted triple into the row's (equal keys keep the earlier block); once per
-                    // sweep up to 2,048 centroids
-                    const int jb = jt >> 4;
-                    const bool p = t1 < g1;
-                    const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
-                    const uint32_t xa = p ? g1 : g2, ya = p ? t2 : t1;
-                    const int xt = p ? j1 : j2;
-                    const bool qn = ya < xa;
-                    g2 = min(xa, ya);
-                    j2 = qn ? jb : xt;
-                    g1 = min(g1, t1);
-                    j1 = p ? jb : j1;
-                    g3 = n3;
-                    t1 = t2 = t3 = 0xFFFFFFFFu;
-                }
+                // A grouping: merge the block's sorted triple into the row's (equal keys keep the earlier block)
+                const bool p = t1 < g1;
+                const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
+                const uint32_t xa = p ? g1 : g2, ya = p ? t2 : t1;
+                const int xt = p ? j1 : j2;
+                const bool qn = ya < xa;
+                g2 = min(xa, ya);
+                j2 = qn ? jb : xt;
+                g1 = min(g1, t1);
+                j1 = p ? jb : j1;
+                g3 = n3;
+                t1 = t2 = t3 = 0xFFFFFFFFu;
             }
             // column tiles of the two best A groups
             j1 = j1 * 16 + (int)((g1 >> 3) & 15u), j2 = j2 * 16 + (int)((g2 >> 3) & 15u);
@@ -711,30 +739,28 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                 if (labels64) labels64[row] = ca;
                 if (dist) dist[row] = v1 * inv_s2;
             }
-            // uncertified rows -> tail lists (warp-aggregated appends): candidate rows from the front, full-scan rows
-            // from the back of the same array.  Candidates: the four columns where one of the two best A groups meets one of
-            // the two best B classes.
+            // uncertified rows: candidate rows -> this warp's queue (the four columns where one of the two best A groups
+            // meets one of the two best B classes); rows that need an exact scan (rare) -> the dense global list
             const bool want_full = live && !certified && (fallback || !third_ok || ca >= k);
             const bool want_cand = live && !certified && !want_full;
             const unsigned mc = __ballot_sync(0xffffffffu, want_cand), mf = __ballot_sync(0xffffffffu, want_full);
-            if (mc | mf) {
-                unsigned int sc = 0, sf = 0;
-                if (lane == 0) {
-                    if (mc) sc = atomicAdd(tail_count, (unsigned int)__popc(mc));
-                    if (mf) sf = atomicAdd(tail_count + 1, (unsigned int)__popc(mf));
-                }
-                sc = __shfl_sync(0xffffffffu, sc, 0), sf = __shfl_sync(0xffffffffu, sf, 0);
-                const unsigned lt = (1u << lane) - 1u;
-                if (want_cand) {
-                    const int a1 = (int)((g1 & 7u) << 4), b1 = (int)(h1 & 15u), a2 = (int)((g2 & 7u) << 4), b2 = (int)(h2 & 15u);
-                    int c1 = j1 * TN + a1 + b2, c2 = j2 * TN + a2 + b1, c3 = j2 * TN + a2 + b2;
-                    c1 = c1 < k ? c1 : ca, c2 = c2 < k ? c2 : ca, c3 = c3 < k ? c3 : ca;
-                    tail[sc + __popc(mc & lt)] = make_uint4((uint32_t)row, (uint32_t)ca | ((uint32_t)c1 << 16),
-                                                            (uint32_t)c2 | ((uint32_t)c3 << 16), 0u);
-                }
-                if (want_full) tail[tail_cap - 1 - (sf + __popc(mf & lt))] = make_uint4((uint32_t)row, 0u, 0u, 0u);
+            const unsigned lt = (1u << lane) - 1u;
+            if (want_cand) {
+                const int a1 = (int)((g1 & 7u) << 4), b1 = (int)(h1 & 15u), a2 = (int)((g2 & 7u) << 4), b2 = (int)(h2 & 15u);
+                int c1 = j1 * TN + a1 + b2, c2 = j2 * TN + a2 + b1, c3 = j2 * TN + a2 + b2;
+                c1 = c1 < k ? c1 : ca, c2 = c2 < k ? c2 : ca, c3 = c3 < k ? c3 : ca;
+                queue[qn + __popc(mc & lt)] = make_uint4((uint32_t)row, (uint32_t)ca | ((uint32_t)c1 << 16),
+                                                         (uint32_t)c2 | ((uint32_t)c3 << 16), 0u);
+            }
+            qn += (uint32_t)__popc(mc);
+            if (mf) {
+                unsigned int sf = 0;
+                if (lane == 0) sf = atomicAdd(tail_count + 1, (unsigned int)__popc(mf));
+                sf = __shfl_sync(0xffffffffu, sf, 0);
+                if (want_full) full[sf + __popc(mf & lt)] = (uint32_t)row;
             }
         }
+        if (lane == 0) tail_count[2 + worker * (RT * 4) + sw] = qn;
     }
     tc_fence_before();
     __syncthreads();
@@ -760,18 +786,21 @@ __device__ __forceinline__ float4 tail_row(const float *__restrict__ x, int64_t 
     return xv;
 }
 
-// Uncertified rows with a candidate list (front of the tail array): a 16-lane group per row evaluates the (at most four)
-// candidate columns with the canonical fp32 arithmetic; the lowest index wins exact ties like the exact kernel's scan.
+// Uncertified rows with a candidate list: block q works through queue q (one per scanning warp of k_assign_tc), a
+// 16-lane group per row evaluating the (at most four) candidate columns with the canonical fp32 arithmetic; the lowest
+// index wins exact ties like the exact kernel's scan.
 __global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, int l2norm, const float *__restrict__ c,
-                                                 const float *__restrict__ cn, const uint4 *__restrict__ tail,
-                                                 const unsigned int *__restrict__ tail_count,
+                                                 const float *__restrict__ cn, const uint4 *__restrict__ tail_all,
+                                                 const unsigned int *__restrict__ tail_count, int64_t nsuper, int workers,
                                                  int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
                                                  float *__restrict__ dist, unsigned long long *__restrict__ counters) {
     const int lane = threadIdx.x & 31, half = lane >> 4, g = lane & 15;
-    const unsigned int n_cand = tail_count[0];
-    const unsigned int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int q = (int)blockIdx.x;
+    const unsigned int n_cand = tail_count[2 + q];
+    const uint4 *__restrict__ tail = tail_all + tc_queue_base(nsuper, workers, q / (RT * 4), q % (RT * 4));
+    const unsigned int nwarps = blockDim.x >> 5;
     // warp-uniform trip count: the 16-lane reductions shuffle with the full mask
-    for (unsigned int e0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; e0 < n_cand; e0 += nwarps * 2) {
+    for (unsigned int e0 = (threadIdx.x >> 5) * 2; e0 < n_cand; e0 += nwarps * 2) {
         const unsigned int e = e0 + half;
         const bool live = e < n_cand;
         const uint4 cc = tail[live ? e : e0];
@@ -799,9 +828,9 @@ __global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, in
             if (dist) dist[row] = bd;
         }
     }
-    if (counters && blockIdx.x == 0 && threadIdx.x == 0) {
-        atomicAdd(&counters[0], (unsigned long long)n_cand);
-        atomicAdd(&counters[1], (unsigned long long)tail_count[1]);
+    if (counters && threadIdx.x == 0) {
+        if (n_cand) atomicAdd(&counters[0], (unsigned long long)n_cand);
+        if (blockIdx.x == 0) atomicAdd(&counters[1], (unsigned long long)tail_count[1]);
     }
 }
 
@@ -810,10 +839,40 @@ __global__ void __launch_bounds__(256) k_tc_tail(const float *__restrict__ x, in
 // 4q .. 4q+3 of every 32-centroid tile streamed through shared memory (the next tile is fetched into registers while the
 // current one is scanned) -- the exact SIMT kernel's arithmetic (canonical chunk partials + xor tree); the lowest index
 // wins exact ties.
+// Packed fp32 (FMUL2 / FFMA2 / FADD2, sm_100): the canonical sum is 16 independent 4-term FMA chains (chunk l = elements
+// 4l .. 4l+3) joined by the tree q[i] + q[i+8], a[i] + a[i+4], b[i] + b[i+2], c[0] + c[1].  Chunks 2p and 2p+1 ride in the
+// two halves of a register pair, so each chain step is one packed instruction for two chunks and the first three tree
+// levels are packed additions of pairs -- the same IEEE operations on the same operands in the same association, 40 issue
+// slots per (row, centroid) instead of 79.  The centroid tile is stored in shared memory already interleaved for that:
+// element 4l+e of a centroid sits at 8 (l >> 1) + 2e + (l & 1).
+// fp32x2 on 64-bit registers (the halves are independent IEEE fp32 lanes): keeping the operands as b64 values from the load
+// on makes the register pairs explicit -- built from float2 temporaries the compiler re-packs every operand with MOVs
+typedef unsigned long long u64x;
+__device__ __forceinline__ u64x pack2(float lo, float hi) {
+    u64x r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64x v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64x mul2(u64x a, u64x b) {
+    u64x r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64x fma2(u64x a, u64x b, u64x c) {
+    u64x r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64x addp2(u64x a, u64x b) {
+    u64x r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 constexpr int FULL_ROWS = 32, FULL_KT = 32, FULL_SLICES = 8;
 __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
     const float *__restrict__ x, int l2norm, const float *__restrict__ c, const float *__restrict__ cn, int k,
-    const uint4 *__restrict__ tail, const unsigned int *__restrict__ tail_count, unsigned int tail_cap,
+    const uint32_t *__restrict__ full, const unsigned int *__restrict__ tail_count,
     int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist) {
     __shared__ __align__(16) float ctile[FULL_KT][64];
     __shared__ float cns[FULL_KT];
@@ -828,31 +887,43 @@ __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
     for (unsigned int base = blockIdx.x * FULL_ROWS; base < n_full; base += gridDim.x * FULL_ROWS) {
         const unsigned int e = base + r;
         const bool live = e < n_full;
-        const int64_t row = (int64_t)tail[tail_cap - 1 - (live ? e : base)].x;
-        float xr[64];
+        const int64_t row = (int64_t)full[live ? e : base];
+        // xp[p][e] = (x[8p + e], x[8p + 4 + e]): chunks 2p and 2p+1 side by side.  (A plain mov.b64 pack is transparent to
+        // ptxas, which then keeps the 64 scalars where the loads put them and re-packs both halves before every use: 61
+        // MOVs per centroid.  x + (-0) = x for every x.)
+        u64x negzero2 = 0x8000000080000000ull;
+        asm volatile("" : "+l"(negzero2));
+        u64x xp[8][4];
+        float xn;
         {
-            const float4 *xp = reinterpret_cast<const float4 *>(x + row * 64);
+            float xr[64];
+            const float4 *xq = reinterpret_cast<const float4 *>(x + row * 64);
 #pragma unroll
             for (int t = 0; t < 16; t++) {
-                const float4 v = __ldg(xp + t);
+                const float4 v = __ldg(xq + t);
                 xr[4 * t] = v.x, xr[4 * t + 1] = v.y, xr[4 * t + 2] = v.z, xr[4 * t + 3] = v.w;
             }
-        }
-        float qq[16];
-        if (l2norm) {
+            float qq[16];
+            if (l2norm) {
+#pragma unroll
+                for (int l = 0; l < 16; l++) qq[l] = 0.f;
+#pragma unroll
+                for (int t = 0; t < 64; t++) qq[t >> 2] = fmaf(xr[t], xr[t], qq[t >> 2]);
+                const float den = l2_denominator(tree16(qq));
+#pragma unroll
+                for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
+            }
 #pragma unroll
             for (int l = 0; l < 16; l++) qq[l] = 0.f;
 #pragma unroll
             for (int t = 0; t < 64; t++) qq[t >> 2] = fmaf(xr[t], xr[t], qq[t >> 2]);
-            const float den = l2_denominator(tree16(qq));
+            xn = tree16(qq);
 #pragma unroll
-            for (int t = 0; t < 64; t++) xr[t] = __fdiv_rn(xr[t], den);
+            for (int pp = 0; pp < 8; pp++)
+#pragma unroll
+                for (int ee = 0; ee < 4; ee++)   // + (-0, -0): the identity, as an instruction whose result IS a register pair
+                    xp[pp][ee] = addp2(pack2(xr[8 * pp + ee], xr[8 * pp + 4 + ee]), negzero2);
         }
-#pragma unroll
-        for (int l = 0; l < 16; l++) qq[l] = 0.f;
-#pragma unroll
-        for (int t = 0; t < 64; t++) qq[t >> 2] = fmaf(xr[t], xr[t], qq[t >> 2]);
-        const float xn = tree16(qq);
         float bd = INFINITY;
         int best = 0x7FFFFFFF;
         float4 pre[LD];
@@ -866,7 +937,12 @@ __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
         for (int j0 = 0; j0 < k; j0 += FULL_KT) {
             __syncthreads();   // the previous tile has been consumed
 #pragma unroll
-            for (int t = 0; t < LD; t++) reinterpret_cast<float4 *>(&ctile[0][0])[tid + t * (FULL_ROWS * FULL_SLICES)] = pre[t];
+            for (int t = 0; t < LD; t++) {
+                // float4 `i4` of the tile = chunk l of centroid jj -> interleaved positions 8 (l >> 1) + 2e + (l & 1)
+                const int i4 = tid + t * (FULL_ROWS * FULL_SLICES), jj = i4 >> 4, l = i4 & 15;
+                float *dstp = &ctile[jj][8 * (l >> 1) + (l & 1)];
+                dstp[0] = pre[t].x, dstp[2] = pre[t].y, dstp[4] = pre[t].z, dstp[6] = pre[t].w;
+            }
             if (tid < FULL_KT) cns[tid] = pre_cn;
             __syncthreads();
             const int jn = j0 + FULL_KT;   // fetch the next tile while this one is scanned
@@ -881,16 +957,24 @@ __global__ void __launch_bounds__(FULL_ROWS * FULL_SLICES) k_tc_full(
 #pragma unroll
             for (int u = 0; u < PER; u++) {
                 const int jj = q * PER + u;
+                const ulonglong2 *ct = reinterpret_cast<const ulonglong2 *>(&ctile[jj][0]);
+                u64x sp[8];   // sp[p] = (q[2p], q[2p+1])
 #pragma unroll
-                for (int l = 0; l < 16; l++) {
-                    const float4 cv = *reinterpret_cast<const float4 *>(&ctile[jj][4 * l]);
-                    float sacc = xr[4 * l] * cv.x;
-                    sacc = fmaf(xr[4 * l + 1], cv.y, sacc);
-                    sacc = fmaf(xr[4 * l + 2], cv.z, sacc);
-                    sacc = fmaf(xr[4 * l + 3], cv.w, sacc);
-                    qq[l] = sacc;
+                for (int pp = 0; pp < 8; pp++) {
+                    const ulonglong2 v0 = ct[2 * pp], v1 = ct[2 * pp + 1];
+                    u64x acc = mul2(xp[pp][0], v0.x);
+                    acc = fma2(xp[pp][1], v0.y, acc);
+                    acc = fma2(xp[pp][2], v1.x, acc);
+                    acc = fma2(xp[pp][3], v1.y, acc);
+                    sp[pp] = acc;
                 }
-                const float dj = l2_expanded(xn, cns[jj], tree16(qq));
+                // tree16 on pairs: a[i] = q[i] + q[i+8], b[i] = a[i] + a[i+4], c[i] = b[i] + b[i+2], c[0] + c[1]
+                const u64x a0 = addp2(sp[0], sp[4]), a1 = addp2(sp[1], sp[5]);
+                const u64x a2 = addp2(sp[2], sp[6]), a3 = addp2(sp[3], sp[7]);
+                const u64x cc2 = addp2(addp2(a0, a2), addp2(a1, a3));
+                float2 cc;
+                unpack2(cc2, cc.x, cc.y);
+                const float dj = l2_expanded(xn, cns[jj], __fadd_rn(cc.x, cc.y));
                 if (j0 + jj < k && dj < bd) bd = dj, best = j0 + jj;   // ascending index within the slice: strict '<'
             }
         }
@@ -955,7 +1039,7 @@ int assign_tc_prepare(at_index *ix, cudaStream_t st) {
 }
 
 void tc_rows_free(at_tc_rows *r) {
-    cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->tail_count);
+    cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->full), cudaFree(r->tail_count);
     *r = at_tc_rows();
 }
 
@@ -972,16 +1056,23 @@ int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const fl
     const int64_t n_pad = (n + SROWS - 1) / SROWS * SROWS;
     if (n_pad > r->cap) {
         AT_CUDA_OK(cudaStreamSynchronize(st));
-        cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail);
-        r->img = nullptr, r->erow = r->xns = nullptr, r->tail = nullptr, r->cap = 0;
+        cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->full);
+        r->img = nullptr, r->erow = r->xns = nullptr, r->tail = nullptr, r->full = nullptr, r->cap = 0;
         AT_CUDA_OK(cudaMalloc(&r->img, (size_t)(n_pad / TM) * A_TILE_BYTES));
         AT_CUDA_OK(cudaMalloc(&r->erow, sizeof(float) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->xns, sizeof(float) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->tail, sizeof(uint4) * (size_t)n_pad));
-        if (!r->tail_count) AT_CUDA_OK(cudaMalloc(&r->tail_count, 2 * sizeof(unsigned int)));
+        AT_CUDA_OK(cudaMalloc(&r->full, sizeof(uint32_t) * (size_t)n_pad));
         r->cap = n_pad;
     }
     const int sms = sm_count() > 0 ? sm_count() : 1;
+    if (r->tail_queues < sms * RT * 4) {   // one candidate queue per scanning warp of the search grid (<= one CTA per SM)
+        AT_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(r->tail_count);
+        r->tail_count = nullptr, r->tail_queues = 0;
+        AT_CUDA_OK(cudaMalloc(&r->tail_count, sizeof(unsigned int) * (size_t)(2 + sms * RT * 4)));
+        r->tail_queues = sms * RT * 4;
+    }
     k_tc_rows<<<sms * 8, 256, 0, st>>>(x, n, n_pad, l2norm, sx, reinterpret_cast<unsigned char *>(r->img), r->erow, r->xns);
     AT_LAUNCH_OK();
     r->x = x, r->n = n, r->l2norm = l2norm;
@@ -1029,29 +1120,33 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     if (resident)
         k_assign_tc<true><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
                                                             ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
-                                                            rows->tail_count, (unsigned int)rows->cap);
+                                                            rows->full, rows->tail_count);
     else
         k_assign_tc<false><<<grid, TC_THREADS, TC_SMEM, st>>>(img, rows->erow, rows->xns, n, op, ix->ktiles, ix->k,
                                                              ix->tc_scale, 128u, l32, labels64, kdist, rows->tail,
-                                                             rows->tail_count, (unsigned int)rows->cap);
+                                                             rows->full, rows->tail_count);
     AT_LAUNCH_OK();
     // The two tail kernels touch disjoint rows: the exact scans (few rows, FMA-bound) run on the index's side stream while
     // the candidate re-checks (many rows, latency-bound) run on the caller's, joined again before anything reads the labels.
 #ifndef AT_TC_TAIL_FORK
 #define AT_TC_TAIL_FORK 1
 #endif
-    const bool fork = AT_TC_TAIL_FORK && ix->side_ok();
+    // timing experiments only (wrong labels): AT_TC_SKIP bit 0 drops the exact scans, bit 1 the candidate re-checks
+    static const int skip = getenv("AT_TC_SKIP") ? atoi(getenv("AT_TC_SKIP")) : 0;
+    const bool fork = AT_TC_TAIL_FORK && ix->side_ok() && !skip;
     cudaStream_t fs = fork ? ix->side : st;
     if (fork) {
         AT_CUDA_OK(cudaEventRecord(ix->ev_fork, st));
         AT_CUDA_OK(cudaStreamWaitEvent(ix->side, ix->ev_fork, 0));
     }
-    k_tc_full<<<sms * 8, FULL_ROWS * FULL_SLICES, 0, fs>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->tail, rows->tail_count,
-                                            (unsigned int)rows->cap, l32, labels64, kdist);
+    if (!(skip & 1))
+    k_tc_full<<<sms * 8, FULL_ROWS * FULL_SLICES, 0, fs>>>(x, l2norm_rows, ix->c, ix->cn, ix->k, rows->full, rows->tail_count,
+                                            l32, labels64, kdist);
     AT_LAUNCH_OK();
     if (fork) AT_CUDA_OK(cudaEventRecord(ix->ev_join, ix->side));
-    k_tc_tail<<<sms * 8, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, rows->tail, rows->tail_count, l32, labels64, kdist,
-                                      ix->tc_counters);
+    if (!(skip & 2))
+    k_tc_tail<<<grid * RT * 4, 256, 0, st>>>(x, l2norm_rows, ix->c, ix->cn, rows->tail, rows->tail_count, nsuper, grid, l32,
+                                            labels64, kdist, ix->tc_counters);
     AT_LAUNCH_OK();
     if (fork) AT_CUDA_OK(cudaStreamWaitEvent(st, ix->ev_join, 0));
     if (dist && exact_dist) {

@@ -9,8 +9,11 @@ struct at_tc_rows {
     void *img = nullptr;        // (n_pad / 128) tiles of 20,480 bytes
     float *erow = nullptr;      // (n_pad) |Sx delta| per row
     float *xns = nullptr;       // (n_pad) Sx^2 |x|^2 per row
-    uint4 *tail = nullptr;      // (n_pad) uncertified rows of the last search: {row, candidate columns 0|1, 2|3, -}
-    unsigned int *tail_count = nullptr;
+    uint4 *tail = nullptr;      // (n_pad) uncertified rows of the last search with a candidate list, one queue per scanning
+                                // warp of k_assign_tc (no shared counter): {row, candidate columns 0|1, 2|3, -}
+    uint32_t *full = nullptr;   // (n_pad) uncertified rows that need an exact scan (dense list)
+    unsigned int *tail_count = nullptr;   // [1] rows in `full`, [2 + q] entries of candidate queue q
+    int tail_queues = 0;        // queues allocated in tail_count
     int64_t cap = 0;            // rows allocated (multiple of 256)
     const float *x = nullptr;   // what the image was built from
     int64_t n = 0;
