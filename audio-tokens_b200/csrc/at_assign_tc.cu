@@ -126,7 +126,9 @@ constexpr float TAU_SAFETY = 1.0625f;
 
 // scale[] layout (device floats written by k_tc_scale).  Sx is the scale of the row image (x~ = fp16(Sx x)): the
 // index's own S unless a prepared image with its own scale is attached (k-means), R = S / Sx.
-enum { SC_S = 0, SC_EMAX = 1, SC_INV_S2 = 2, SC_TAU = 3, SC_CMAX = 4, SC_SX = 5, SC_RATIO = 6, SC_COUNT = 8 };
+// SC_CANON = S (|m| + max |c_j|): with S |x - m| it bounds S (|x| + |c|), the scale of the canonical fp32 formula's own
+// rounding error (the tail kernels evaluate the UNSHIFTED rows and centroids).
+enum { SC_S = 0, SC_EMAX = 1, SC_INV_S2 = 2, SC_TAU = 3, SC_CMAX = 4, SC_SX = 5, SC_RATIO = 6, SC_CANON = 7, SC_COUNT = 8 };
 
 // (mbarrier / bulk-copy wrappers: at_ptx.cuh)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -250,10 +252,14 @@ __device__ __host__ __forceinline__ uint32_t aug_off(int r, int kc) { return (ui
 // ------------------------------------------------------------------------------------------ operand prep
 // S = 2^s, the largest power of two with S * max|c_j| <= SC_LIMIT (so P d + BIAS stays inside [2^13, 2^17) for every
 // row with S |x| <= X_LIMIT); tau = absolute part of the certification threshold in accumulator units.
-__global__ void k_tc_scale(unsigned int *__restrict__ maxes, const float *__restrict__ ext_sx, float *__restrict__ scale) {
+// maxes: bit patterns of {max |c_ij - m_i|, max |c_j - m|^2, max |c_j|^2} (k_centroid_norms).
+__global__ void k_tc_scale(unsigned int *__restrict__ maxes, const float *__restrict__ ext_sx, const float *__restrict__ shift,
+                           float *__restrict__ scale) {
     if (threadIdx.x == 0) {
-        const float m = __uint_as_float(maxes[0]), n2 = __uint_as_float(maxes[1]);
-        maxes[0] = 0u, maxes[1] = 0u;   // ready for the next set of centroids
+        const float m = __uint_as_float(maxes[0]), n2 = __uint_as_float(maxes[1]), n2_orig = __uint_as_float(maxes[2]);
+        maxes[0] = 0u, maxes[1] = 0u, maxes[2] = 0u;   // ready for the next set of centroids
+        float m2 = 0.f;
+        for (int t = 0; t < 64; t++) m2 = fmaf(shift[t], shift[t], m2);
         const float cmax = sqrtf(n2) * 1.0009765625f;
         int e = 0;
         if (cmax > 0.f && isfinite(cmax)) {
@@ -282,7 +288,7 @@ __global__ void k_tc_scale(unsigned int *__restrict__ maxes, const float *__rest
         scale[SC_CMAX] = S * cmax;
         scale[SC_SX] = Sx;
         scale[SC_RATIO] = S / Sx;
-        scale[7] = 0.f;
+        scale[SC_CANON] = S * (sqrtf(m2) + sqrtf(n2_orig)) * 1.001f;
     }
 }
 
@@ -291,7 +297,7 @@ __global__ void k_tc_scale(unsigned int *__restrict__ maxes, const float *__rest
 // per-centroid error norm goes to scale[SC_EMAX] (non-negative floats order like their bit patterns); lane 0 also
 // writes the aug chunk.  Padding columns (j >= k) repeat centroid k-1 with PAD_BUMP added to the norm: always behind the
 // real column by far more than any threshold, inside the key range, skipped by the tail kernel.
-__global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, const float *__restrict__ cn, int k, int ktiles,
+__global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, const float *__restrict__ shift, int k, int ktiles,
                                                  float *__restrict__ scale, unsigned char *__restrict__ op) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = idx >> 3, chunk = idx & 7;
@@ -302,10 +308,12 @@ __global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, co
     const int r = j % TN;
     const int js = j < k ? j : k - 1;
     __align__(16) __half hi[8], lo[8];
-    float e2 = 0.f;
+    float e2 = 0.f, cn2 = 0.f;   // cn2: |c_j - m|^2 (need not be canonical: its rounding is inside tau_abs)
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-        const float v = -2.0f * Sc * c[(size_t)js * 64 + chunk * 8 + e];
+        const float cs = c[(size_t)js * 64 + chunk * 8 + e] - shift[chunk * 8 + e];
+        cn2 = fmaf(cs, cs, cn2);
+        const float v = -2.0f * Sc * cs;
         hi[e] = __float2half_rn(v);
         float err = v - __half2float(hi[e]);
         if (SPLIT_C) {
@@ -319,6 +327,9 @@ __global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, co
     e2 += __shfl_xor_sync(0xffffffffu, e2, 1);
     e2 += __shfl_xor_sync(0xffffffffu, e2, 2);
     e2 += __shfl_xor_sync(0xffffffffu, e2, 4);
+    cn2 += __shfl_xor_sync(0xffffffffu, cn2, 1);
+    cn2 += __shfl_xor_sync(0xffffffffu, cn2, 2);
+    cn2 += __shfl_xor_sync(0xffffffffu, cn2, 4);
     float en = sqrtf(e2) * 1.001f;
     if (!(en == en)) en = INFINITY;   // a non-finite centroid: nothing is certified
     en = fmaxf(en, __shfl_xor_sync(0xffffffffu, en, 8));
@@ -330,7 +341,7 @@ __global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, co
         __align__(16) __half a[8];
         const __half w = __float2half_rn(AUG_ONE * R * R), zero = __float2half_rn(0.f);
         a[0] = a[1] = a[2] = w;
-        split3(fmaf(cn[js], S * S * AUG_INV, (j < k ? BIAS : BIAS + PAD_BUMP) * AUG_INV), a[3], a[4], a[5]);
+        split3(fmaf(cn2, S * S * AUG_INV, (j < k ? BIAS : BIAS + PAD_BUMP) * AUG_INV), a[3], a[4], a[5]);
         a[6] = a[7] = zero;
         unsigned char *aug = tile + B_MAIN_BYTES;
         *reinterpret_cast<uint4 *>(aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
@@ -342,11 +353,18 @@ __global__ void __launch_bounds__(256) k_tc_prep(const float *__restrict__ c, co
 // 4 lanes per row (lane jq holds floats 16 jq .. 16 jq + 15), 8 rows per warp step.  Rows beyond n are zero.
 // The reductions here need not follow the canonical association: a row that differs from the canonically normalised
 // one in the last bit is inside the certification threshold (the 1e-6 |Sx x| term of erow).
+// The image is that of x - m (m = shift, see at_index.cuh): xns = Sx^2 |x - m|^2; erow bounds the image's distance from the
+// exact shifted row: fp16 rounding + the fp32 rounding of the subtraction (<= 2^-24 |x - m|) + the normalisation slack, which
+// scales with the UNSHIFTED norm.
 __global__ void __launch_bounds__(256) k_tc_rows(const float *__restrict__ x, int64_t n, int64_t n_pad, int l2norm,
-                                                 const float *__restrict__ sx_ptr, unsigned char *__restrict__ img,
-                                                 float *__restrict__ erow, float *__restrict__ xns) {
+                                                 const float *__restrict__ sx_ptr, const float *__restrict__ shift,
+                                                 unsigned char *__restrict__ img, float *__restrict__ erow,
+                                                 float *__restrict__ xns) {
     const int lane = threadIdx.x & 31, rsub = lane >> 2, jq = lane & 3;
     const float Sx = sx_ptr[0];
+    float ms[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) ms[t] = shift[16 * jq + t];
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r0 = warp * 8; r0 < n_pad; r0 += nwarps * 8) {   // warp-uniform trip count
@@ -378,6 +396,15 @@ __global__ void __launch_bounds__(256) k_tc_rows(const float *__restrict__ x, in
             q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
             xn = q2;
         }
+        const float xn_orig = xn;   // |x|^2 of the (normalised) row itself
+        if (r < n) {
+            float q3 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; t++) xs[t] -= ms[t], q3 = fmaf(xs[t], xs[t], q3);
+            q3 += __shfl_xor_sync(0xffffffffu, q3, 1);
+            q3 += __shfl_xor_sync(0xffffffffu, q3, 2);
+            xn = q3;
+        }
         __align__(16) __half2 hh[8];
         float e2 = 0.f;
 #pragma unroll
@@ -405,7 +432,7 @@ __global__ void __launch_bounds__(256) k_tc_rows(const float *__restrict__ x, in
             unsigned char *a_aug = a_tile + A_MAIN_BYTES;
             *reinterpret_cast<uint4 *>(a_aug + aug_off(rr, 0)) = *reinterpret_cast<uint4 *>(a);
             *reinterpret_cast<uint4 *>(a_aug + aug_off(rr, 1)) = make_uint4(0, 0, 0, 0);
-            erow[r] = sqrtf(e2) * 1.001f + 1e-6f * sqrtf(xnS);
+            erow[r] = sqrtf(e2) * 1.001f + 1e-6f * Sx * sqrtf(xn_orig) + 2e-7f * sqrtf(xnS);
             xns[r] = xnS;
         }
     }
@@ -714,8 +741,9 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             }
             // (the scale constants are re-read per super tile rather than held in registers across the scan)
             const float inv_s2 = __ldg(scale + SC_INV_S2), tau_abs = __ldg(scale + SC_TAU), cmax = __ldg(scale + SC_CMAX);
-            const float R = __ldg(scale + SC_RATIO), emax = __ldg(scale + SC_EMAX);
-            const float e = R * erow_r;                      // S |delta|
+            const float R = __ldg(scale + SC_RATIO), emax = __ldg(scale + SC_EMAX), canon = __ldg(scale + SC_CANON);
+            // S |delta|: the row image's distance from the exact shifted row, plus the fp32 rounding of c - m
+            const float e = fmaf(1.2e-7f, cmax, R * erow_r);
             const float xnP = R * R * xnS;                   // S^2 |x|^2
             const bool fallback = !(xnP <= X_LIMIT * X_LIMIT);   // outside the accumulator range, Inf, NaN
             // ---- certification (accumulator units)
@@ -724,7 +752,10 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
             const float v1 = fmaxf(A1 - BIAS, 0.f);
             const float cterm = sqrtf(xnS) * 1.001f * emax;                          // >= |<x~, e_j>| for every column j
             const float ub = v1 + 2.0f * e * cmax + tau_abs + cterm;                 // >= S^2 d_best
-            const float tau = TAU_SAFETY * (tau_abs + 4.0f * e * sqrtf(ub + tau_abs) + 2.0f * cterm);
+            // + the canonical fp32 formula's own resolution on the difference of two candidates, 2 x 2^-20 S^2 (|x| + |c|)^2
+            // with S |x| <= S |x - m| + S |m|: what is certified must also be what the exact kernels' arithmetic decides
+            const float sxc = sqrtf(xnP) + canon;
+            const float tau = TAU_SAFETY * (tau_abs + 4.0f * e * sqrtf(ub + tau_abs) + 2.0f * cterm + 1.9073486e-6f * sxc * sxc);
             const bool second_ok = (A2 - A1) > tau;   // exact second smallest column: no other column can win
             // every column outside (best two A groups) x (best two B groups) is out of reach
             const bool third_ok = (A3 - A1) > tau;
@@ -1029,10 +1060,11 @@ bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16
 
 int assign_tc_prepare(at_index *ix, cudaStream_t st) {
     if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, SC_COUNT * sizeof(float)));
-    k_tc_scale<<<1, 32, 0, st>>>(ix->tc_max, ix->ext_sx, ix->tc_scale);
+    const float *shift = ix->ext_shift ? ix->ext_shift : ix->shift;
+    k_tc_scale<<<1, 32, 0, st>>>(ix->tc_max, ix->ext_sx, shift, ix->tc_scale);
     AT_LAUNCH_OK();
     const int total = ix->ktiles * TN * 8;
-    k_tc_prep<<<(total + 255) / 256, 256, 0, st>>>(ix->c, ix->cn, ix->k, ix->ktiles, ix->tc_scale,
+    k_tc_prep<<<(total + 255) / 256, 256, 0, st>>>(ix->c, shift, ix->k, ix->ktiles, ix->tc_scale,
                                                   reinterpret_cast<unsigned char *>(ix->op));
     AT_LAUNCH_OK();
     return AT_OK;
@@ -1044,7 +1076,30 @@ void tc_rows_free(at_tc_rows *r) {
 }
 
 // (Re)builds the operand image of x.  sx: device float, the image scale (a power of two).
-int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, cudaStream_t st) {
+// mean of the centroids (d == 64): 16 row slices x 64 columns, summed in a fixed order
+__global__ void __launch_bounds__(1024) k_tc_mean(const float *__restrict__ c, int k, float *__restrict__ shift) {
+    __shared__ float part[16][64];
+    const int col = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    float s = 0.f;
+    for (int j = sl; j < k; j += 16) s += c[(size_t)j * 64 + col];
+    part[sl][col] = s;
+    __syncthreads();
+    if (sl == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; q++) t += part[q][col];
+        t /= (float)k;
+        shift[col] = isfinite(t) ? t : 0.f;   // any vector is a valid centre; a non-finite one would poison every row
+    }
+}
+
+int tc_mean(const float *c, int k, float *shift, cudaStream_t st) {
+    k_tc_mean<<<1, 1024, 0, st>>>(c, k, shift);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, const float *shift, cudaStream_t st) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) {
         set_error("search: tensor path needs 16-byte aligned rows");
         return AT_ERR_UNSUPPORTED;
@@ -1073,7 +1128,8 @@ int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const fl
         AT_CUDA_OK(cudaMalloc(&r->tail_count, sizeof(unsigned int) * (size_t)(2 + sms * RT * 4)));
         r->tail_queues = sms * RT * 4;
     }
-    k_tc_rows<<<sms * 8, 256, 0, st>>>(x, n, n_pad, l2norm, sx, reinterpret_cast<unsigned char *>(r->img), r->erow, r->xns);
+    k_tc_rows<<<sms * 8, 256, 0, st>>>(x, n, n_pad, l2norm, sx, shift, reinterpret_cast<unsigned char *>(r->img), r->erow,
+                                       r->xns);
     AT_LAUNCH_OK();
     r->x = x, r->n = n, r->l2norm = l2norm;
     return AT_OK;
@@ -1091,7 +1147,7 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     }
     if (!rows) {
         rows = &ix->rows;
-        int rc = tc_rows_build(rows, x, n, l2norm_rows, ix->tc_scale + SC_SX, st);
+        int rc = tc_rows_build(rows, x, n, l2norm_rows, ix->tc_scale + SC_SX, ix->ext_shift ? ix->ext_shift : ix->shift, st);
         if (rc != AT_OK) return rc;
     }
     // a distance request without labels still needs labels for the second pass

@@ -32,6 +32,11 @@ struct at_index {
     float *tc_scale = nullptr;  // device: {S, max centroid rounding error, 1 / S^2, tau, S max|c|, Sx, S / Sx}
     unsigned int *tc_max = nullptr;  // device: {max |c_ij|, max |c_j|^2} bit patterns (k_centroid_norms -> k_tc_scale)
     const float *ext_sx = nullptr;  // device float: scale of an attached row image (k-means); nullptr = the index's own S
+    // Centering: |x - c|^2 = |(x - m) - (c - m)|^2 for any m, and the fp16 rounding errors of the operands scale with
+    // |x - m| |c - m| instead of |x| |c| -- m = mean of the centroids (the index's own `shift`, refreshed with the
+    // centroids), or the vector an attached row image was built with (`ext_shift`, k-means: fixed for the training run)
+    float *shift = nullptr;         // (64) device
+    const float *ext_shift = nullptr;
     at_tc_rows rows;            // workspace of one-off searches
     unsigned long long *tc_counters = nullptr;  // device: rows re-checked on their candidate columns, rows scanned exactly (cumulative)
     int tc_mode = 0;            // 0 auto, 1 stream operand tiles, 2 keep them resident when they fit
@@ -76,6 +81,7 @@ struct at_kmeans {
     // passes the same (x, n_local) -- the rows must not change between at_kmeans_begin and the last accumulate
     at_tc_rows rows;
     float *rows_sx = nullptr;   // device float: image scale, fixed by at_kmeans_begin from max |x|
+    float *rows_shift = nullptr;   // device (64): centering vector of the image = mean of the centroids when it was built
     bool rows_valid = false;
     // incremental update: the local sums / counts persist between accumulate calls (exact integers), so an iteration
     // only moves the rows whose label changed: -x from the old cluster, +x to the new one (same invariant on x as above)
@@ -124,7 +130,8 @@ __device__ __forceinline__ float l2_denominator(float sumsq) { return __fadd_rn(
 int assign_tc_prepare(at_index *ix, cudaStream_t st);
 int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32,
                      int64_t *labels64, float *dist, int exact_dist, at_tc_rows *rows, cudaStream_t st);
-int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, cudaStream_t st);
+int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, const float *shift, cudaStream_t st);
+int tc_mean(const float *c, int k, float *shift, cudaStream_t st);   // shift = mean of the k centroids (d == 64)
 void tc_rows_free(at_tc_rows *r);
 bool assign_tc_supported(const at_index *ix);
 // at_conv.cu: exact fp32 search for rows wider than 128 values (pre-normalised rows)

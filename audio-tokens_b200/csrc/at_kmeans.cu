@@ -46,10 +46,12 @@ __global__ void k_row_l2norm(const float *__restrict__ x, int64_t n, int d, floa
 // canonical |c|^2, one thread per centroid (k is small).  maxes (may be null): {max |c_ij|, max |c_j|^2} as float bit
 // patterns raised with atomicMax (non-negative floats order like their patterns; NaN patterns sort above every number,
 // so a non-finite centroid is seen by the consumer), consumed and reset by k_tc_scale.
+// maxes (tensor path, d == 64): {max |c_ij - m_i|, max |c_j - m|^2, max |c_j|^2} with m = shift, the centring vector of the
+// operand image (at_index.cuh).
 __global__ void k_centroid_norms(const float *__restrict__ c, int k, int d, float *__restrict__ cn,
-                                 unsigned int *__restrict__ maxes) {
+                                 unsigned int *__restrict__ maxes, const float *__restrict__ shift) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    float m = 0.f, n2 = 0.f;
+    float m = 0.f, n2 = 0.f, ns = 0.f;
     if (j < k) {
         float q[16];
 #pragma unroll
@@ -61,8 +63,12 @@ __global__ void k_centroid_norms(const float *__restrict__ c, int k, int d, floa
                 if (base + t < d) {
                     float v = cj[base + t];
                     q[(t >> 2) & 15] = fmaf(v, v, q[(t >> 2) & 15]);
-                    m = fmaxf(m, fabsf(v));
-                    if (!(v == v)) m = v;
+                    if (maxes) {
+                        const float vs = v - shift[base + t];
+                        ns = fmaf(vs, vs, ns);
+                        m = fmaxf(m, fabsf(vs));
+                        if (!(vs == vs)) m = vs;
+                    }
                 }
             }
         }
@@ -70,13 +76,14 @@ __global__ void k_centroid_norms(const float *__restrict__ c, int k, int d, floa
         cn[j] = n2;
     }
     if (maxes) {
-        unsigned int um = __float_as_uint(fabsf(m)), un = __float_as_uint(fabsf(n2));
+        unsigned int um = __float_as_uint(fabsf(m)), un = __float_as_uint(fabsf(ns)), uo = __float_as_uint(fabsf(n2));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             um = max(um, __shfl_xor_sync(0xffffffffu, um, o));
             un = max(un, __shfl_xor_sync(0xffffffffu, un, o));
+            uo = max(uo, __shfl_xor_sync(0xffffffffu, uo, o));
         }
-        if ((threadIdx.x & 31) == 0) atomicMax(maxes, um), atomicMax(maxes + 1, un);
+        if ((threadIdx.x & 31) == 0) atomicMax(maxes, um), atomicMax(maxes + 1, un), atomicMax(maxes + 2, uo);
     }
 }
 
@@ -584,6 +591,7 @@ int at_index_destroy(at_index *ix) {
     cudaFree(ix->op);
     cudaFree(ix->tc_scale);
     cudaFree(ix->tc_max);
+    cudaFree(ix->shift);
     cudaFree(ix->tc_counters);
     cudaFree(ix->part_lab);
     tc_rows_free(&ix->rows);
@@ -597,7 +605,12 @@ int at_index_destroy(at_index *ix) {
 // canonical norms + (d == 64) the tensor operands of the centroids currently in ix->c
 static int index_refresh(at_index *ix, cudaStream_t st) {
     const bool tc = assign_tc_supported(ix);
-    k_centroid_norms<<<(ix->k + 127) / 128, 128, 0, st>>>(ix->c, ix->k, ix->d, ix->cn, tc ? ix->tc_max : nullptr);
+    if (tc && !ix->ext_shift) {   // the index's own centring vector follows its centroids
+        int rc = tc_mean(ix->c, ix->k, ix->shift, st);
+        if (rc != AT_OK) return rc;
+    }
+    k_centroid_norms<<<(ix->k + 127) / 128, 128, 0, st>>>(ix->c, ix->k, ix->d, ix->cn, tc ? ix->tc_max : nullptr,
+                                                          ix->ext_shift ? ix->ext_shift : ix->shift);
     AT_LAUNCH_OK();
     if (tc) return assign_tc_prepare(ix, st);
     return AT_OK;
@@ -618,8 +631,12 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
         if (ix->d == 64) {
             AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 36864)   /* room for the hi | lo | aug form */);
             if (!ix->tc_max) {
-                AT_CUDA_OK(cudaMalloc(&ix->tc_max, 2 * sizeof(unsigned int)));
-                AT_CUDA_OK(cudaMemsetAsync(ix->tc_max, 0, 2 * sizeof(unsigned int), st));
+                AT_CUDA_OK(cudaMalloc(&ix->tc_max, 4 * sizeof(unsigned int)));
+                AT_CUDA_OK(cudaMemsetAsync(ix->tc_max, 0, 4 * sizeof(unsigned int), st));
+            }
+            if (!ix->shift) {
+                AT_CUDA_OK(cudaMalloc(&ix->shift, 64 * sizeof(float)));
+                AT_CUDA_OK(cudaMemsetAsync(ix->shift, 0, 64 * sizeof(float), st));
             }
             if (!ix->tc_counters) {
                 AT_CUDA_OK(cudaMalloc(&ix->tc_counters, 8 * sizeof(unsigned long long)));
@@ -694,7 +711,7 @@ int at_kmeans_destroy(at_kmeans *km) {
     at_index_destroy(km->index);
     cudaFree(km->labels), cudaFree(km->order);
     cudaFree(km->off), cudaFree(km->cursor), cudaFree(km->hassign), cudaFree(km->newc), cudaFree(km->fin);
-    cudaFree(km->rows_sx);
+    cudaFree(km->rows_sx), cudaFree(km->rows_shift);
     tc_rows_free(&km->rows);
     cudaFree(km->lacc), cudaFree(km->prev), cudaFree(km->d_row), cudaFree(km->d_lab), cudaFree(km->d_order);
     cudaFree(km->d_count), cudaFree(km->d_hist);
@@ -772,6 +789,7 @@ int at_kmeans_begin_on(at_kmeans *km, float max_abs, int64_t n_total, void *stre
         k_set_float<<<1, 1, 0, st>>>(km->rows_sx, sx);
         AT_LAUNCH_OK();
         km->index->ext_sx = km->rows_sx;
+        km->index->ext_shift = nullptr;   // until the first accumulate builds the image and fixes its centre
         if (km->index->k > 0 && assign_tc_supported(km->index)) {
             int rc = index_refresh(km->index, st);
             if (rc != AT_OK) return rc;
@@ -833,7 +851,15 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     const bool tc = algo == AT_ALGO_TENSOR || (algo == AT_ALGO_AUTO && assign_tc_supported(km->index) && km->index->k >= 64);
     if (tc && assign_tc_supported(km->index) && km->rows_sx) {
         if (!km->rows_valid || km->rows.x != x || km->rows.n != n_local) {
-            rc = tc_rows_build(&km->rows, x, n_local, 0, km->rows_sx, st);
+            // centre of the image = mean of the centroids it is first searched with, fixed until the image is rebuilt;
+            // the index's operands are re-derived for it
+            if (!km->rows_shift) AT_CUDA_OK(cudaMalloc(&km->rows_shift, 64 * sizeof(float)));
+            rc = tc_mean(km->index->c, km->k, km->rows_shift, st);
+            if (rc != AT_OK) return rc;
+            km->index->ext_shift = km->rows_shift;
+            rc = index_refresh(km->index, st);
+            if (rc != AT_OK) return rc;
+            rc = tc_rows_build(&km->rows, x, n_local, 0, km->rows_sx, km->rows_shift, st);
             if (rc != AT_OK) return rc;
             km->rows_valid = true;
         }
@@ -919,12 +945,14 @@ int at_index_search_trained_rows(at_index *ix, at_kmeans *km, const float *x, in
     cudaStream_t st = (cudaStream_t)stream;
     // the image carries its own scale: re-derive this index's operands for it, search, and put the index back
     ix->ext_sx = km->rows_sx;
+    ix->ext_shift = km->rows_shift;
     int rc = index_refresh(ix, st);
     if (rc == AT_OK) {
         ProfScope prof(PROF_SEARCH, st);
         rc = assign_tc_search(ix, x, n, l2norm_rows, labels32, labels64, dist, 1, &km->rows, st);
     }
     ix->ext_sx = nullptr;
+    ix->ext_shift = nullptr;
     const int rc2 = index_refresh(ix, st);
     return rc != AT_OK ? rc : rc2;
 }
