@@ -198,8 +198,9 @@ class HotPath:
         host_chunks: iterable of pinned (nb <= chunk_clips, L) tensors, fp32 waveforms or int16 PCM, same L throughout.
         centroids: (k, d) fp32 CUDA tensor, unit-norm rows as ClusterCreator saves them.
         Yields (tokens int64 pinned host tensor (nb * T,), bad int32 pinned host tensor (nb,)) per chunk, in order; the
-        copy of chunk i+1 and the read-back of chunk i-1 overlap the kernels of chunk i.  The yielded tensors are
-        re-used two chunks later: consume (or copy) them before advancing twice."""
+        copy of chunk i+1 and the read-back of chunk i-1 overlap the kernels of chunk i.  The yielded tensors are views of
+        two pinned slots: the slot of the chunk just yielded is written again (asynchronously) as soon as the generator is
+        advanced, so consume or copy a result BEFORE asking for the next one."""
         import torch
 
         self.index.set_centroids(centroids)
