@@ -7,10 +7,10 @@
 //   normalize_spectrogram   -> (s - min s) / (max s - min s) over the clip
 //   check_for_nan_inf       -> bad flag
 //
-// Kernel shape (one persistent CTA per SM = two independent groups of 8 warps, clips dealt round-robin to the groups; a
-// group works through its clip in batches of 8 jobs and synchronises on its own named barrier, so one group's FFT phase
-// overlaps the other's mel / write-out phases):
-//   * the sample window of the next batch of frames (15 hops + n_fft samples at n_fft 1024, 34.8 KB) is fetched into
+// Kernel shape (one persistent CTA per SM = four independent groups of 4 warps, clips dealt round-robin to the groups; a
+// group works through its clip in batches of 4 jobs and synchronises on its own named barrier, so one group's FFT phase
+// overlaps the others' mel / write-out phases):
+//   * the sample window of the next batch of frames (7 hops + n_fft samples at n_fft 1024, 18.4 KB) is fetched into
 //     shared memory by one cp.async.bulk (TMA engine) while the current batch is in its mel / write-out phases, so
 //     overlapping frames are read from HBM once and no warp ever waits on DRAM (reflected edge frames read global memory);
 //   * a warp owns one "job": 1024 complex points = G complex FFTs of n_fft points, each packing TWO real
@@ -180,16 +180,25 @@ __device__ __forceinline__ int64_t reflect_index(int64_t s, int64_t L) {
 // A CTA holds MEL_GROUPS independent groups of MEL_WARPS warps.  Each group runs its own clips through its own
 // exchange / power / staging buffers and synchronises on its own named barrier, so one group's FFT phase overlaps the
 // other's mel projection, write-out and clip epilogue (one 16-warp group spends a third of its cycles at barriers).
-constexpr int MEL_GROUPS = 2;
-constexpr int MEL_WARPS = 8;                            // per group
+#ifndef AT_MEL_GROUPS
+// measured on B200 (tools/bench_mel.py, 1024 / 512 / 64): 2 groups x 8 warps 13.19 ms per 20,000 clips, 4 x 4 12.65 ms --
+// four phase streams per SM overlap the FMA-heavy FFT phase with the shared-memory-heavy mel / write-out phases better
+#define AT_MEL_GROUPS 4
+#define AT_MEL_WARPS 4
+#define AT_MEL_STAGE 4608   // staged sample window of a batch: (BF - 1) hops + n_fft samples at 1024 / 512 (8 frames)
+#define AT_MEL_WT 1536      // filterbank weights kept in shared memory when they fit (1024 / 64 needs ~1,300)
+#define AT_MEL_PAR 128
+#endif
+constexpr int MEL_GROUPS = AT_MEL_GROUPS;
+constexpr int MEL_WARPS = AT_MEL_WARPS;                 // per group
 constexpr int MEL_THREADS = MEL_WARPS * 32;             // per group
 constexpr int CTA_THREADS = MEL_GROUPS * MEL_THREADS;
 constexpr int XCH_STRIDE = 33;                          // floats per exchange row (32 + 1 pad)
 constexpr int XCH_WARP_F = 32 * XCH_STRIDE;             // floats per warp (real and imaginary parts go through in turn)
 constexpr int XCH_BYTES = MEL_WARPS * XCH_WARP_F * 4;   // 33,792 per group
-constexpr int STAGE_FLOATS = 8704;                      // staged sample window: 15 * 512 + 1024 samples (34,816 B) per group
-constexpr int WT_SMEM_FLOATS = 2048;                    // filterbank weights kept in shared memory when they fit
-constexpr int PAR_SMEM_MELS = 256;                      // filter parameters (first bin, groups of four, weight offset)
+constexpr int STAGE_FLOATS = AT_MEL_STAGE;                      // staged sample window: 15 * 512 + 1024 samples (34,816 B) per group
+constexpr int WT_SMEM_FLOATS = AT_MEL_WT;                    // filterbank weights kept in shared memory when they fit
+constexpr int PAR_SMEM_MELS = AT_MEL_PAR;                      // filter parameters (first bin, groups of four, weight offset)
 
 __device__ __forceinline__ void group_sync(int grp) {   // named barrier 1 + grp over the group's 256 threads
     asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(MEL_THREADS) : "memory");

@@ -279,6 +279,62 @@ def test_search_tensor_random_and_out_of_range_rows():
     _check_labels(lt.cpu().numpy(), x.cpu().numpy(), c.cpu().numpy(), "tensor randn")
 
 
+def test_search_tensor_on_badly_centred_data():
+    """The tensor path works on rows and centroids shifted by the centroid mean (the fp16 rounding errors then scale with
+    |x - m| |c - m|).  The shift is only a conditioning device: data for which it is useless or harmful -- two far-apart
+    blobs (the mean lies between them, far from every row), rows offset by a large constant, a single centroid cluster far
+    from the rows -- must still give the exact kernel's labels (certified, re-checked or scanned exactly)."""
+    import torch
+    from at_b200 import FlatL2, _lib
+
+    g = torch.Generator(device="cuda").manual_seed(21)
+    n, k = 20000, 512
+    blob = (torch.arange(n, device="cuda") % 2).float().reshape(-1, 1) * 40.0 - 20.0       # rows at -20 / +20
+    x1 = blob + torch.randn(n, 64, device="cuda", generator=g)
+    c1 = x1[torch.randperm(n, device="cuda", generator=g)[:k]].contiguous() + 0.05 * torch.randn(k, 64, device="cuda", generator=g)
+    x2 = 300.0 + torch.rand(n, 64, device="cuda", generator=g)                              # large common offset
+    c2 = x2[torch.randperm(n, device="cuda", generator=g)[:k]].contiguous() + 0.01
+    x3 = torch.rand(n, 64, device="cuda", generator=g)                                      # centroids far from the rows
+    c3 = 5.0 + 0.01 * torch.randn(k, 64, device="cuda", generator=g)
+    for name, x, c in (("blobs", x1, c1), ("offset", x2, c2), ("far", x3, c3)):
+        ix = FlatL2(64)
+        ix.set_centroids(c)
+        ls, _ = ix.search(x, algo=_lib.ALGO_SIMT)
+        lt, _ = ix.search(x, algo=_lib.ALGO_TENSOR)
+        mism = int((ls != lt).sum())
+        re, full = ix.tc_stats()
+        print(f"{name}: mismatches {mism}, re-checked {re}, exact scans {full}")
+        # (no oracle gate here: with |x|^2 >> |x - c|^2 the expanded fp32 formula itself is ill-conditioned and two correct
+        # evaluations of it differ in their summation order; the claim under test is tensor path == exact kernel)
+        assert mism == 0, name
+
+
+def test_lloyd_tensor_image_centre_survives_moving_centroids():
+    """k-means builds the row image once, centred on the mean of the INITIAL centroids; the centroids then move away from it
+    (here: initial centroids taken from one corner of the data).  Labels stay the exact kernel's in every iteration."""
+    import torch
+    from at_b200 import LloydTrainer, _lib
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, k = 30000, 96
+    x = torch.cat([torch.randn(n // 2, 64, device="cuda", generator=g) * 0.3,
+                   4.0 + torch.randn(n // 2, 64, device="cuda", generator=g) * 0.3]).contiguous()
+    init = x[:k].contiguous()   # every initial centroid in the first blob
+    outs = []
+    for algo in (_lib.ALGO_SIMT, _lib.ALGO_TENSOR):
+        tr = LloydTrainer(64, k, algo=algo)
+        tr.begin(x)
+        tr.set_centroids(init)
+        labels = torch.empty(n, dtype=torch.int32, device="cuda")
+        traj = []
+        for _ in range(6):
+            tr.step(x, None, labels)
+            traj.append((labels.clone(), tr.get_centroids()))
+        outs.append(traj)
+    for (la, ca), (lb, cb) in zip(*outs):
+        assert torch.equal(la, lb) and torch.equal(ca, cb)
+
+
 def test_lloyd_tensor_vs_simt_bit_identical_centroids():
     """Same labels + exact integer sums => the two search paths give bit-identical k-means trajectories."""
     import torch

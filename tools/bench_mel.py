@@ -19,5 +19,8 @@ for _ in range(5):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
+import hashlib
+spec, bad, l2 = plan.forward(w[:64].contiguous(), want_l2=True)
+print("digest spec", hashlib.sha1(spec.cpu().numpy().tobytes()).hexdigest()[:16], "l2", hashlib.sha1(l2.cpu().numpy().tobytes()).hexdigest()[:16])
 print(f"lib {_lib.LIB_PATH}: mel {n} clips: {ms:.3f} ms -> {n * 431 / ms / 1e3:.1f} M frames/s; {ms * 20000 / n:.2f} ms per 20,000 clips; "
       f"{n * 992336 / ms / 1e6:.0f} GB/s algorithmic")
