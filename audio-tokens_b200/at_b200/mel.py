@@ -61,6 +61,10 @@ class MelPlan:
     def num_frames(self, n_samples: int) -> int:
         return 1 + n_samples // self.hop
 
+    def work_groups(self) -> int:
+        """Independent clip streams of one launch (at_mel_work_groups): size streaming chunks as a multiple of it."""
+        return int(self.lib.at_mel_work_groups(self.h))
+
     def forward(self, wave, out=None, out_l2=None, want_l2: bool = False):
         """Uniform batch: wave (B, L) fp32 CUDA -> (spec [B, T, n_mels] frame-major, bad_flags [B] int32[, l2])."""
         import torch

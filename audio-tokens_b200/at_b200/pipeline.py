@@ -127,7 +127,7 @@ class HotPath:
         done.record(mel_stream)
         return done
 
-    def run_host(self, wave_host, bufs, chunk_clips=296, row_offset=0, n_total=None):
+    def run_host(self, wave_host, bufs, chunk_clips=None, row_offset=0, n_total=None):
         """End to end from HOST memory: wave_host (B, L) pinned tensor, fp32 waveforms or the decoder's int16 PCM (half
         the PCIe bytes; widened on the device with at_pcm16_to_f32, bufs from alloc_bufs(..., pcm16=True)).  Chunks are
         copied H2D on a copy stream while the mel kernel works on the previous chunk; tokens (int64) and centroids are
@@ -138,6 +138,8 @@ class HotPath:
         B = wave_host.shape[0]
         main = torch.cuda.current_stream()
         bad = torch.zeros(B, dtype=torch.int32, device="cuda")
+        if chunk_clips is None:
+            chunk_clips = bufs["stage"].shape[1]   # what alloc_bufs sized the staging buffers for
         self._ingest(wave_host, bufs, bad, chunk_clips, main)
         tok, cents = self.cluster_and_tokenize(bufs["spec"], bufs["l2"], row_offset, n_total, None, bufs.get("tokens"))
         bufs["tokens_host"].copy_(tok, non_blocking=True)
@@ -146,7 +148,7 @@ class HotPath:
         main.synchronize()
         return bufs["tokens_host"], bufs["centroids_host"], bufs["bad_host"]
 
-    def run_host_stream(self, batches, bufs_pair, chunk_clips=296, row_offset=0, n_total=None):
+    def run_host_stream(self, batches, bufs_pair, chunk_clips=None, row_offset=0, n_total=None):
         """The same end-to-end step for a SEQUENCE of host batches (each one a full k-means + tokenize job, e.g. one split
         or one day's clips): the H2D copy and the mel transform of batch i+1 run on side streams while batch i goes through
         k-means and tokenization, so in steady state a step costs max(PCIe time, device time) instead of their sum.
@@ -169,7 +171,7 @@ class HotPath:
             # everything queued on the main stream so far is older than this batch: the previous occupant of the slot has
             # been read back (its result event was synchronised before it was yielded), `bad` has been zeroed
             mel_stream.wait_stream(main)
-            return bufs, bad, self._ingest(batch, bufs, bad, chunk_clips, mel_stream)
+            return bufs, bad, self._ingest(batch, bufs, bad, chunk_clips or bufs["stage"].shape[1], mel_stream)
 
         slot = 0
         first = next(it, None)
@@ -191,11 +193,13 @@ class HotPath:
             bufs["result_event"].synchronize()
             yield bufs["tokens_host"], bufs["centroids_host"], bufs["bad_host"]
 
-    def stream_tokenize(self, host_chunks, centroids, chunk_clips=296):
+    def stream_tokenize(self, host_chunks, centroids, chunk_clips=None):
         """Spectrogram -> tokens for a stream of HOST chunks with fixed centroids (the unbalanced-train shape: far more
         clips than fit in HBM, SpectrogramGenerator.run + SpecTokenizer.run without the spectrogram files in between).
 
-        host_chunks: iterable of pinned (nb <= chunk_clips, L) tensors, fp32 waveforms or int16 PCM, same L throughout.
+        host_chunks: iterable of pinned (nb <= chunk_clips, L) tensors, fp32 waveforms or int16 PCM, same L throughout
+        (chunk_clips defaults to the first chunk's clip count; a multiple of MelPlan.work_groups() keeps every mel launch
+        balanced).
         centroids: (k, d) fp32 CUDA tensor, unit-norm rows as ClusterCreator saves them.
         Yields (tokens int64 pinned host tensor (nb * T,), bad int32 pinned host tensor (nb,)) per chunk, in order; the
         copy of chunk i+1 and the read-back of chunk i-1 overlap the kernels of chunk i.  The yielded tensors are views of
@@ -210,6 +214,8 @@ class HotPath:
         prev = None
         for ci, chunk in enumerate(host_chunks):
             nb, L = chunk.shape
+            if chunk_clips is None:
+                chunk_clips = nb   # capacity of the staging slots = the first chunk's clip count
             assert nb <= chunk_clips
             pcm16 = chunk.dtype == torch.int16
             T = self.plan.num_frames(L)
@@ -265,11 +271,13 @@ class HotPath:
             T = self.plan.num_frames(st["L"])
             yield st["tok_h"][psb, :pn * T], st["bad_h"][psb, :pn]
 
-    def alloc_bufs(self, B, L, host=False, chunk_clips=296, pcm16=False, device_outputs=True):
+    def alloc_bufs(self, B, L, host=False, chunk_clips=None, pcm16=False, device_outputs=True):
         """device_outputs=False leaves out spec / l2 / tokens (the caller plugs in buffers it already owns)."""
         import torch
 
         T = self.plan.num_frames(L)
+        if chunk_clips is None:
+            chunk_clips = self.plan.work_groups()   # a balanced mel launch per staged chunk
         bufs = {}
         if device_outputs:
             bufs.update(

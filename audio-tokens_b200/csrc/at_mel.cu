@@ -807,6 +807,12 @@ int at_mel_plan_destroy(at_mel_plan *p) {
     return AT_OK;
 }
 
+int at_mel_work_groups(const at_mel_plan *p) {
+    (void)p;
+    const int sms = sm_count();
+    return (sms > 0 ? sms : 1) * MEL_GROUPS;
+}
+
 int64_t at_mel_num_frames(const at_mel_plan *p, int64_t n_samples) {
     if (!p || n_samples < 0) return -1;
     return 1 + n_samples / p->hop;

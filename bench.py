@@ -453,9 +453,10 @@ def config_c5(hp_plan_args, wave, clips_target, world, pk):
     from at_b200 import row_l2norm
     from at_b200.pipeline import HotPath
 
-    K, CH = 4096, 296
+    K = 4096
     T = 1 + CLIP_SAMPLES // HOP
     hp = HotPath(SR, N_FFT, HOP, N_MELS, True, K, 1)
+    CH = hp.plan.work_groups()   # clips per streamed chunk: one per clip stream of a mel launch
     spec, _, l2 = hp.mel(wave[:2000].contiguous())
     rows = l2.reshape(-1, N_MELS)
     g = torch.Generator("cuda").manual_seed(11)
@@ -840,10 +841,11 @@ def run_b200(args):
                     "launches": n_search, "avg_ms": ms_search / max(n_search, 1),
                     "algorithmic_flops_per_launch": flops,
                     "note": "algorithmic 2*N*K*D flops; the kernel executes 1.25x as many fp16 MMA flops (four K steps + "
-                            "one K step carrying the norms); the accumulator scan (1.25 min/max per score on the alu pipe, "
-                            "81 % busy) and the 1 kW power cap (SM clock ~1.65 GHz inside the kernel) bind, not the tensor "
-                            "pipe (62 % busy; profiles/); avg_ms covers every launch of a search (row image when rebuilt + "
-                            "scan + candidate re-check + exact scan of the rest); peak = bf16 sustained, " + pk["source"]}
+                            "one K step carrying the norms); the accumulator scan (1.26 min/max per score on the alu pipe, "
+                            "81 % busy) and the 1 kW power cap (SM clock ~1.62 GHz inside the kernel) bind, not the tensor "
+                            "pipe (64 % busy; profiles/r02_ncu_full_summary.txt); avg_ms covers every launch of a search "
+                            "(row image when rebuilt + scan + candidate re-check of 1.4 % of the rows + exact scan of 0.02 "
+                            "%); peak = bf16 sustained, " + pk["source"]}
         n_mel, ms_mel = prof["mel"]
         n_upd, ms_upd = prof["update"]
         mel_bytes = B * (L * 4 + T * N_MELS * 4)

@@ -82,6 +82,9 @@ int at_mel_plan_set_output(at_mel_plan *plan, int kind);
 int at_mel_plan_destroy(at_mel_plan *plan);
 /* 1 + n_samples / hop_length (center=True). */
 int64_t at_mel_num_frames(const at_mel_plan *plan, int64_t n_samples);
+/* Number of independent clip streams one launch works on (SMs x warp groups per CTA): a launch is balanced when its
+ * clip count is a multiple of this (or much larger), which is how callers should size streaming chunks. */
+int at_mel_work_groups(const at_mel_plan *plan);
 
 /* B clips.  Clip b occupies wave[sample_offsets[b] .. sample_offsets[b+1]) and writes frames
  * out[frame_offsets[b] .. frame_offsets[b+1]) x n_mels, FRAME-MAJOR ([T][n_mels], the physical layout of
