@@ -31,6 +31,7 @@ PROTOTYPES = {
     "at_mel_plan_destroy": (c_int, [c_ptr]),
     "at_mel_num_frames": (c_i64, [c_ptr, c_i64]),
     "at_mel_work_groups": (c_int, [c_ptr]),
+    "at_mel_plan_set_absmax_out": (c_int, [c_ptr, c_ptr]),
     "at_mel_forward": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "at_mel_forward_host": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     "at_amplitude_to_db": (c_int, [c_ptr, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr]),

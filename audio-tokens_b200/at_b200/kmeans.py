@@ -168,14 +168,17 @@ class LloydTrainer:
         except Exception:
             pass
 
-    def begin(self, x_local, n_total: int | None = None):
-        """Fix the fixed-point scale from the global max |x| and row count. One host sync."""
+    def begin(self, x_local, n_total: int | None = None, absmax=None):
+        """Fix the fixed-point scale from the global max |x| and row count. One host sync.  absmax: CUDA float32[1] already
+        holding max |x_local| (the mel kernel produces it on the way out, MelPlan.set_absmax_out); None = scan the rows."""
         import torch
 
         dist, _, world = _world(self.group)
         self._rows_key = self._key(x_local)
         if x_local.numel() == 0:   # a shard left empty by the subsample: nothing to scan (at_absmax rejects a null pointer)
             self._absmax.zero_()
+        elif absmax is not None:
+            self._absmax.copy_(absmax.reshape(self._absmax.shape))
         else:
             _lib.check(self.lib.at_absmax(_lib.ptr(x_local), x_local.numel(), _lib.ptr(self._absmax), _lib.stream_ptr()))
         if world > 1:

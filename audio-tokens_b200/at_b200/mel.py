@@ -61,6 +61,11 @@ class MelPlan:
     def num_frames(self, n_samples: int) -> int:
         return 1 + n_samples // self.hop
 
+    def set_absmax_out(self, t):
+        """Attach (or detach with None) a CUDA float32[1] tensor that every forward writing the L2-normalised copy raises to
+        the largest |element| written (at_mel_plan_set_absmax_out); the caller zeroes it."""
+        _lib.check(self.lib.at_mel_plan_set_absmax_out(self.h, _lib.ptr(t)))
+
     def work_groups(self) -> int:
         """Independent clip streams of one launch (at_mel_work_groups): size streaming chunks as a multiple of it."""
         return int(self.lib.at_mel_work_groups(self.h))

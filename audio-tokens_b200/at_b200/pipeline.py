@@ -35,11 +35,21 @@ class HotPath:
             self._init_rows[n_total] = rand_perm(n_total, self.seed + 1)[: self.k].astype(np.int64)
         return self._init_rows[n_total]
 
-    def mel(self, wave, spec=None, l2=None):
-        return self.plan.forward(wave, out=spec, out_l2=l2, want_l2=True)
+    def mel(self, wave, spec=None, l2=None, absmax=None):
+        """absmax: CUDA float32[1] that receives max |element| of the L2-normalised copy (what k-means' begin needs), computed
+        by the mel kernel on the way out instead of by a separate pass over the rows."""
+        if absmax is None:
+            return self.plan.forward(wave, out=spec, out_l2=l2, want_l2=True)
+        absmax.zero_()
+        self.plan.set_absmax_out(absmax)
+        try:
+            return self.plan.forward(wave, out=spec, out_l2=l2, want_l2=True)
+        finally:
+            self.plan.set_absmax_out(None)
 
-    def kmeans(self, l2_rows, row_offset=0, n_total=None, stats=None):
-        """Lloyd iterations over this rank's L2-normalised rows (n_local, d). Returns device centroids (k, d)."""
+    def kmeans(self, l2_rows, row_offset=0, n_total=None, stats=None, absmax=None):
+        """Lloyd iterations over this rank's L2-normalised rows (n_local, d). Returns device centroids (k, d).
+        absmax: see mel()."""
         import torch
         import torch.distributed as dist
 
@@ -53,7 +63,7 @@ class HotPath:
         cent.index_copy_(0, idx, l2_rows.index_select(0, src))
         if self.group is not False and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(cent, group=self.group or None)
-        self.trainer.begin(l2_rows, n_total)
+        self.trainer.begin(l2_rows, n_total, absmax=absmax)
         self.trainer.set_centroids(cent)
         for it in range(self.niter):
             self.trainer.step(l2_rows, None if stats is None else stats[it])
@@ -77,20 +87,25 @@ class HotPath:
         return lab
 
     # -- whole path ------------------------------------------------------------------------------
-    def cluster_and_tokenize(self, spec, l2, row_offset=0, n_total=None, stats=None, tokens=None):
+    def cluster_and_tokenize(self, spec, l2, row_offset=0, n_total=None, stats=None, tokens=None, absmax=None):
         """spec / l2: (B, T, d) device tensors from mel().  Returns (tokens int64 (B*T,), unit-norm centroids)."""
         from . import row_l2norm
 
-        cents = self.kmeans(l2.reshape(-1, self.d), row_offset, n_total, stats)
+        cents = self.kmeans(l2.reshape(-1, self.d), row_offset, n_total, stats, absmax=absmax)
         cents = row_l2norm(cents)  # ClusterCreator saves normalize_vectors(kmeans.centroids) (cluster_creator.py:58-61)
         tok = self.tokenize(spec.reshape(-1, self.d), cents, tokens, trained_rows=True)   # l2 is spec's normalised copy
         return tok, cents
 
     def run_device(self, wave, bufs=None, row_offset=0, n_total=None, stats=None):
         """wave (B, L) fp32 CUDA.  Returns (tokens int64 (B*T,), centroids (k, d), bad (B,))."""
+        import torch
+
         bufs = bufs or {}
-        spec, bad, l2 = self.mel(wave, bufs.get("spec"), bufs.get("l2"))
-        tok, cents = self.cluster_and_tokenize(spec, l2, row_offset, n_total, stats, bufs.get("tokens"))
+        absmax = bufs.get("absmax")
+        if absmax is None:
+            absmax = torch.zeros(1, dtype=torch.float32, device=wave.device)
+        spec, bad, l2 = self.mel(wave, bufs.get("spec"), bufs.get("l2"), absmax=absmax)
+        tok, cents = self.cluster_and_tokenize(spec, l2, row_offset, n_total, stats, bufs.get("tokens"), absmax=absmax)
         return tok, cents, bad
 
     def _ingest(self, wave_host, bufs, bad, chunk_clips, mel_stream):
@@ -107,6 +122,11 @@ class HotPath:
         copy.wait_stream(mel_stream)
         ev_free = [None, None]
         sp = _lib.ctypes_stream(mel_stream)
+        absmax = bufs.get("absmax")   # raised by every chunk's mel launch (k-means' begin reads it instead of scanning l2)
+        if absmax is not None:
+            with torch.cuda.stream(mel_stream):
+                absmax.zero_()
+            self.plan.set_absmax_out(absmax)
         for ci, b0 in enumerate(range(0, B, chunk_clips)):
             nb = min(chunk_clips, B - b0)
             sb = ci & 1
@@ -123,6 +143,8 @@ class HotPath:
                                                     _lib.ptr(spec[b0:]), _lib.ptr(l2[b0:]), _lib.ptr(bad[b0:]), sp))
             ev_free[sb] = torch.cuda.Event()
             ev_free[sb].record(mel_stream)
+        if absmax is not None:
+            self.plan.set_absmax_out(None)
         done = torch.cuda.Event()
         done.record(mel_stream)
         return done
@@ -141,7 +163,8 @@ class HotPath:
         if chunk_clips is None:
             chunk_clips = bufs["stage"].shape[1]   # what alloc_bufs sized the staging buffers for
         self._ingest(wave_host, bufs, bad, chunk_clips, main)
-        tok, cents = self.cluster_and_tokenize(bufs["spec"], bufs["l2"], row_offset, n_total, None, bufs.get("tokens"))
+        tok, cents = self.cluster_and_tokenize(bufs["spec"], bufs["l2"], row_offset, n_total, None, bufs.get("tokens"),
+                                               absmax=bufs.get("absmax"))
         bufs["tokens_host"].copy_(tok, non_blocking=True)
         bufs["centroids_host"].copy_(cents, non_blocking=True)
         bufs["bad_host"].copy_(bad, non_blocking=True)
@@ -184,7 +207,8 @@ class HotPath:
             slot ^= 1
             pend = start(nxt, slot) if nxt is not None else None
             main.wait_event(ev)
-            tok, cents = self.cluster_and_tokenize(bufs["spec"], bufs["l2"], row_offset, n_total, None, bufs.get("tokens"))
+            tok, cents = self.cluster_and_tokenize(bufs["spec"], bufs["l2"], row_offset, n_total, None, bufs.get("tokens"),
+                                                   absmax=bufs.get("absmax"))
             bufs["tokens_host"].copy_(tok, non_blocking=True)
             bufs["centroids_host"].copy_(cents, non_blocking=True)
             bufs["bad_host"].copy_(bad, non_blocking=True)
@@ -284,6 +308,7 @@ class HotPath:
                 spec=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
                 l2=torch.empty((B, T, self.d), dtype=torch.float32, device="cuda"),
                 tokens=torch.empty(B * T, dtype=torch.int64, device="cuda"),
+                absmax=torch.zeros(1, dtype=torch.float32, device="cuda"),
             )
         if host:
             bufs.update(

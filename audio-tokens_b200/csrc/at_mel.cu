@@ -37,6 +37,7 @@
 struct at_mel_plan {
     int sample_rate = 0, n_fft = 0, hop = 0, n_mels = 0, normalize = 0;
     int power_out = 0;        // 1: write the mel POWER (MelSpectrogram alone), 0: dB (MelSpectrogram + AmplitudeToDB)
+    float *absmax_out = nullptr;   // device float raised (atomicMax) to the largest |element| of the L2-normalised copy
     int log2nf = 0;
     // device constants
     float *win = nullptr;     // n_fft
@@ -245,7 +246,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
       int normalize, int power_out, const float *__restrict__ g_win, const float2 *__restrict__ g_tw,
       const int *__restrict__ fstart, const int *__restrict__ fcnt, const int *__restrict__ woff,
       const float *__restrict__ wt, int wt_count, float *__restrict__ out, float *__restrict__ out_l2,
-      int32_t *__restrict__ bad_flags) {
+      int32_t *__restrict__ bad_flags, unsigned int *__restrict__ absmax_bits) {
     using C = MelCfg<LOG2NF>;
     constexpr int NF = C::NF, N2 = C::N2, G = C::G, FR = C::FR, BF = C::BF, PS = C::PS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -345,6 +346,7 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
     uint32_t stage_phase = 0;
     float vmin = INFINITY, vmax = -INFINITY;
     int nonfinite = 0;
+    float l2max = 0.f;   // largest |element| this thread wrote to the L2-normalised copy (k-means' fixed-point scale)
 
     while (have) {
         const float *x = wave + cur.s0;
@@ -567,9 +569,12 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                             q = v.x * v.x;
                             q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
                             const float den = l2_denominator(half16_sum(q));
-                            if (on)
-                                *reinterpret_cast<float4 *>(out_l2 + (cur.f0 + r) * n_mels + 4 * g) =
-                                    make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
+                            if (on) {
+                                const float4 o4 = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den),
+                                                              __fdiv_rn(v.w, den));
+                                l2max = fmaxf(fmaxf(l2max, fmaxf(fabsf(o4.x), fabsf(o4.y))), fmaxf(fabsf(o4.z), fabsf(o4.w)));
+                                *reinterpret_cast<float4 *>(out_l2 + (cur.f0 + r) * n_mels + 4 * g) = o4;
+                            }
                         }
                         continue;
                     }
@@ -603,10 +608,12 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 const int base = 4 * g + 64 * j;
-                                if (live && base < n_mels)
-                                    *reinterpret_cast<float4 *>(orow + base) =
-                                        make_float4(__fdiv_rn(v[j].x, den), __fdiv_rn(v[j].y, den), __fdiv_rn(v[j].z, den),
-                                                    __fdiv_rn(v[j].w, den));
+                                if (live && base < n_mels) {
+                                    const float4 o4 = make_float4(__fdiv_rn(v[j].x, den), __fdiv_rn(v[j].y, den),
+                                                                  __fdiv_rn(v[j].z, den), __fdiv_rn(v[j].w, den));
+                                    l2max = fmaxf(fmaxf(l2max, fmaxf(fabsf(o4.x), fabsf(o4.y))), fmaxf(fabsf(o4.z), fabsf(o4.w)));
+                                    *reinterpret_cast<float4 *>(orow + base) = o4;
+                                }
                             }
                         }
                         continue;
@@ -635,7 +642,11 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
 #pragma unroll
                                 for (int e = 0; e < 4; e++) {
                                     // final value of the row (this thread wrote it just above when normalising)
-                                    if (base + e < n_mels) orow[base + e] = __fdiv_rn(__ldcg(row + base + e), den);
+                                    if (base + e < n_mels) {
+                                        const float o1 = __fdiv_rn(__ldcg(row + base + e), den);
+                                        l2max = fmaxf(l2max, fabsf(o1));
+                                        orow[base + e] = o1;
+                                    }
                                 }
                             }
                         }
@@ -643,6 +654,11 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 }
             }
             if (nonfinite) s_flag = 1;
+            if (absmax_bits && out_l2) {   // non-negative floats order like their bit patterns; NaNs never raise fmaxf
+                l2max = warp_max(l2max);
+                if (lane == 0 && l2max > 0.f) atomicMax(absmax_bits, __float_as_uint(l2max));
+                l2max = 0.f;
+            }
             group_sync(grp);
             if (tid == 0 && bad_flags) bad_flags[cur.clip] = s_flag;
             group_sync(grp);
@@ -739,7 +755,7 @@ static int launch_mel(at_mel_plan *p, const float *wave, const int64_t *so, cons
     ProfScope prof(PROF_MEL, st);
     k_mel<LOG2NF><<<grid, CTA_THREADS, C::SMEM, st>>>(wave, so, fo, us, B, p->hop, p->n_mels, p->normalize, p->power_out, p->win,
                                                      p->tw, p->fstart, p->fcnt, p->woff, p->wt, p->wt_count, out, out_l2,
-                                                     bad);
+                                                     bad, reinterpret_cast<unsigned int *>(p->absmax_out));
     AT_LAUNCH_OK();
     return AT_OK;
 }
@@ -804,6 +820,12 @@ int at_mel_plan_destroy(at_mel_plan *p) {
         if (p->streams[i]) cudaStreamDestroy(p->streams[i]);
     }
     delete p;
+    return AT_OK;
+}
+
+int at_mel_plan_set_absmax_out(at_mel_plan *p, float *absmax_dev) {
+    AT_REQUIRE(p, "at_mel_plan_set_absmax_out: null plan");
+    p->absmax_out = absmax_dev;
     return AT_OK;
 }
 

@@ -567,10 +567,11 @@ def run_b200(args):
     def step(ev=None):
         if ev:
             ev[0].record()
-        spec, bad, l2 = hp.mel(wave, bufs["spec"], bufs["l2"])
+        # (the mel kernel also leaves max |normalised element| in bufs["absmax"]: k-means' begin reads it instead of scanning)
+        spec, bad, l2 = hp.mel(wave, bufs["spec"], bufs["l2"], absmax=bufs["absmax"])
         if ev:
             ev[1].record()
-        cents = hp.kmeans(l2.reshape(-1, N_MELS), row_offset, n_total)
+        cents = hp.kmeans(l2.reshape(-1, N_MELS), row_offset, n_total, absmax=bufs["absmax"])
         from at_b200 import row_l2norm
 
         cents = row_l2norm(cents)
@@ -679,7 +680,7 @@ def run_b200(args):
                 wave_host = torch.empty((B, L), dtype=torch.float32, pin_memory=True)
                 wave_host.copy_(wave)
             hb1 = hp.alloc_bufs(B, L, host=True, pcm16=pcm16, device_outputs=False)
-            hb1["spec"], hb1["l2"], hb1["tokens"] = bufs["spec"], bufs["l2"], bufs["tokens"]
+            hb1["spec"], hb1["l2"], hb1["tokens"], hb1["absmax"] = bufs["spec"], bufs["l2"], bufs["tokens"], bufs["absmax"]
             hb2 = hp.alloc_bufs(B, L, host=True, pcm16=pcm16)
         except Exception as ex:
             err = ex
@@ -767,10 +768,10 @@ def run_b200(args):
             def step_s(ev=None):
                 if ev:
                     ev[0].record()
-                spec_s, _, l2_s = hp_s.mel(wave_s, bs["spec"], bs["l2"])
+                spec_s, _, l2_s = hp_s.mel(wave_s, bs["spec"], bs["l2"], absmax=bs["absmax"])
                 if ev:
                     ev[1].record()
-                hp_s.cluster_and_tokenize(spec_s, l2_s, rank * Bs * T, nts, None, bs["tokens"])
+                hp_s.cluster_and_tokenize(spec_s, l2_s, rank * Bs * T, nts, None, bs["tokens"], absmax=bs["absmax"])
                 if ev:
                     ev[2].record()
 

@@ -85,6 +85,10 @@ int64_t at_mel_num_frames(const at_mel_plan *plan, int64_t n_samples);
 /* Number of independent clip streams one launch works on (SMs x warp groups per CTA): a launch is balanced when its
  * clip count is a multiple of this (or much larger), which is how callers should size streaming chunks. */
 int at_mel_work_groups(const at_mel_plan *plan);
+/* While absmax_dev (device float, zeroed by the caller) is attached, every forward that writes the L2-normalised copy
+ * raises it to the largest |element| written: the value at_kmeans_begin needs (normalize_vectors' output range,
+ * processors/cluster_creator.py:52-56,64-66), without a separate at_absmax pass over the rows.  NULL detaches. */
+int at_mel_plan_set_absmax_out(at_mel_plan *plan, float *absmax_dev);
 
 /* B clips.  Clip b occupies wave[sample_offsets[b] .. sample_offsets[b+1]) and writes frames
  * out[frame_offsets[b] .. frame_offsets[b+1]) x n_mels, FRAME-MAJOR ([T][n_mels], the physical layout of
