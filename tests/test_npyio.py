@@ -74,9 +74,12 @@ def test_spec_tokenizer_process_batch_splits_tokens_per_file(tmp_path):
             lab = np.arange(x.shape[0], dtype=np.int64)[:, None]   # token = global frame number: easy to check
             return np.zeros((x.shape[0], 1), dtype=np.float32), lab
 
+    import types
+
     st = object.__new__(SpecTokenizer)
     st.index = FakeIndex()
     st.logger = logging.getLogger("test")
+    st.config = types.SimpleNamespace(use_convolution=False)   # process_batch reads it like the reference's (:70)
     flat = st.process_batch(files, dst)
     lengths = [np.load(f).shape[1] for f in files]
     assert flat == list(range(sum(lengths)))
