@@ -56,7 +56,7 @@ def _trained_centroids(x, k, iters):
     return tr.get_centroids()
 
 
-@pytest.mark.parametrize("k,sample", [(1024, 200_000), (16384, 16_000)])
+@pytest.mark.parametrize("k,sample", [(1024, 200_000), (1000, 50_000), (4133, 20_000), (16384, 16_000)])   # 1000, 4133: padded last tile
 def test_tensor_search_equals_exact_search_on_every_row_and_the_oracle_on_a_sample(rows, k, sample):
     import torch
     from at_b200 import FlatL2, _lib
