@@ -4,14 +4,21 @@
 // processors/spec_tokenizer.py:77 and, inside faiss.Kmeans.train, processors/cluster_creator.py:54-56).
 //
 // Four kernels:
-//   k_tc_rows    rows (fp32) -> optional L2 normalisation -> the fp16 operand image of the rows, laid out exactly as the
-//                tensor core reads it (128-row tiles: 128x64 K-major SWIZZLE_128B + a 128x16 tile carrying |x|^2), plus
-//                per row the norm of the fp16 rounding error |delta| and |x|^2.  K-means builds it ONCE per training set
-//                and re-uses it for every Lloyd iteration (the rows do not change); a one-off search builds it per call.
-//   k_assign_tc  distances + scan (below).  Certifies 93-97 % of the rows from the accumulators.
-//   k_tc_tail    uncertified rows with a candidate list (5-7 %): canonical fp32 re-evaluation of <= 4 columns, a
-//                16-lane group per row.
-//   k_tc_full    the remaining rows (0.1-0.5 %): exact scan of every centroid.
+//   k_tc_rows    rows (fp32) -> optional L2 normalisation -> minus the centring vector m -> the fp16 operand image of the
+//                rows, laid out exactly as the tensor core reads it (128-row tiles: 128x64 K-major SWIZZLE_128B + a 128x16
+//                tile carrying |x - m|^2), plus per row the norm of the fp16 rounding error |delta| and Sx^2 |x - m|^2.
+//                K-means builds it ONCE per training set and re-uses it for every Lloyd iteration (the rows do not
+//                change); a one-off search builds it per call.
+//   k_assign_tc  distances + scan (below).  Certifies ~98.6 % of the rows from the accumulators (benchmark data).
+//   k_tc_tail    uncertified rows with a candidate list (~1.4 %): canonical fp32 re-evaluation of <= 4 columns, a
+//                16-lane group per row, one block per candidate queue (a queue per scanning warp of k_assign_tc).
+//   k_tc_full    the remaining rows (~0.02 %): exact scan of every centroid (packed fp32).
+//
+// Centring.  |x - c|^2 = |(x - m) - (c - m)|^2 for any vector m; the operands are the SHIFTED rows and centroids
+// (x' = x - m, c' = c - m, m = mean of the centroids: at_index.cuh), because every rounding error below scales with
+// |x'| |c'| instead of |x| |c| (L2-normalised mel frames: |x| = 1, |x'| ~ 0.3).  In what follows x, c, d stand for the
+// shifted quantities; the tail kernels evaluate the UNSHIFTED rows and centroids with the canonical formula, whose own
+// resolution is part of the threshold.
 //
 // Arithmetic.  For a tile of 128 rows x 128 centroids the tensor core evaluates, in ONE chain of 5 tcgen05.mma
 // (kind::f16, fp32 accumulate in TMEM),
@@ -37,7 +44,8 @@
 // the second smallest COLUMN of a row is exactly min(second A minimum, second B minimum): a runner-up can hide behind the
 // winner in one grouping, never in both.
 //
-// Certification (per row, accumulator units):  tau = 1.0625 (tau_abs + 4 S|delta| sqrt(ub) + 2 |x~| e_max)
+// Certification (per row, accumulator units):
+//   tau = 1.0625 (tau_abs + 4 S|delta| sqrt(ub) + 2 |x~| e_max + 2^-19 S^2 (|x| + |c|)^2 [unshifted: the canonical formula])
 //   second smallest column further than tau from the best -> the best column is the argmin: label final.
 //   else, third A minimum and third B minimum both further than tau -> every column within reach lies where one of the
 //   two best A groups meets one of the two best B classes: <= 4 columns, re-evaluated by k_tc_tail with the library's
@@ -49,7 +57,7 @@
 // exact cluster sums).
 //
 // Roofline note: 2*N*K*64 algorithmic flops are executed as 1.25x that many fp16 MMA flops; the alu pipe of the scan binds
-// (ncu: alu 67 % of peak, tensor 50 %, profiles/r01_ncu_full_summary.txt).
+// (ncu: alu 81 % of peak, tensor 64 %, SM clock 1.62 GHz under the power cap, profiles/r02_ncu_full_summary.txt).
 //
 // k_assign_tc: persistent CTAs (one per SM), 16 warps; the unit of work is a SUPER TILE of 384 rows (three 128-row MMA
 // tiles) so every centroid operand tile fetched from L2 is used three times and every scheduler holds three scanning
@@ -1187,8 +1195,13 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
 #ifndef AT_TC_TAIL_FORK
 #define AT_TC_TAIL_FORK 1
 #endif
-    // timing experiments only (wrong labels): AT_TC_SKIP bit 0 drops the exact scans, bit 1 the candidate re-checks
+    // timing experiments only (wrong labels; experiment builds with -DAT_TC_EXPERIMENTS, never the product library):
+    // AT_TC_SKIP bit 0 drops the exact scans, bit 1 the candidate re-checks
+#ifdef AT_TC_EXPERIMENTS
     static const int skip = getenv("AT_TC_SKIP") ? atoi(getenv("AT_TC_SKIP")) : 0;
+#else
+    constexpr int skip = 0;
+#endif
     const bool fork = AT_TC_TAIL_FORK && ix->side_ok() && !skip;
     cudaStream_t fs = fork ? ix->side : st;
     if (fork) {
