@@ -12,26 +12,41 @@
 
 namespace at {
 
+// Block = kc * (256 / kc) threads: thread t owns channel c = t % kc (its ks weights and bias live in registers for the
+// whole launch) and walks the mel bins m = t / kc, + threads / kc, ... of one row after the other, so consecutive threads
+// write consecutive floats of the output row (coalesced) and nothing is divided inside the loops.  CONV_ROWS rows are
+// staged in shared memory per block step (zero padded at both ends: no bounds tests on the taps).
+constexpr int CONV_ROWS = 8, CONV_MAX_KS = 15;
 __global__ void __launch_bounds__(256) k_conv_expand(const float *__restrict__ x, int64_t n, int n_mels,
                                                      const float *__restrict__ w, const float *__restrict__ b, int kc, int ks,
                                                      float *__restrict__ out) {
-    extern __shared__ float s_w[];   // kc * ks weights + kc biases
-    for (int i = threadIdx.x; i < kc * ks + kc; i += blockDim.x) s_w[i] = i < kc * ks ? w[i] : b[i - kc * ks];
-    __syncthreads();
-    const int pad = ks / 2;
+    extern __shared__ float s_x[];   // CONV_ROWS rows of (pad + n_mels + pad) floats
+    const int pad = ks / 2, stride = n_mels + 2 * pad;
+    const int c = (int)threadIdx.x % kc, m0 = (int)threadIdx.x / kc, mstep = (int)blockDim.x / kc;
+    float wr[CONV_MAX_KS];
+#pragma unroll
+    for (int t = 0; t < CONV_MAX_KS; t++) wr[t] = t < ks ? w[c * ks + t] : 0.f;
+    const float bias = b[c];
     const int64_t d_out = (int64_t)n_mels * kc;
-    const int64_t total = n * d_out;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = o / d_out;
-        const int r = (int)(o - i * d_out);
-        const int m = r / kc, c = r - m * kc;
-        const float *xi = x + i * n_mels;
-        float acc = s_w[kc * ks + c];
-        for (int t = 0; t < ks; t++) {
-            const int mm = m + t - pad;
-            if (mm >= 0 && mm < n_mels) acc = fmaf(s_w[c * ks + t], xi[mm], acc);
+    for (int64_t r0 = (int64_t)blockIdx.x * CONV_ROWS; r0 < n; r0 += (int64_t)gridDim.x * CONV_ROWS) {
+        const int rows = (int)min((int64_t)CONV_ROWS, n - r0);
+        __syncthreads();   // the previous step's rows have been consumed
+        for (int i = threadIdx.x; i < rows * stride; i += blockDim.x) {
+            const int r = i / stride, p = i - r * stride - pad;
+            s_x[i] = (p >= 0 && p < n_mels) ? x[(r0 + r) * n_mels + p] : 0.f;
         }
-        out[o] = acc;
+        __syncthreads();
+        for (int r = 0; r < rows; r++) {
+            const float *xr = s_x + r * stride;   // xr[m + t] = x[row, m + t - pad]
+            float *orow = out + (r0 + r) * d_out + c;
+            for (int m = m0; m < n_mels; m += mstep) {
+                float acc = bias;
+#pragma unroll
+                for (int t = 0; t < CONV_MAX_KS; t++)
+                    if (t < ks) acc = fmaf(wr[t], xr[m + t], acc);   // ascending taps, like the first version (same rounding)
+                orow[(int64_t)m * kc] = acc;
+            }
+        }
     }
 }
 
@@ -154,14 +169,19 @@ extern "C" int at_conv_expand(const float *x, int64_t n, int n_mels, const float
                               int kernel_size, float *out, void *stream) {
     AT_REQUIRE(x && weight && bias && out && n >= 0 && n_mels > 0 && num_kernels > 0 && kernel_size > 0 && (kernel_size & 1),
                "at_conv_expand: bad arguments (odd kernel sizes only: padding = kernel_size // 2 keeps the width)");
-    AT_REQUIRE(num_kernels * (kernel_size + 1) <= 8192, "at_conv_expand: too many weights");
+    AT_REQUIRE(num_kernels <= 256 && kernel_size <= CONV_MAX_KS && n_mels <= 4096,
+               "at_conv_expand: at most 256 kernels of at most %d taps over at most 4096 mel bins", CONV_MAX_KS);
     if (n == 0) return AT_OK;
-    const int64_t total = n * n_mels * num_kernels;
-    int64_t want = ceil_div(total, 256 * 8);
-    int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+    const int threads = num_kernels * (256 / num_kernels);
+    int64_t want = ceil_div(n, CONV_ROWS);
+    int blocks = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
     if (blocks < 1) blocks = 1;
-    k_conv_expand<<<blocks, 256, sizeof(float) * (size_t)(num_kernels * (kernel_size + 1)), (cudaStream_t)stream>>>(
-        x, n, n_mels, weight, bias, num_kernels, kernel_size, out);
+    const size_t smem = sizeof(float) * (size_t)CONV_ROWS * (size_t)(n_mels + 2 * (kernel_size / 2));
+    if (smem > 48 * 1024) {
+        set_error("at_conv_expand: rows of %d mel bins do not fit the staging buffer", n_mels);
+        return AT_ERR_UNSUPPORTED;
+    }
+    k_conv_expand<<<blocks, threads, smem, (cudaStream_t)stream>>>(x, n, n_mels, weight, bias, num_kernels, kernel_size, out);
     AT_LAUNCH_OK();
     return AT_OK;
 }

@@ -201,8 +201,12 @@ constexpr int STAGE_FLOATS = AT_MEL_STAGE;                      // staged sample
 constexpr int WT_SMEM_FLOATS = AT_MEL_WT;                    // filterbank weights kept in shared memory when they fit
 constexpr int PAR_SMEM_MELS = AT_MEL_PAR;                      // filter parameters (first bin, groups of four, weight offset)
 
-__device__ __forceinline__ void group_sync(int grp) {   // named barrier 1 + grp over the group's 256 threads
+__device__ __forceinline__ void group_sync(int grp) {   // named barrier 1 + grp over the group's threads
+#ifdef AT_MEL_NOSYNC   // timing experiment only (races, wrong results): what the group barriers cost
+    __syncwarp();
+#else
     asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(MEL_THREADS) : "memory");
+#endif
 }
 
 template <int LOG2NF>
