@@ -44,6 +44,30 @@ def _wave(ytid):
     return torch.from_numpy(synth_ref.make_clip(4242, idx, L if idx % 5 else L - 777)).reshape(1, -1)
 
 
+def _check_tokens_against_the_oracle(wave, clip_ids, tokens, cents, T, what):
+    """tokens of the listed clips (a (B*T,) array, T frames per clip) against the CPU oracle end to end: the reference's own
+    torchaudio expressions for mel dB + min-max (oracle.mel_ref), normalize_vectors, and the scalar FAISS search formula;
+    mismatches only where the oracle's own fp64 top-2 gap is a near tie."""
+    from oracle import faiss_ref, mel_ref
+
+    cents = np.ascontiguousarray(cents, dtype=np.float32)
+    flips = total = 0
+    for b in clip_ids:
+        ref_spec = mel_ref.mel_db_torchaudio(wave[b].cpu().numpy(), SR, 1024, 512, 64, True).T.astype(np.float32)
+        xn = mel_ref.normalize_rows(np.ascontiguousarray(ref_spec))
+        lab, d1, d2 = faiss_ref.assign_l2_scalar(xn, cents)
+        _, e1, e2 = faiss_ref.assign_l2_f64(xn, cents)
+        got = np.asarray(tokens[b * T:(b + 1) * T])
+        mism = got != lab
+        # the GPU rows differ from the oracle's by the mel kernel's <= 1e-4 error as well: a flip needs a small gap
+        gap = (e2 - e1) / np.maximum(e1, 1e-30)
+        assert (gap[mism] < 2e-3).all(), (what, b, float(gap[mism].max()))
+        flips += int(mism.sum())
+        total += len(got)
+    print(f"{what}: {total} tokens of {len(clip_ids)} clips against the oracle, {flips} near-tie flips")
+    assert flips <= max(2, total // 200)
+
+
 def test_three_stages_run_with_the_reference_file_contract(tmp_path, monkeypatch):
     import torch
     from oracle import faiss_ref, mel_ref
@@ -140,6 +164,18 @@ def test_hot_path_in_hbm_matches_the_staged_classes(tmp_path):
     wh.copy_(wave)
     th, ch, bh = hp.run_host(wh, hb, chunk_clips=8)
     assert torch.equal(th.cuda(), tok) and torch.equal(ch.cuda(), cents)
+    # ... and against the CPU oracle: tokens of a few clips end to end (reference mel expressions + FAISS search formula on
+    # the final centroids), the centroids against the oracle's k-means over the same rows (free-running: share within 1e-4)
+    _check_tokens_against_the_oracle(wave, [0, 7, 29], tok.cpu().numpy(), cents.cpu().numpy(), spec.shape[1], "HotPath")
+    from oracle import faiss_ref, mel_ref
+
+    kmo = faiss_ref.Kmeans(64, K, niter=5, max_points_per_centroid=10 ** 9)
+    kmo.exact_search = True
+    kmo.train(l2.reshape(-1, 64).cpu().numpy())
+    ref_c = mel_ref.normalize_rows(kmo.centroids)
+    rel = np.linalg.norm(cents.cpu().numpy() - ref_c, axis=1) / np.linalg.norm(ref_c, axis=1)
+    print("HotPath centroids within 1e-4 of the oracle's:", float((rel <= 1e-4).mean()))
+    assert (rel <= 1e-4).mean() >= 0.75   # free-running: one near-tie flip moves two centroids and then spreads
 
 
 def test_pcm16_host_path_matches_fp32_host_path():
@@ -153,6 +189,8 @@ def test_pcm16_host_path_matches_fp32_host_path():
     wave = synth_clips(4242, 0, B, L)
     pcm = (wave * 32768.0).to(torch.int16)
     assert torch.equal(pcm16_to_f32(pcm), wave)
+    # the oracle's statement of torchaudio.load's scaling for 16-bit files (sample / 32768)
+    assert np.array_equal(pcm16_to_f32(pcm).cpu().numpy(), pcm.cpu().numpy().astype(np.float32) / np.float32(32768.0))
     odd = pcm.reshape(-1)[1:1001].clone()          # unaligned source pointer: scalar path
     assert torch.equal(pcm16_to_f32(odd), wave.reshape(-1)[1:1001])
     hp = HotPath(22050, 1024, 512, 64, True, K, 3)
@@ -190,6 +228,8 @@ def test_streaming_spectrogram_to_tokens_matches_the_staged_path():
         got = torch.cat(got)
         assert torch.equal(got, want.cpu())
         assert int(torch.cat(flags).sum()) == 0
+        # ... and the streamed tokens against the CPU oracle, end to end, on clips of three different chunks
+        _check_tokens_against_the_oracle(wave, [1, 40, 99], got.numpy(), cents.cpu().numpy(), spec.shape[1], f"stream {dtype}")
 
 
 def test_large_vocab_tensor_search_matches_exact_scan():
