@@ -6,8 +6,9 @@
 //   k_conv_expand   rows (n, n_mels) -> (n, n_mels * num_kernels), out[i, m * Kc + c] = b[c] + sum_t w[c][t] x[i, m + t - pad]
 //                   (the layout of conv_output.transpose(1, 2).reshape(-1, Kc * n_mels))
 //   k_assign_gemm   exact fp32 nearest-centroid search for rows wider than the register-resident kernel covers (d > 128):
-//                   a 64 x 64 tile of inner products per block (4 x 4 per thread, K chunks of 16 through shared memory),
-//                   |x|^2 + |c|^2 - 2 <x, c> clamped at 0, strict '<' in ascending column order (lowest index wins ties).
+//                   a 128 x 128 tile of inner products per block (8 x 8 per thread in packed fp32, K chunks of 8 through
+//                   double-buffered shared memory), |x|^2 + |c|^2 - 2 <x, c> clamped at 0, strict '<' in ascending column
+//                   order (lowest index wins ties).
 #include "at_index.cuh"
 
 namespace at {
@@ -50,86 +51,121 @@ __global__ void __launch_bounds__(256) k_conv_expand(const float *__restrict__ x
     }
 }
 
-constexpr int GM = 64, GN = 64, GK = 16;
-__global__ void __launch_bounds__(256) k_assign_gemm(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ c,
-                                                     const float *__restrict__ cn, int k, int32_t *__restrict__ labels32,
-                                                     int64_t *__restrict__ labels64, float *__restrict__ dist) {
-    __shared__ float sa[GK][GM + 4];   // sa[kk][row]
-    __shared__ float sb[GK][GN + 4];   // sb[kk][col]
+// ---------------------------------------------------------------------------------------------------------------------
+// k_assign_gemm: exact fp32 nearest-centroid search for wide rows.  A block owns 128 rows and sweeps the centroids in tiles
+// of 128; thread (ty, tx) of a 16 x 16 grid accumulates the 8 x 8 inner products of rows {4 ty .. 4 ty + 3, 64 + 4 ty ..}
+// and columns {4 tx .. 4 tx + 3, 64 + 4 tx ..}.  K chunks of 8 go through double-buffered shared memory (one float4 of each
+// operand per thread and chunk, fetched one chunk ahead into registers).  The products are packed fp32 (fma.rn.f32x2: two
+// adjacent columns per instruction): the row operand is stored DUPLICATED in shared memory ((a, a) pairs) so that a 128-bit
+// load yields two ready-made register pairs, the centroid operand's adjacent columns are pairs as they are -- 32 FFMA2 + 6
+// LDS.128 per k instead of 64 FFMA + 4 LDS.128.  Each inner product is still one sequential fp32 FMA chain over k.
+// |x|^2 + |c|^2 - 2 <x, c> clamped at 0, strict '<' in ascending column order (the lowest index wins exact ties).
+constexpr int GM = 128, GN = 128, GK = 8;
+typedef unsigned long long u64g;
+__device__ __forceinline__ u64g gfma2(u64g a, u64g b, u64g c) {
+    u64g r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void gunpack(u64g v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
+__global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ c,
+                                                        const float *__restrict__ cn, int k, int32_t *__restrict__ labels32,
+                                                        int64_t *__restrict__ labels64, float *__restrict__ dist) {
+    __shared__ __align__(16) float2 sa[2][GK][GM];   // (a, a): rows duplicated            16 KB
+    __shared__ __align__(16) float sb[2][GK][GN];    //                                      8 KB
+    __shared__ float s_xn[GM];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int64_t row0 = (int64_t)blockIdx.x * GM;
-    float best[4];
-    int bidx[4];
-    float xn[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < 4; r++) best[r] = INFINITY, bidx[r] = 0;
-    // loader roles: 256 threads fetch a 64 x 16 tile of each operand, one float4 per thread (d is a multiple of 4 or
-    // handled element-wise)
-    const int lr = tid >> 2, lk = (tid & 3) * 4;
+    // |x|^2 of the block's rows: one sequential FMA chain per row (thread t < 128 walks row t)
+    if (tid < GM) {
+        float q = 0.f;
+        const int64_t r = row0 + tid;
+        if (r < n) {
+            const float *xr = x + r * d;
+            for (int t = 0; t < d; t++) q = fmaf(xr[t], xr[t], q);
+        }
+        s_xn[tid] = q;
+    }
+    // loader role: float4 `tid` of a 128 x 8 chunk = row / column (tid >> 1), k offset 4 (tid & 1)
+    const int lr = tid >> 1, lk = (tid & 1) * 4;
     const bool vec = (d & 3) == 0;
+    auto fetch = [&](const float *base, int64_t r, int64_t rmax, int k0) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rmax) {
+            const float *p = base + r * d + k0 + lk;
+            if (vec && k0 + lk + 3 < d) v = *reinterpret_cast<const float4 *>(p);
+            else {
+                if (k0 + lk + 0 < d) v.x = p[0];
+                if (k0 + lk + 1 < d) v.y = p[1];
+                if (k0 + lk + 2 < d) v.z = p[2];
+                if (k0 + lk + 3 < d) v.w = p[3];
+            }
+        }
+        return v;
+    };
+    auto stash = [&](int buf, const float4 av, const float4 bv) {
+        sa[buf][lk + 0][lr] = make_float2(av.x, av.x), sa[buf][lk + 1][lr] = make_float2(av.y, av.y);
+        sa[buf][lk + 2][lr] = make_float2(av.z, av.z), sa[buf][lk + 3][lr] = make_float2(av.w, av.w);
+        sb[buf][lk + 0][lr] = bv.x, sb[buf][lk + 1][lr] = bv.y, sb[buf][lk + 2][lr] = bv.z, sb[buf][lk + 3][lr] = bv.w;
+    };
+    float best[8];
+    int bidx[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) best[r] = INFINITY, bidx[r] = 0x7FFFFFFF;
+    const int nchunk = (d + GK - 1) / GK;
     for (int j0 = 0; j0 < k; j0 += GN) {
-        float acc[4][4];
+        u64g acc[8][4];   // acc[r][q]: row r of the thread, columns 2q, 2q+1 of its eight
 #pragma unroll
-        for (int r = 0; r < 4; r++)
+        for (int r = 0; r < 8; r++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) acc[r][q] = 0.f;
-        float xs[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k0 = 0; k0 < d; k0 += GK) {
-            float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
-            const int64_t ar = row0 + lr;
-            const int bc = j0 + lr;
-            if (ar < n) {
-                if (vec && k0 + lk + 3 < d) {
-                    const float4 v = *reinterpret_cast<const float4 *>(x + ar * d + k0 + lk);
-                    av[0] = v.x, av[1] = v.y, av[2] = v.z, av[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        if (k0 + lk + e < d) av[e] = x[ar * d + k0 + lk + e];
-                }
-            }
-            if (bc < k) {
-                if (vec && k0 + lk + 3 < d) {
-                    const float4 v = *reinterpret_cast<const float4 *>(c + (int64_t)bc * d + k0 + lk);
-                    bv[0] = v.x, bv[1] = v.y, bv[2] = v.z, bv[3] = v.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; e++)
-                        if (k0 + lk + e < d) bv[e] = c[(int64_t)bc * d + k0 + lk + e];
-                }
-            }
-            __syncthreads();   // the previous chunk has been consumed
-#pragma unroll
-            for (int e = 0; e < 4; e++) sa[lk + e][lr] = av[e], sb[lk + e][lr] = bv[e];
-            __syncthreads();
+            for (int q = 0; q < 4; q++) acc[r][q] = 0ull;
+        float4 av = fetch(x, row0 + lr, n, 0), bv = fetch(c, (int64_t)j0 + lr, k, 0);
+        __syncthreads();   // the previous tile's last chunk (and s_xn) are done with
+        stash(0, av, bv);
+        __syncthreads();
+        for (int ch = 0; ch < nchunk; ch++) {
+            const int buf = ch & 1;
+            if (ch + 1 < nchunk) av = fetch(x, row0 + lr, n, (ch + 1) * GK), bv = fetch(c, (int64_t)j0 + lr, k, (ch + 1) * GK);
 #pragma unroll
             for (int kk = 0; kk < GK; kk++) {
-                const float4 a4 = *reinterpret_cast<const float4 *>(&sa[kk][ty * 4]);
-                const float4 b4 = *reinterpret_cast<const float4 *>(&sb[kk][tx * 4]);
-                const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                // rows 4 ty .. 4 ty + 3 and 64 + 4 ty ..: four 128-bit loads of (a, a) pairs; columns: two loads
+                const ulonglong2 a01 = *reinterpret_cast<const ulonglong2 *>(&sa[buf][kk][ty * 4]);
+                const ulonglong2 a23 = *reinterpret_cast<const ulonglong2 *>(&sa[buf][kk][ty * 4 + 2]);
+                const ulonglong2 a45 = *reinterpret_cast<const ulonglong2 *>(&sa[buf][kk][64 + ty * 4]);
+                const ulonglong2 a67 = *reinterpret_cast<const ulonglong2 *>(&sa[buf][kk][64 + ty * 4 + 2]);
+                const ulonglong2 b03 = *reinterpret_cast<const ulonglong2 *>(&sb[buf][kk][tx * 4]);
+                const ulonglong2 b47 = *reinterpret_cast<const ulonglong2 *>(&sb[buf][kk][64 + tx * 4]);
+                const u64g ar[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+                const u64g bq[4] = {b03.x, b03.y, b47.x, b47.y};
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    if (j0 == 0) xs[r] = fmaf(a[r], a[r], xs[r]);
+                for (int r = 0; r < 8; r++)
 #pragma unroll
-                    for (int q = 0; q < 4; q++) acc[r][q] = fmaf(a[r], bb[q], acc[r][q]);
-                }
+                    for (int q = 0; q < 4; q++) acc[r][q] = gfma2(ar[r], bq[q], acc[r][q]);
+            }
+            if (ch + 1 < nchunk) {
+                stash(buf ^ 1, av, bv);   // the other buffer was last read in iteration ch - 1, before the barrier below
+                __syncthreads();
             }
         }
-        if (j0 == 0) {
+        // tile epilogue: distances, the thread's best of its 8 columns per row (ascending), then across the 16 threads of the row
 #pragma unroll
-            for (int r = 0; r < 4; r++) xn[r] = xs[r];
-        }
-        // tile epilogue: distance, per-row best of this thread's 4 columns (ascending), then across the 16 threads of the row
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < 8; r++) {
+            const float xn = s_xn[(r < 4 ? 0 : 64) + ty * 4 + (r & 3)];
             float tb = INFINITY;
             int ti = 0x7FFFFFFF;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int j = j0 + tx * 4 + q;
+                float p0, p1;
+                gunpack(acc[r][q], p0, p1);
+                const int j = j0 + (q < 2 ? 0 : 64) + tx * 4 + (q & 1) * 2;
                 if (j < k) {
-                    const float dj = l2_expanded(xn[r], cn[j], acc[r][q]);
+                    const float dj = l2_expanded(xn, cn[j], p0);
                     if (dj < tb) tb = dj, ti = j;
+                }
+                if (j + 1 < k) {
+                    const float dj = l2_expanded(xn, cn[j + 1], p1);
+                    if (dj < tb) tb = dj, ti = j + 1;
                 }
             }
 #pragma unroll
@@ -143,8 +179,8 @@ __global__ void __launch_bounds__(256) k_assign_gemm(const float *__restrict__ x
     }
     if (tx == 0) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int64_t row = row0 + ty * 4 + r;
+        for (int r = 0; r < 8; r++) {
+            const int64_t row = row0 + (r < 4 ? 0 : 64) + ty * 4 + (r & 3);
             if (row < n) {
                 const int bj = bidx[r] == 0x7FFFFFFF ? 0 : bidx[r];
                 if (labels32) labels32[row] = bj;
