@@ -26,6 +26,7 @@ class HotPath:
         self.index = FlatL2(n_mels)
         self.algo = algo
         self._init_rows = {}
+        self._init_dev = {}
 
     # -- pieces ----------------------------------------------------------------------------------
     def init_rows(self, n_total: int) -> np.ndarray:
@@ -55,11 +56,15 @@ class HotPath:
 
         n_local = l2_rows.shape[0]
         n_total = n_local if n_total is None else n_total
-        rows = self.init_rows(n_total)
-        mine = (rows >= row_offset) & (rows < row_offset + n_local)
+        # which of FAISS's k initial rows live in this shard: device index tensors, built once per (size, shard)
+        key = (n_total, row_offset, n_local, str(l2_rows.device))
+        if key not in self._init_dev:
+            rows = self.init_rows(n_total)
+            mine = (rows >= row_offset) & (rows < row_offset + n_local)
+            self._init_dev[key] = (torch.from_numpy(np.nonzero(mine)[0]).to(l2_rows.device),
+                                   torch.from_numpy(rows[mine] - row_offset).to(l2_rows.device))
+        idx, src = self._init_dev[key]
         cent = torch.zeros((self.k, self.d), dtype=torch.float32, device=l2_rows.device)
-        idx = torch.from_numpy(np.nonzero(mine)[0]).to(l2_rows.device)
-        src = torch.from_numpy(rows[mine] - row_offset).to(l2_rows.device)
         cent.index_copy_(0, idx, l2_rows.index_select(0, src))
         if self.group is not False and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(cent, group=self.group or None)

@@ -693,11 +693,19 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
                     // tile's scan (a short stall on the load latency, covered by the scheduler's other scanning warps): the
                     // three scanning groups of a CTA run in lockstep and share ONE spare TMEM slot, so a slot released after
                     // the third fold would have the next round of MMAs finish after the groups need them.
+#ifndef AT_TC_LATE_RELEASE
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     mbar_arrive_elect(bar_empty + 8u * slot);
                     fold32<4>(c0, c1, tk, m16, m8, t1, t2, t3, bp);
+#else   // experiment: release after the third fold (no exposed load latency, later MMAs)
+                    fold32<4>(c0, c1, tk, m16, m8, t1, t2, t3, bp);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    mbar_arrive_elect(bar_empty + 8u * slot);
+#endif
                     // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
                     v += RT;
                     left--;
