@@ -279,6 +279,41 @@ def test_search_tensor_random_and_out_of_range_rows():
     _check_labels(lt.cpu().numpy(), x.cpu().numpy(), c.cpu().numpy(), "tensor randn")
 
 
+def test_search_tensor_adversarial_near_ties():
+    """Near ties on purpose: every centroid has a twin that is bit-identical (exact tie: the lower index must win) or
+    differs by one or a few ulps in a few coordinates (the fp32 formula decides), twins placed in the same and in different
+    128-centroid tiles; rows sit on and next to the centroids.  The tensor path must return the exact kernel's labels."""
+    import torch
+    from at_b200 import FlatL2, _lib, row_l2norm
+
+    g = torch.Generator(device="cuda").manual_seed(77)
+    base = row_l2norm(torch.rand(300, 64, device="cuda", generator=g) + 0.2)
+    twins = base.clone()
+    # a third exact copies, a third one-ulp nudges of 3 coordinates, a third 1e-6 relative noise
+    ulp = torch.nextafter(twins[100:200, :3], torch.full_like(twins[100:200, :3], 2.0))
+    twins[100:200, :3] = ulp
+    twins[200:] = twins[200:] * (1.0 + 1e-6 * torch.randn(100, 64, device="cuda", generator=g))
+    for order in ("adjacent", "far"):
+        if order == "adjacent":   # twin right after its original: same tile, same 16-column group most of the time
+            c = torch.stack([base, twins], dim=1).reshape(-1, 64).contiguous()
+        else:                     # twins 300 columns later: other tiles
+            c = torch.cat([base, twins]).contiguous()
+        x = torch.cat([base, twins, row_l2norm(base + 1e-4 * torch.randn(300, 64, device="cuda", generator=g)),
+                       row_l2norm(0.5 * (base + twins))]).contiguous()
+        ix = FlatL2(64)
+        ix.set_centroids(c)
+        ls, ds = ix.search(x, algo=_lib.ALGO_SIMT)
+        lt, dt = ix.search(x, algo=_lib.ALGO_TENSOR)
+        re, full = ix.tc_stats()
+        print(f"{order}: tensor vs exact mismatches {int((ls != lt).sum())} of {x.shape[0]}, re-checked {re}, exact scans {full}")
+        assert torch.equal(ls, lt), order
+        assert torch.equal(ds, dt), order    # uncertified rows carry the canonical distance
+        # exact copies: the lower index of the pair must have won for the rows sitting on them
+        first = ls[:100]
+        want = (torch.arange(100, device="cuda") * 2) if order == "adjacent" else torch.arange(100, device="cuda")
+        assert torch.equal(first.long(), want)
+
+
 def test_search_tensor_on_badly_centred_data():
     """The tensor path works on rows and centroids shifted by the centroid mean (the fp16 rounding errors then scale with
     |x - m| |c - m|).  The shift is only a conditioning device: data for which it is useless or harmful -- two far-apart
