@@ -873,6 +873,17 @@ def run_b200(args):
                                          "algorithmic_bytes": upd_bytes}
         n_fin, ms_fin = prof["finalize"]
         lloyd_ms = (ms_search * (NITER / (NITER + 1.0)) / args.steps + ms_upd / args.steps + ms_fin / args.steps) / NITER
+        # the two GEMM-shaped stages against the same tensor bound as the search kernel: one Lloyd iteration (search + update
+        # + finalize, stage time / NITER incl. the once-per-training-set work) and the tokenization of every frame
+        it_ms = stage_ms[1] / NITER
+        rs["lloyd_iteration"] = {"bound": "tensor", "achieved": flops / (it_ms * 1e-3) / 1e12, "peak": pk["tensor_sustained"],
+                                 "unit": "TFLOP/s", "frac": flops / (it_ms * 1e-3) / 1e12 / pk["tensor_sustained"],
+                                 "avg_ms": it_ms, "note": "2*N*K*D flops of the iteration's search over kmeans_ms / NITER "
+                                                          "(row image, first full regroup and set-up amortised in)"}
+        rs["tokenize"] = {"bound": "tensor", "achieved": flops / (stage_ms[2] * 1e-3) / 1e12, "peak": pk["tensor_sustained"],
+                          "unit": "TFLOP/s", "frac": flops / (stage_ms[2] * 1e-3) / 1e12 / pk["tensor_sustained"],
+                          "avg_ms": stage_ms[2], "note": "2*N*K*D flops over the tokenize stage (operand rebuild + search of "
+                                                         "the trained rows' image + int64 labels)"}
         line = {
             "metric": METRIC, "value": n_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
