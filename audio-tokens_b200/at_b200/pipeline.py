@@ -132,24 +132,26 @@ class HotPath:
             with torch.cuda.stream(mel_stream):
                 absmax.zero_()
             self.plan.set_absmax_out(absmax)
-        for ci, b0 in enumerate(range(0, B, chunk_clips)):
-            nb = min(chunk_clips, B - b0)
-            sb = ci & 1
-            with torch.cuda.stream(copy):
-                if ev_free[sb] is not None:
-                    copy.wait_event(ev_free[sb])
-                (bufs["stage16"] if pcm16 else stage)[sb, :nb].copy_(wave_host[b0:b0 + nb], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            mel_stream.wait_event(ev)
-            if pcm16:
-                _lib.check(self.plan.lib.at_pcm16_to_f32(_lib.ptr(bufs["stage16"][sb]), nb * L, _lib.ptr(stage[sb]), sp))
-            _lib.check(self.plan.lib.at_mel_forward(self.plan.h, _lib.ptr(stage[sb]), None, None, L, nb,
-                                                    _lib.ptr(spec[b0:]), _lib.ptr(l2[b0:]), _lib.ptr(bad[b0:]), sp))
-            ev_free[sb] = torch.cuda.Event()
-            ev_free[sb].record(mel_stream)
-        if absmax is not None:
-            self.plan.set_absmax_out(None)
+        try:
+            for ci, b0 in enumerate(range(0, B, chunk_clips)):
+                nb = min(chunk_clips, B - b0)
+                sb = ci & 1
+                with torch.cuda.stream(copy):
+                    if ev_free[sb] is not None:
+                        copy.wait_event(ev_free[sb])
+                    (bufs["stage16"] if pcm16 else stage)[sb, :nb].copy_(wave_host[b0:b0 + nb], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                mel_stream.wait_event(ev)
+                if pcm16:
+                    _lib.check(self.plan.lib.at_pcm16_to_f32(_lib.ptr(bufs["stage16"][sb]), nb * L, _lib.ptr(stage[sb]), sp))
+                _lib.check(self.plan.lib.at_mel_forward(self.plan.h, _lib.ptr(stage[sb]), None, None, L, nb,
+                                                        _lib.ptr(spec[b0:]), _lib.ptr(l2[b0:]), _lib.ptr(bad[b0:]), sp))
+                ev_free[sb] = torch.cuda.Event()
+                ev_free[sb].record(mel_stream)
+        finally:
+            if absmax is not None:
+                self.plan.set_absmax_out(None)
         done = torch.cuda.Event()
         done.record(mel_stream)
         return done
