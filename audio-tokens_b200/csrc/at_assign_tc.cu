@@ -136,7 +136,8 @@ constexpr float TAU_SAFETY = 1.0625f;
 // index's own S unless a prepared image with its own scale is attached (k-means), R = S / Sx.
 // SC_CANON = S (|m| + max |c_j|): with S |x - m| it bounds S (|x| + |c|), the scale of the canonical fp32 formula's own
 // rounding error (the tail kernels evaluate the UNSHIFTED rows and centroids).
-enum { SC_S = 0, SC_EMAX = 1, SC_INV_S2 = 2, SC_TAU = 3, SC_CMAX = 4, SC_SX = 5, SC_RATIO = 6, SC_CANON = 7, SC_COUNT = 8 };
+enum { SC_S = 0, SC_EMAX = 1, SC_INV_S2 = 2, SC_TAU = 3, SC_CMAX = 4, SC_SX = 5, SC_RATIO = 6, SC_CANON = 7, SC_CCOEF = 8,
+       SC_COUNT = 12 };
 
 // (mbarrier / bulk-copy wrappers: at_ptx.cuh)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -262,12 +263,12 @@ __device__ __host__ __forceinline__ uint32_t aug_off(int r, int kc) { return (ui
 // row with S |x| <= X_LIMIT); tau = absolute part of the certification threshold in accumulator units.
 // maxes: bit patterns of {max |c_ij - m_i|, max |c_j - m|^2, max |c_j|^2} (k_centroid_norms).
 __global__ void k_tc_scale(unsigned int *__restrict__ maxes, const float *__restrict__ ext_sx, const float *__restrict__ shift,
-                           float *__restrict__ scale) {
+                           int d, float *__restrict__ scale) {
     if (threadIdx.x == 0) {
         const float m = __uint_as_float(maxes[0]), n2 = __uint_as_float(maxes[1]), n2_orig = __uint_as_float(maxes[2]);
         maxes[0] = 0u, maxes[1] = 0u, maxes[2] = 0u;   // ready for the next set of centroids
         float m2 = 0.f;
-        for (int t = 0; t < 64; t++) m2 = fmaf(shift[t], shift[t], m2);
+        for (int t = 0; t < d; t++) m2 = fmaf(shift[t], shift[t], m2);
         const float cmax = sqrtf(n2) * 1.0009765625f;
         int e = 0;
         if (cmax > 0.f && isfinite(cmax)) {
@@ -292,11 +293,17 @@ __global__ void k_tc_scale(unsigned int *__restrict__ maxes, const float *__rest
         scale[SC_INV_S2] = 1.0f / (S * S);
         // the three-piece norms carry ~2^-21 of S^2 (|x|^2 + |c|^2), fp32 accumulation a few 2^-24 of the partial sums
         // (|.| <= 2^17): 2^-19 S^2 64 m^2 (>= 2^-19 S^2 |c|^2) plus 8 ulps of the accumulator leaves a factor ~4
-        scale[SC_TAU] = ldexpf(S * S * 64.0f * m * m, -19) + 0.0625f;
+        // (d > 64: the accumulator collects d / 16 + 1 products instead of 5, its rounding grows in proportion)
+        scale[SC_TAU] = ldexpf(S * S * (float)d * m * m, -19) + 0.0625f * (float)(d / 16 + 1) / 5.0f;
         scale[SC_CMAX] = S * cmax;
         scale[SC_SX] = Sx;
         scale[SC_RATIO] = S / Sx;
         scale[SC_CANON] = S * (sqrtf(m2) + sqrtf(n2_orig)) * 1.001f;
+        // wide rows: the exact kernel (k_assign_gemm) sums the inner product as ONE d-term FMA chain, error <= d u |x||c| with
+        // u = 2^-24; |c|^2 comes from 16 chains of d / 16 terms + a 4-level tree; |x|^2 is the same number for both
+        // candidates of a comparison and cancels.  Difference of two candidates: 2 u (2 d |x||c| + (d / 16 + 5) |c|^2 + |x|^2)
+        // <= 1.25 d u (|x| + |c|)^2 for d >= 128
+        scale[SC_CCOEF] = 1.25f * ldexpf((float)d, -24);
     }
 }
 
@@ -629,185 +636,9 @@ k_assign_tc(const unsigned char *__restrict__ img, const float *__restrict__ ero
 #else
         asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
 #endif
-        // ================================================================== epilogue: accumulator scan
-        const int rt = (warp - 4) >> 2;   // row tile of the super tile
-        const int ew = warp & 3;          // the TMEM lane quadrant this warp may read
-        const int row_in_super = rt * TM + ew * 32 + lane;
-        // Loop-invariant addresses, pinned in registers (the compiler otherwise re-derives them from %tid every tile, on
-        // the alu pipe the scan saturates).  v = (centroid tile counter) * RT + rt numbers this warp's accumulators: slot
-        // v & 3 of the TMEM ring, barrier phase (v >> 2) & 1.
-        uint32_t tbase = tmem + ((uint32_t)(ew * 32) << 16);
-        uint32_t bar_full = BAR(BAR_ACC_FULL), bar_empty = BAR(BAR_ACC_EMPTY);
-        asm volatile("" : "+r"(tbase), "+r"(bar_full), "+r"(bar_empty));
-        const uint32_t m16 = key_mul >> 3, m8 = key_mul >> 4;   // 16, 8
-        const int ntiles = (int)my_tiles;
-        // This warp's private queue of uncertified rows with a candidate list (tc_queue_base): a shared global counter
-        // costs one contended atomic round trip per warp and super tile in the middle of the lock-stepped scan (measured:
-        // 0.18 ms of a 1.1 ms launch); a private queue needs none.
-        const int sw = warp - 4;
-        uint4 *const queue = tail + tc_queue_base(nsuper, workers, worker, sw);
-        uint32_t qn = 0;
-        uint32_t v = (uint32_t)rt;
-        uint32_t left = (uint32_t)ntiles * (uint32_t)ktiles;   // accumulators this warp still has to scan
-        bool primed = false;
-        uint32_t c0[16], c1[16], c2[16], c3[16];
-        for (int i = 0; i < ntiles; i++) {
-            uint32_t g1 = 0xFFFFFFFFu, g2 = 0xFFFFFFFFu, g3 = 0xFFFFFFFFu;   // A grouping: best three group minima of the row
-            uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu, t3 = 0xFFFFFFFFu;   // ... of the current block of 16 tiles
-            uint32_t bp[16];                               // B grouping: class minima over the whole sweep
-#pragma unroll
-            for (int h = 0; h < 16; h++) bp[h] = 0xFFFFFFFFu;
-            int j1 = 0, j2 = 0;                            // 16-tile blocks of g1, g2
-            const int64_t row = ((int64_t)worker + (int64_t)i * workers) * SROWS + row_in_super;
-            const float erow_r = __ldg(erow + row);          // Sx |delta|
-            const float xnS = __ldg(xns + row);              // Sx^2 |x|^2
-            // Accumulator read-out in eight 16-column loads through four register buffers: two loads are always in flight
-            // behind a fold of two, and the first two loads of the NEXT tile are issued before the last fold of this one.
-            if (!primed) {   // very first tile of this warp
-                mbar_waitx(bar_full + 8u * (v & 3u), (v >> 2) & 1u);
-                tc_fence_after();
-                const uint32_t ta = tbase + (v & 3u) * TN;
-                tmem_ld16(ta, c0);
-                tmem_ld16(ta + 16, c1);
-                primed = true;
-            }
-            // centroid tiles in blocks of 16 (2,048 centroids): the running top-3 of a block is merged into the row's once
-            // per block, outside the tile loop
-            for (int jb = 0; jb * 16 < ktiles; jb++) {
-                const uint32_t nt = (uint32_t)min(16, ktiles - jb * 16);
-                for (uint32_t tk = 0; tk < nt; tk++) {   // (tile mod 16, group) rides in the low 7 bits of an A key
-                    const uint32_t slot = v & 3u;
-                    const uint32_t ta = tbase + slot * TN;
-                    tmem_ld_wait();                       // c0, c1 (issued during the previous tile)
-                    tmem_ld16(ta + 32, c2);
-                    tmem_ld16(ta + 48, c3);
-                    fold32<0>(c0, c1, tk, m16, m8, t1, t2, t3, bp);
-                    tmem_ld_wait();
-                    tmem_ld16(ta + 64, c0);
-                    tmem_ld16(ta + 80, c1);
-                    fold32<2>(c2, c3, tk, m16, m8, t1, t2, t3, bp);
-                    tmem_ld_wait();
-                    tmem_ld16(ta + 96, c2);
-                    tmem_ld16(ta + 112, c3);
-                    // Release the accumulator as soon as its last columns are in registers, i.e. half way through the
-                    // tile's scan (a short stall on the load latency, covered by the scheduler's other scanning warps): the
-                    // three scanning groups of a CTA run in lockstep and share ONE spare TMEM slot, so a slot released after
-                    // the third fold would have the next round of MMAs finish after the groups need them.
-#ifndef AT_TC_LATE_RELEASE
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    mbar_arrive_elect(bar_empty + 8u * slot);
-                    fold32<4>(c0, c1, tk, m16, m8, t1, t2, t3, bp);
-#else   // experiment: release after the third fold (no exposed load latency, later MMAs)
-                    fold32<4>(c0, c1, tk, m16, m8, t1, t2, t3, bp);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    mbar_arrive_elect(bar_empty + 8u * slot);
-#endif
-                    // next tile of this warp (same super tile or the next one): start its first two loads now if it is ready
-                    v += RT;
-                    left--;
-                    const bool more = left != 0u;
-                    const uint32_t nbar = bar_full + 8u * (v & 3u), nph = (v >> 2) & 1u;
-                    const uint32_t tn = tbase + (v & 3u) * TN;
-                    bool started = false;
-                    if (more && mbar_test(nbar, nph)) {   // warp-uniform: every lane probes the same barrier
-                        tc_fence_after();
-                        tmem_ld16(tn, c0);
-                        tmem_ld16(tn + 16, c1);
-                        started = true;
-                    }
-                    fold32<6>(c2, c3, tk, m16, m8, t1, t2, t3, bp);
-                    if (more && !started) {
-                        mbar_waitx(nbar, nph);
-                        tc_fence_after();
-                        tmem_ld16(tn, c0);
-                        tmem_ld16(tn + 16, c1);
-                    }
-                }
-                // A grouping: merge the block's sorted triple into the row's (equal keys keep the earlier block)
-                const bool p = t1 < g1;
-                const uint32_t n3 = min(umin3(g3, t3, max(g2, t1)), max(g1, t2));
-                const uint32_t xa = p ? g1 : g2, ya = p ? t2 : t1;
-                const int xt = p ? j1 : j2;
-                const bool qn = ya < xa;
-                g2 = min(xa, ya);
-                j2 = qn ? jb : xt;
-                g1 = min(g1, t1);
-                j1 = p ? jb : j1;
-                g3 = n3;
-                t1 = t2 = t3 = 0xFFFFFFFFu;
-            }
-            // column tiles of the two best A groups
-            j1 = j1 * 16 + (int)((g1 >> 3) & 15u), j2 = j2 * 16 + (int)((g2 >> 3) & 15u);
-            // B grouping: the class index is appended now (pattern * 16 + class), then the top-3 of the 16 class minima
-            // (the row minimum is the same value in both groupings: acc_b(h1) == acc_a(g1))
-#pragma unroll
-            for (int h = 0; h < 16; h++) bp[h] = bp[h] * (key_mul >> 3) + (uint32_t)h;
-            uint32_t h1 = min(bp[0], bp[1]), h2 = max(bp[0], bp[1]), h3 = 0xFFFFFFFFu;
-#pragma unroll
-            for (int pr = 1; pr < 8; pr++) {
-                const uint32_t lo = min(bp[2 * pr], bp[2 * pr + 1]), hi = max(bp[2 * pr], bp[2 * pr + 1]);
-                const uint32_t m3 = umin3(h3, max(h2, lo), max(h1, hi));
-                h2 = umin3(h2, hi, max(h1, lo));
-                h1 = min(h1, lo);
-                h3 = m3;
-            }
-            // (the scale constants are re-read per super tile rather than held in registers across the scan)
-            const float inv_s2 = __ldg(scale + SC_INV_S2), tau_abs = __ldg(scale + SC_TAU), cmax = __ldg(scale + SC_CMAX);
-            const float R = __ldg(scale + SC_RATIO), emax = __ldg(scale + SC_EMAX), canon = __ldg(scale + SC_CANON);
-            // S |delta|: the row image's distance from the exact shifted row, plus the fp32 rounding of c - m
-            const float e = fmaf(1.2e-7f, cmax, R * erow_r);
-            const float xnP = R * R * xnS;                   // S^2 |x|^2
-            const bool fallback = !(xnP <= X_LIMIT * X_LIMIT);   // outside the accumulator range, Inf, NaN
-            // ---- certification (accumulator units)
-            const float A1 = acc_a(g1), A2 = fminf(acc_a(g2), acc_b(h2)), A3 = fminf(acc_a(g3), acc_b(h3));
-            const int ca = j1 * TN + (int)((g1 & 7u) << 4) + (int)(h1 & 15u);   // best A group x best B class
-            const float v1 = fmaxf(A1 - BIAS, 0.f);
-            const float cterm = sqrtf(xnS) * 1.001f * emax;                          // >= |<x~, e_j>| for every column j
-            const float ub = v1 + 2.0f * e * cmax + tau_abs + cterm;                 // >= S^2 d_best
-            // + the canonical fp32 formula's own resolution on the difference of two candidates, 2 x 2^-20 S^2 (|x| + |c|)^2
-            // with S |x| <= S |x - m| + S |m|: what is certified must also be what the exact kernels' arithmetic decides
-            const float sxc = sqrtf(xnP) + canon;
-            const float tau = TAU_SAFETY * (tau_abs + 4.0f * e * sqrtf(ub + tau_abs) + 2.0f * cterm + 1.9073486e-6f * sxc * sxc);
-            const bool second_ok = (A2 - A1) > tau;   // exact second smallest column: no other column can win
-            // every column outside (best two A groups) x (best two B groups) is out of reach
-            const bool third_ok = (A3 - A1) > tau;
-#ifdef AT_TC_FORCE_CERT
-            const bool certified = true;
-#else
-            const bool certified = !fallback && second_ok && ca < k;
-#endif
-            const bool live = row < n;
-            if (certified && live) {
-                if (labels32) labels32[row] = ca;
-                if (labels64) labels64[row] = ca;
-                if (dist) dist[row] = v1 * inv_s2;
-            }
-            // uncertified rows: candidate rows -> this warp's queue (the four columns where one of the two best A groups
-            // meets one of the two best B classes); rows that need an exact scan (rare) -> the dense global list
-            const bool want_full = live && !certified && (fallback || !third_ok || ca >= k);
-            const bool want_cand = live && !certified && !want_full;
-            const unsigned mc = __ballot_sync(0xffffffffu, want_cand), mf = __ballot_sync(0xffffffffu, want_full);
-            const unsigned lt = (1u << lane) - 1u;
-            if (want_cand) {
-                const int a1 = (int)((g1 & 7u) << 4), b1 = (int)(h1 & 15u), a2 = (int)((g2 & 7u) << 4), b2 = (int)(h2 & 15u);
-                int c1 = j1 * TN + a1 + b2, c2 = j2 * TN + a2 + b1, c3 = j2 * TN + a2 + b2;
-                c1 = c1 < k ? c1 : ca, c2 = c2 < k ? c2 : ca, c3 = c3 < k ? c3 : ca;
-                queue[qn + __popc(mc & lt)] = make_uint4((uint32_t)row, (uint32_t)ca | ((uint32_t)c1 << 16),
-                                                         (uint32_t)c2 | ((uint32_t)c3 << 16), 0u);
-            }
-            qn += (uint32_t)__popc(mc);
-            if (mf) {
-                unsigned int sf = 0;
-                if (lane == 0) sf = atomicAdd(tail_count + 1, (unsigned int)__popc(mf));
-                sf = __shfl_sync(0xffffffffu, sf, 0);
-                if (want_full) full[sf + __popc(mf & lt)] = (uint32_t)row;
-            }
-        }
-        if (lane == 0) tail_count[2 + worker * (RT * 4) + sw] = qn;
+#define AT_SCAN_WIDE 0
+#include "at_tc_scan.inc"
+#undef AT_SCAN_WIDE
     }
     tc_fence_before();
     __syncthreads();
@@ -1071,17 +902,297 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float *__restrict__ x,
     }
 }
 
+
+// ====================================================================================================== wide rows
+// d = 64 NS (2 <= NS <= 16: the use_convolution branch, d = 640).  Same arithmetic, same scan, same certification; the
+// product is accumulated over NS slices of 64 values: an accumulator receives 4 NS + 1 MMAs (the last one carries the norms)
+// before it is committed to the scanning warps.  Operand images: per 128 rows / 128 centroids NS tiles of 16 KB (the d = 64
+// layout per slice) followed by the 4 KB aug tile.  Neither operand fits shared memory whole, so BOTH are streamed slice by
+// slice: warp 3 brings the RT row tiles' slice (RT x 16 KB per stage, 2 stages), warp 0 the centroid tile's slice (16 KB,
+// 4 stages), in the order (super tile, centroid tile, slice) -- the row slices are fetched again for every centroid tile
+// (L2 / HBM traffic NS x 16 KB x RT per centroid tile; the tensor pipe, 41 MMAs per accumulator at NS = 10, is what binds).
+// Uncertified rows all go to the exact-scan list (k_assign_gemm over the list); there is no wide candidate re-check.
+constexpr uint32_t W_MAIN = TM * 128;                    // one 64-value slice of 128 rows / centroids: 16,384 B
+constexpr uint32_t W_AUG = TM * 32;                      // 4,096 B
+constexpr int WA_SLOTS = 2, WB_SLOTS = 4;
+constexpr uint32_t WOFF_A = 0;
+constexpr uint32_t WOFF_B = WOFF_A + WA_SLOTS * RT * W_MAIN;
+constexpr uint32_t WOFF_BAR = WOFF_B + WB_SLOTS * W_MAIN;
+constexpr uint32_t TCW_SMEM = WOFF_BAR + 256 + 1024;
+static_assert(TCW_SMEM <= 232448 && WB_SLOTS == B_SLOTS, "wide kernel shared memory / barrier layout");
+__host__ __device__ inline size_t wide_tile_bytes(int ns) { return (size_t)ns * W_MAIN + W_AUG; }
+
+__device__ __forceinline__ void bulk_expect_elect(uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_elect(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+        "}" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// rows -> wide image.  8 lanes per row (lane `chunk` owns the 16-byte chunk `chunk` of every slice), 4 rows per warp step.
+__global__ void __launch_bounds__(256) k_tc_rows_wide(const float *__restrict__ x, int64_t n, int64_t n_pad, int d,
+                                                      const float *__restrict__ sx_ptr, const float *__restrict__ shift,
+                                                      unsigned char *__restrict__ img, float *__restrict__ erow,
+                                                      float *__restrict__ xns) {
+    const int lane = threadIdx.x & 31, rsub = lane >> 3, chunk = lane & 7;
+    const int ns = d >> 6;
+    const size_t wt = wide_tile_bytes(ns);
+    const float Sx = sx_ptr[0];
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp * 4; r0 < n_pad; r0 += nwarps * 4) {   // warp-uniform trip count
+        const int64_t r = r0 + rsub;
+        const int rr = (int)(r & (TM - 1));
+        unsigned char *tile = img + (size_t)(r >> 7) * wt;
+        float q = 0.f, q0 = 0.f, e2 = 0.f;
+        for (int sl = 0; sl < ns; sl++) {
+            float xs[8];
+            if (r < n) {
+                const float4 *xp = reinterpret_cast<const float4 *>(x + r * d + sl * 64 + chunk * 8);
+                const float4 a = __ldg(xp), b = __ldg(xp + 1);
+                xs[0] = a.x, xs[1] = a.y, xs[2] = a.z, xs[3] = a.w, xs[4] = b.x, xs[5] = b.y, xs[6] = b.z, xs[7] = b.w;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; t++) xs[t] = 0.f;
+            }
+            __align__(16) __half2 hh[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                float v0 = xs[2 * t], v1 = xs[2 * t + 1];
+                q0 = fmaf(v0, v0, q0), q0 = fmaf(v1, v1, q0);
+                if (r < n) v0 -= shift[sl * 64 + chunk * 8 + 2 * t], v1 -= shift[sl * 64 + chunk * 8 + 2 * t + 1];
+                q = fmaf(v0, v0, q), q = fmaf(v1, v1, q);
+                const float s0 = Sx * v0, s1 = Sx * v1;
+                hh[t] = __floats2half2_rn(s0, s1);
+                const float2 f = __half22float2(hh[t]);
+                const float e0 = s0 - f.x, e1 = s1 - f.y;
+                e2 = fmaf(e0, e0, e2), e2 = fmaf(e1, e1, e2);
+            }
+            *reinterpret_cast<uint4 *>(tile + (size_t)sl * W_MAIN + sw128_off(rr, chunk)) = *reinterpret_cast<uint4 *>(hh);
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+        }
+        if (chunk == 0) {
+            const float xnS = Sx * Sx * q;
+            __align__(16) __half a[8];
+            const __half one = __float2half_rn(AUG_ONE), zero = __float2half_rn(0.f);
+            split3(xnS * AUG_INV, a[0], a[1], a[2]);
+            a[3] = a[4] = a[5] = one;
+            a[6] = a[7] = zero;
+            unsigned char *a_aug = tile + (size_t)ns * W_MAIN;
+            *reinterpret_cast<uint4 *>(a_aug + aug_off(rr, 0)) = *reinterpret_cast<uint4 *>(a);
+            *reinterpret_cast<uint4 *>(a_aug + aug_off(rr, 1)) = make_uint4(0, 0, 0, 0);
+            erow[r] = sqrtf(e2) * 1.001f + 1e-6f * Sx * sqrtf(q0) + 2e-7f * sqrtf(xnS);
+            xns[r] = xnS;
+        }
+    }
+}
+
+// centroids -> wide operand image (8 lanes per padded centroid, like k_tc_prep, looping over the slices)
+__global__ void __launch_bounds__(256) k_tc_prep_wide(const float *__restrict__ c, const float *__restrict__ shift, int k,
+                                                      int ktiles, int d, float *__restrict__ scale,
+                                                      unsigned char *__restrict__ op) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = idx >> 3, chunk = idx & 7;
+    if (j >= ktiles * TN) return;
+    const int ns = d >> 6;
+    const float S = scale[SC_S], R = scale[SC_RATIO];
+    const float Sc = S * R;
+    unsigned char *tile = op + (size_t)(j / TN) * wide_tile_bytes(ns);
+    const int r = j % TN;
+    const int js = j < k ? j : k - 1;
+    float e2 = 0.f, cn2 = 0.f;
+    for (int sl = 0; sl < ns; sl++) {
+        __align__(16) __half hi[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float cs = c[(size_t)js * d + sl * 64 + chunk * 8 + e] - shift[sl * 64 + chunk * 8 + e];
+            cn2 = fmaf(cs, cs, cn2);
+            const float v = -2.0f * Sc * cs;
+            hi[e] = __float2half_rn(v);
+            const float err = v - __half2float(hi[e]);
+            e2 = fmaf(err, err, e2);
+        }
+        *reinterpret_cast<uint4 *>(tile + (size_t)sl * W_MAIN + sw128_off(r, chunk)) = *reinterpret_cast<uint4 *>(hi);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+        cn2 += __shfl_xor_sync(0xffffffffu, cn2, o);
+    }
+    float en = sqrtf(e2) * 1.001f;
+    if (!(en == en)) en = INFINITY;
+    en = fmaxf(en, __shfl_xor_sync(0xffffffffu, en, 8));
+    en = fmaxf(en, __shfl_xor_sync(0xffffffffu, en, 16));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int *>(scale + SC_EMAX), __float_as_uint(en));
+    if (chunk == 0) {
+        __align__(16) __half a[8];
+        const __half w = __float2half_rn(AUG_ONE * R * R), zero = __float2half_rn(0.f);
+        a[0] = a[1] = a[2] = w;
+        split3(fmaf(cn2, S * S * AUG_INV, (j < k ? BIAS : BIAS + PAD_BUMP) * AUG_INV), a[3], a[4], a[5]);
+        a[6] = a[7] = zero;
+        unsigned char *aug = tile + (size_t)ns * W_MAIN;
+        *reinterpret_cast<uint4 *>(aug + aug_off(r, 0)) = *reinterpret_cast<uint4 *>(a);
+        *reinterpret_cast<uint4 *>(aug + aug_off(r, 1)) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_assign_tc_wide(const unsigned char *__restrict__ img, const float *__restrict__ erow, const float *__restrict__ xns, int64_t n,
+                 const unsigned char *__restrict__ op, int ktiles, int k, int ns, const float *__restrict__ scale,
+                 uint32_t key_mul, int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist,
+                 uint4 *__restrict__ tail, uint32_t *__restrict__ full, unsigned int *__restrict__ tail_count) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ uint32_t s_tmem_base;
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t bar0 = base + WOFF_BAR;
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int worker = (int)blockIdx.x, workers = (int)gridDim.x;
+    const int64_t nsuper = (n + SROWS - 1) / SROWS;
+    const int64_t my_tiles = worker < nsuper ? (nsuper - worker + workers - 1) / workers : 0;
+    const size_t wt = wide_tile_bytes(ns);
+
+    if (tid == 0) {
+        for (int i = 0; i < WA_SLOTS; i++) {
+            mbar_init(BAR(BAR_A_FULL + i), 1);
+            mbar_init(BAR(BAR_A_EMPTY + i), 1);
+        }
+        for (int i = 0; i < 4; i++) {
+            mbar_init(BAR(BAR_ACC_FULL + i), 1);
+            mbar_init(BAR(BAR_ACC_EMPTY + i), 4);
+        }
+        for (int i = 0; i < WB_SLOTS; i++) {
+            mbar_init(BAR(BAR_B_FULL + i), 1);
+            mbar_init(BAR(BAR_B_EMPTY + i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+    if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // ================================================================== centroid slices (whole warp, elected lane)
+        uint32_t st = 0, ph = 0;
+        for (int64_t i = 0; i < my_tiles; i++)
+            for (int jt = 0; jt < ktiles; jt++)
+                for (int sl = 0; sl <= ns; sl++) {
+                    mbar_waitx(BAR(BAR_B_EMPTY + st), ph ^ 1);
+                    bulk_g2s_elect(base + WOFF_B + st * W_MAIN, op + (size_t)jt * wt + (size_t)sl * W_MAIN, sl < ns ? W_MAIN : W_AUG,
+                                   BAR(BAR_B_FULL + st));
+                    if (++st == WB_SLOTS) st = 0, ph ^= 1;
+                }
+    } else if (warp == 3) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // ================================================================== row slices of the super tile's RT row tiles
+        uint32_t st = 0, ph = 0;
+        for (int64_t i = 0; i < my_tiles; i++) {
+            const unsigned char *t0 = img + (size_t)(worker + i * workers) * RT * wt;
+            for (int jt = 0; jt < ktiles; jt++)
+                for (int sl = 0; sl <= ns; sl++) {
+                    const uint32_t bytes = sl < ns ? W_MAIN : W_AUG;
+                    mbar_waitx(BAR(BAR_A_EMPTY + st), ph ^ 1);
+                    bulk_expect_elect(BAR(BAR_A_FULL + st), RT * bytes);
+#pragma unroll
+                    for (int rt = 0; rt < RT; rt++)
+                        bulk_copy_elect(base + WOFF_A + st * (RT * W_MAIN) + rt * W_MAIN, t0 + (size_t)rt * wt + (size_t)sl * W_MAIN,
+                                        bytes, BAR(BAR_A_FULL + st));
+                    if (++st == WA_SLOTS) st = 0, ph ^= 1;
+                }
+        }
+    } else if (warp == 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // ================================================================== MMA issuer (whole warp, elected lane)
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, u = 0;
+        for (int64_t i = 0; i < my_tiles; i++) {
+            for (int jt = 0; jt < ktiles; jt++, u++) {
+                for (int sl = 0; sl <= ns; sl++) {
+                    mbar_waitx(BAR(BAR_A_FULL + sa), pa);
+                    mbar_waitx(BAR(BAR_B_FULL + sb), pb);
+                    tc_fence_after();
+                    const uint32_t a0 = base + WOFF_A + sa * (RT * W_MAIN), b0 = base + WOFF_B + sb * W_MAIN;
+#pragma unroll
+                    for (int rt = 0; rt < RT; rt++) {
+                        const uint32_t v = u * RT + rt, acc = v % ACC_SLOTS, aph = (v / ACC_SLOTS) & 1;
+                        if (sl == 0) {
+                            mbar_waitx(BAR(BAR_ACC_EMPTY + acc), aph ^ 1);
+                            tc_fence_after();
+                        }
+                        const uint32_t dt = tmem + acc * TN;
+                        if (sl < ns) {
+                            const uint64_t dA = desc_sw128(a0 + rt * W_MAIN), dB = desc_sw128(b0);
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) umma_f16(dt, dA + 2 * kk, dB + 2 * kk, IDESC, (sl > 0 || kk > 0) ? 1u : 0u);
+                        } else {
+                            umma_f16(dt, desc_nosw(a0 + rt * W_MAIN), desc_nosw(b0), IDESC, 1u);
+                            umma_commit(BAR(BAR_ACC_FULL + acc));
+                        }
+                    }
+                    umma_commit(BAR(BAR_A_EMPTY + sa));
+                    umma_commit(BAR(BAR_B_EMPTY + sb));
+                    if (++sa == WA_SLOTS) sa = 0, pa ^= 1;
+                    if (++sb == WB_SLOTS) sb = 0, pb ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+#if AT_TC_RT == 3
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+#else
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+#endif
+#define AT_SCAN_WIDE 1
+#include "at_tc_scan.inc"
+#undef AT_SCAN_WIDE
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 bool assign_tc_supported(const at_index *ix) { return ix->d == 64 && ix->k >= 16 && ix->k <= 65536 && ix->op != nullptr; }
+bool assign_tc_wide_supported(const at_index *ix) {
+    return ix->d > 64 && ix->d % 64 == 0 && ix->d <= 1024 && ix->k >= 16 && ix->k <= 65536 && ix->op != nullptr;
+}
 
 int assign_tc_prepare(at_index *ix, cudaStream_t st) {
     if (!ix->tc_scale) AT_CUDA_OK(cudaMalloc(&ix->tc_scale, SC_COUNT * sizeof(float)));
     const float *shift = ix->ext_shift ? ix->ext_shift : ix->shift;
-    k_tc_scale<<<1, 32, 0, st>>>(ix->tc_max, ix->ext_sx, shift, ix->tc_scale);
+    k_tc_scale<<<1, 32, 0, st>>>(ix->tc_max, ix->ext_sx, shift, ix->d, ix->tc_scale);
     AT_LAUNCH_OK();
     const int total = ix->ktiles * TN * 8;
-    k_tc_prep<<<(total + 255) / 256, 256, 0, st>>>(ix->c, shift, ix->k, ix->ktiles, ix->tc_scale,
-                                                  reinterpret_cast<unsigned char *>(ix->op));
+    if (ix->d == 64)
+        k_tc_prep<<<(total + 255) / 256, 256, 0, st>>>(ix->c, shift, ix->k, ix->ktiles, ix->tc_scale,
+                                                      reinterpret_cast<unsigned char *>(ix->op));
+    else
+        k_tc_prep_wide<<<(total + 255) / 256, 256, 0, st>>>(ix->c, shift, ix->k, ix->ktiles, ix->d, ix->tc_scale,
+                                                           reinterpret_cast<unsigned char *>(ix->op));
     AT_LAUNCH_OK();
     return AT_OK;
 }
@@ -1093,11 +1204,14 @@ void tc_rows_free(at_tc_rows *r) {
 
 // (Re)builds the operand image of x.  sx: device float, the image scale (a power of two).
 // mean of the centroids (d == 64): 16 row slices x 64 columns, summed in a fixed order
-__global__ void __launch_bounds__(1024) k_tc_mean(const float *__restrict__ c, int k, float *__restrict__ shift) {
+// (d = 64 NS: block b takes columns 64 b .. 64 b + 63)
+__global__ void __launch_bounds__(1024) k_tc_mean(const float *__restrict__ c, int k, int d, float *__restrict__ shift_all) {
     __shared__ float part[16][64];
     const int col = threadIdx.x & 63, sl = threadIdx.x >> 6;
+    float *shift = shift_all + blockIdx.x * 64;
+    c += blockIdx.x * 64;
     float s = 0.f;
-    for (int j = sl; j < k; j += 16) s += c[(size_t)j * 64 + col];
+    for (int j = sl; j < k; j += 16) s += c[(size_t)j * d + col];
     part[sl][col] = s;
     __syncthreads();
     if (sl == 0) {
@@ -1109,13 +1223,18 @@ __global__ void __launch_bounds__(1024) k_tc_mean(const float *__restrict__ c, i
     }
 }
 
-int tc_mean(const float *c, int k, float *shift, cudaStream_t st) {
-    k_tc_mean<<<1, 1024, 0, st>>>(c, k, shift);
+int tc_mean(const float *c, int k, int d, float *shift, cudaStream_t st) {
+    k_tc_mean<<<d / 64, 1024, 0, st>>>(c, k, d, shift);
     AT_LAUNCH_OK();
     return AT_OK;
 }
 
-int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, const float *shift, cudaStream_t st) {
+size_t tc_operand_bytes(int d, int ktiles) {
+    return d == 64 ? (size_t)ktiles * 36864 /* room for the hi | lo | aug form */ : (size_t)ktiles * wide_tile_bytes(d / 64);
+}
+
+int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, const float *shift, cudaStream_t st,
+                  int d) {
     if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) {
         set_error("search: tensor path needs 16-byte aligned rows");
         return AT_ERR_UNSUPPORTED;
@@ -1125,11 +1244,16 @@ int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const fl
         return AT_ERR_UNSUPPORTED;
     }
     const int64_t n_pad = (n + SROWS - 1) / SROWS * SROWS;
-    if (n_pad > r->cap) {
+    if (d != 64 && l2norm) {
+        set_error("search: the wide-row tensor path takes pre-normalised rows");
+        return AT_ERR_UNSUPPORTED;
+    }
+    if (n_pad > r->cap || d != r->d) {
         AT_CUDA_OK(cudaStreamSynchronize(st));
         cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->full);
         r->img = nullptr, r->erow = r->xns = nullptr, r->tail = nullptr, r->full = nullptr, r->cap = 0;
-        AT_CUDA_OK(cudaMalloc(&r->img, (size_t)(n_pad / TM) * A_TILE_BYTES));
+        AT_CUDA_OK(cudaMalloc(&r->img, (size_t)(n_pad / TM) * (d == 64 ? (size_t)A_TILE_BYTES : wide_tile_bytes(d / 64))));
+        r->d = d;
         AT_CUDA_OK(cudaMalloc(&r->erow, sizeof(float) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->xns, sizeof(float) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->tail, sizeof(uint4) * (size_t)n_pad));
@@ -1144,8 +1268,12 @@ int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const fl
         AT_CUDA_OK(cudaMalloc(&r->tail_count, sizeof(unsigned int) * (size_t)(2 + sms * RT * 4)));
         r->tail_queues = sms * RT * 4;
     }
-    k_tc_rows<<<sms * 8, 256, 0, st>>>(x, n, n_pad, l2norm, sx, shift, reinterpret_cast<unsigned char *>(r->img), r->erow,
-                                       r->xns);
+    if (d == 64)
+        k_tc_rows<<<sms * 8, 256, 0, st>>>(x, n, n_pad, l2norm, sx, shift, reinterpret_cast<unsigned char *>(r->img), r->erow,
+                                           r->xns);
+    else
+        k_tc_rows_wide<<<sms * 8, 256, 0, st>>>(x, n, n_pad, d, sx, shift, reinterpret_cast<unsigned char *>(r->img), r->erow,
+                                                r->xns);
     AT_LAUNCH_OK();
     r->x = x, r->n = n, r->l2norm = l2norm;
     return AT_OK;
@@ -1231,6 +1359,36 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
         AT_LAUNCH_OK();
     }
     return AT_OK;
+}
+
+// rows: a prepared image of exactly these rows (k-means), or nullptr to build one in the index's own workspace.  Labels only
+// (callers that want exact distances of wide rows use the exact kernel).
+int assign_tc_wide_search(at_index *ix, const float *x, int64_t n, int32_t *labels32, int64_t *labels64, float *dist,
+                          at_tc_rows *rows, cudaStream_t st) {
+    static bool configured[MAX_DEVICES] = {};   // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
+        AT_CUDA_OK(cudaFuncSetAttribute(k_assign_tc_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCW_SMEM));
+        configured[dev] = true;
+    }
+    if (!rows) {
+        rows = &ix->rows;
+        int rc = tc_rows_build(rows, x, n, 0, ix->tc_scale + SC_SX, ix->ext_shift ? ix->ext_shift : ix->shift, st, ix->d);
+        if (rc != AT_OK) return rc;
+    }
+    const int64_t nsuper = (n + SROWS - 1) / SROWS;
+    const int sms = sm_count() > 0 ? sm_count() : 1;
+    int grid = sms;
+    if (grid > nsuper) grid = (int)nsuper;
+    if (grid < 1) grid = 1;
+    AT_CUDA_OK(cudaMemsetAsync(rows->tail_count, 0, 2 * sizeof(unsigned int), st));
+    k_assign_tc_wide<<<grid, TC_THREADS, TCW_SMEM, st>>>(reinterpret_cast<const unsigned char *>(rows->img), rows->erow, rows->xns,
+                                                        n, reinterpret_cast<const unsigned char *>(ix->op), ix->ktiles, ix->k,
+                                                        ix->d / 64, ix->tc_scale, 128u, labels32, labels64, dist, rows->tail,
+                                                        rows->full, rows->tail_count);
+    AT_LAUNCH_OK();
+    // every uncertified row: the exact wide-row kernel over the list
+    return launch_assign_gemm_list(ix, x, rows->full, rows->tail_count + 1, n, labels32, labels64, dist, st);
 }
 
 }  // namespace at

@@ -69,19 +69,29 @@ __device__ __forceinline__ u64g gfma2(u64g a, u64g b, u64g c) {
 }
 __device__ __forceinline__ void gunpack(u64g v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
+// list != nullptr: the rows are list[0 .. *n_list) (the uncertified rows of the wide tensor search) instead of 0 .. n.
 __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ c,
                                                         const float *__restrict__ cn, int k, int32_t *__restrict__ labels32,
-                                                        int64_t *__restrict__ labels64, float *__restrict__ dist) {
+                                                        int64_t *__restrict__ labels64, float *__restrict__ dist,
+                                                        const uint32_t *__restrict__ list,
+                                                        const unsigned int *__restrict__ n_list,
+                                                        unsigned long long *__restrict__ counters) {
     __shared__ __align__(16) float2 sa[2][GK][GM];   // (a, a): rows duplicated            16 KB
     __shared__ __align__(16) float sb[2][GK][GN];    //                                      8 KB
     __shared__ float s_xn[GM];
+    __shared__ int64_t s_row[GM];                    // global row of the block's row slot (-1: none)
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int64_t row0 = (int64_t)blockIdx.x * GM;
+    if (list) n = (int64_t)*n_list;
+    if (counters && blockIdx.x == 0 && tid == 0) atomicAdd(&counters[1], (unsigned long long)n);   // rows scanned exactly
+    if (row0 >= n) return;   // block-uniform
+    if (tid < GM) s_row[tid] = row0 + tid < n ? (list ? (int64_t)list[row0 + tid] : row0 + tid) : -1;
+    __syncthreads();
     // |x|^2 of the block's rows: one sequential FMA chain per row (thread t < 128 walks row t)
     if (tid < GM) {
         float q = 0.f;
-        const int64_t r = row0 + tid;
-        if (r < n) {
+        const int64_t r = s_row[tid];
+        if (r >= 0) {
             const float *xr = x + r * d;
             for (int t = 0; t < d; t++) q = fmaf(xr[t], xr[t], q);
         }
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict_
     const bool vec = (d & 3) == 0;
     auto fetch = [&](const float *base, int64_t r, int64_t rmax, int k0) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < rmax) {
+        if (r >= 0 && r < rmax) {
             const float *p = base + r * d + k0 + lk;
             if (vec && k0 + lk + 3 < d) v = *reinterpret_cast<const float4 *>(p);
             else {
@@ -120,13 +130,14 @@ __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict_
         for (int r = 0; r < 8; r++)
 #pragma unroll
             for (int q = 0; q < 4; q++) acc[r][q] = 0ull;
-        float4 av = fetch(x, row0 + lr, n, 0), bv = fetch(c, (int64_t)j0 + lr, k, 0);
+        const int64_t xrow = s_row[lr];   // this loader thread's row of x (-1: zero fill)
+        float4 av = fetch(x, xrow, INT64_MAX, 0), bv = fetch(c, (int64_t)j0 + lr, k, 0);
         __syncthreads();   // the previous tile's last chunk (and s_xn) are done with
         stash(0, av, bv);
         __syncthreads();
         for (int ch = 0; ch < nchunk; ch++) {
             const int buf = ch & 1;
-            if (ch + 1 < nchunk) av = fetch(x, row0 + lr, n, (ch + 1) * GK), bv = fetch(c, (int64_t)j0 + lr, k, (ch + 1) * GK);
+            if (ch + 1 < nchunk) av = fetch(x, xrow, INT64_MAX, (ch + 1) * GK), bv = fetch(c, (int64_t)j0 + lr, k, (ch + 1) * GK);
 #pragma unroll
             for (int kk = 0; kk < GK; kk++) {
                 // rows 4 ty .. 4 ty + 3 and 64 + 4 ty ..: four 128-bit loads of (a, a) pairs; columns: two loads
@@ -180,8 +191,8 @@ __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict_
     if (tx == 0) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            const int64_t row = row0 + (r < 4 ? 0 : 64) + ty * 4 + (r & 3);
-            if (row < n) {
+            const int64_t row = s_row[(r < 4 ? 0 : 64) + ty * 4 + (r & 3)];
+            if (row >= 0) {
                 const int bj = bidx[r] == 0x7FFFFFFF ? 0 : bidx[r];
                 if (labels32) labels32[row] = bj;
                 if (labels64) labels64[row] = bj;
@@ -192,7 +203,18 @@ __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict_
 }
 
 int launch_assign_gemm(const at_index *ix, const float *x, int64_t n, int32_t *l32, int64_t *l64, float *dist, cudaStream_t st) {
-    k_assign_gemm<<<(unsigned)ceil_div(n, GM), 256, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l32, l64, dist);
+    k_assign_gemm<<<(unsigned)ceil_div(n, GM), 256, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l32, l64, dist, nullptr, nullptr,
+                                                             nullptr);
+    AT_LAUNCH_OK();
+    return AT_OK;
+}
+
+// the listed rows only (blocks beyond the list's length leave at once; the length lives on the device)
+int launch_assign_gemm_list(const at_index *ix, const float *x, const uint32_t *list, const unsigned int *n_list, int64_t n_max,
+                            int32_t *l32, int64_t *l64, float *dist, cudaStream_t st) {
+    const int64_t blocks = ceil_div(n_max, GM);
+    k_assign_gemm<<<(unsigned)blocks, 256, 0, st>>>(x, n_max, ix->d, ix->c, ix->cn, ix->k, l32, l64, dist, list, n_list,
+                                                    ix->tc_counters);
     AT_LAUNCH_OK();
     return AT_OK;
 }

@@ -18,6 +18,7 @@ struct at_tc_rows {
     const float *x = nullptr;   // what the image was built from
     int64_t n = 0;
     int l2norm = 0;
+    int d = 64;                 // row width the image was allocated for (64, or 64 NS for the wide-row kernel)
 };
 
 struct at_index {
@@ -35,7 +36,7 @@ struct at_index {
     // Centering: |x - c|^2 = |(x - m) - (c - m)|^2 for any m, and the fp16 rounding errors of the operands scale with
     // |x - m| |c - m| instead of |x| |c| -- m = mean of the centroids (the index's own `shift`, refreshed with the
     // centroids), or the vector an attached row image was built with (`ext_shift`, k-means: fixed for the training run)
-    float *shift = nullptr;         // (64) device
+    float *shift = nullptr;         // (d) device
     const float *ext_shift = nullptr;
     at_tc_rows rows;            // workspace of one-off searches
     unsigned long long *tc_counters = nullptr;  // device: rows re-checked on their candidate columns, rows scanned exactly (cumulative)
@@ -130,8 +131,16 @@ __device__ __forceinline__ float l2_denominator(float sumsq) { return __fadd_rn(
 int assign_tc_prepare(at_index *ix, cudaStream_t st);
 int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, int32_t *labels32,
                      int64_t *labels64, float *dist, int exact_dist, at_tc_rows *rows, cudaStream_t st);
-int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, const float *shift, cudaStream_t st);
-int tc_mean(const float *c, int k, float *shift, cudaStream_t st);   // shift = mean of the k centroids (d == 64)
+int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const float *sx, const float *shift, cudaStream_t st,
+                  int d = 64);
+int tc_mean(const float *c, int k, int d, float *shift, cudaStream_t st);   // shift = mean of the k centroids (d = 64 NS)
+bool assign_tc_wide_supported(const at_index *ix);   // d = 128 .. 1024, a multiple of 64: the slice-accumulating kernel
+size_t tc_operand_bytes(int d, int ktiles);          // bytes of the centroid operand images
+int assign_tc_wide_search(at_index *ix, const float *x, int64_t n, int32_t *labels32, int64_t *labels64, float *dist,
+                          at_tc_rows *rows, cudaStream_t st);
+// at_conv.cu: the exact wide-row kernel over a list of rows (list, *n_list on the device; at most n_max)
+int launch_assign_gemm_list(const at_index *ix, const float *x, const uint32_t *list, const unsigned int *n_list, int64_t n_max,
+                            int32_t *l32, int64_t *l64, float *dist, cudaStream_t st);
 void tc_rows_free(at_tc_rows *r);
 bool assign_tc_supported(const at_index *ix);
 // at_conv.cu: exact fp32 search for rows wider than 128 values (pre-normalised rows)

@@ -542,18 +542,25 @@ static int launch_simt(const at_index *ix, const float *x, int64_t n, int l2norm
 static int index_search(at_index *ix, const float *x, int64_t n, int l2norm, int algo, int32_t *l32,
                         int64_t *l64, float *dist, int exact_dist, at_tc_rows *rows, cudaStream_t st) {
     if (n == 0) return AT_OK;
-    bool tc = false;
+    bool tc = false, tcw = false;
+    // wide rows (d = 64 NS): labels from the slice-accumulating tensor kernel; pre-normalised rows, no exact distances
+    const bool wide_ok = assign_tc_wide_supported(ix) && !l2norm && !(dist && exact_dist);
     if (algo == AT_ALGO_TENSOR) {
-        if (!assign_tc_supported(ix)) {
-            set_error("search: tensor path needs d == 64 and k >= 16 (d=%d, k=%d)", ix->d, ix->k);
+        if (assign_tc_supported(ix)) tc = true;
+        else if (wide_ok) tcw = true;
+        else {
+            set_error("search: tensor path needs d == 64 (or a multiple of 64 up to 1024 with pre-normalised rows and no "
+                      "distances) and k >= 16 (d=%d, k=%d)", ix->d, ix->k);
             return AT_ERR_UNSUPPORTED;
         }
-        tc = true;
     } else if (algo == AT_ALGO_AUTO) {
         tc = assign_tc_supported(ix) && ix->k >= 64;
+        // (below ~8 M scores the exact tile kernel is as fast: the image build and a 148-CTA launch are fixed costs)
+        tcw = !tc && wide_ok && ix->k >= 64 && !dist && n * (int64_t)ix->k >= (8LL << 20);
     }
     ProfScope prof(PROF_SEARCH, st);
     if (tc) return assign_tc_search(ix, x, n, l2norm, l32, l64, dist, exact_dist, rows, st);
+    if (tcw) return assign_tc_wide_search(ix, x, n, l32, l64, dist, rows && rows->d == ix->d ? rows : nullptr, st);
     return launch_simt(ix, x, n, l2norm, l32, l64, dist, st);
 }
 
@@ -604,9 +611,9 @@ int at_index_destroy(at_index *ix) {
 
 // canonical norms + (d == 64) the tensor operands of the centroids currently in ix->c
 static int index_refresh(at_index *ix, cudaStream_t st) {
-    const bool tc = assign_tc_supported(ix);
+    const bool tc = assign_tc_supported(ix) || assign_tc_wide_supported(ix);
     if (tc && !ix->ext_shift) {   // the index's own centring vector follows its centroids
-        int rc = tc_mean(ix->c, ix->k, ix->shift, st);
+        int rc = tc_mean(ix->c, ix->k, ix->d, ix->shift, st);
         if (rc != AT_OK) return rc;
     }
     k_centroid_norms<<<(ix->k + 127) / 128, 128, 0, st>>>(ix->c, ix->k, ix->d, ix->cn, tc ? ix->tc_max : nullptr,
@@ -628,15 +635,15 @@ int at_index_set_centroids(at_index *ix, const float *centroids, int k, void *st
         int ktiles = (k + 127) / 128;
         AT_CUDA_OK(cudaMalloc(&ix->c, sizeof(float) * (size_t)k * ix->d));
         AT_CUDA_OK(cudaMalloc(&ix->cn, sizeof(float) * (size_t)k));
-        if (ix->d == 64) {
-            AT_CUDA_OK(cudaMalloc(&ix->op, (size_t)ktiles * 36864)   /* room for the hi | lo | aug form */);
+        if (ix->d % 64 == 0 && ix->d <= 1024) {
+            AT_CUDA_OK(cudaMalloc(&ix->op, tc_operand_bytes(ix->d, ktiles)));
             if (!ix->tc_max) {
                 AT_CUDA_OK(cudaMalloc(&ix->tc_max, 4 * sizeof(unsigned int)));
                 AT_CUDA_OK(cudaMemsetAsync(ix->tc_max, 0, 4 * sizeof(unsigned int), st));
             }
             if (!ix->shift) {
-                AT_CUDA_OK(cudaMalloc(&ix->shift, 64 * sizeof(float)));
-                AT_CUDA_OK(cudaMemsetAsync(ix->shift, 0, 64 * sizeof(float), st));
+                AT_CUDA_OK(cudaMalloc(&ix->shift, ix->d * sizeof(float)));
+                AT_CUDA_OK(cudaMemsetAsync(ix->shift, 0, ix->d * sizeof(float), st));
             }
             if (!ix->tc_counters) {
                 AT_CUDA_OK(cudaMalloc(&ix->tc_counters, 8 * sizeof(unsigned long long)));
@@ -775,7 +782,7 @@ int at_kmeans_begin_on(at_kmeans *km, float max_abs, int64_t n_total, void *stre
     // operands for it; the image itself is built by the first accumulate
     km->rows_valid = false;
     km->prev_valid = false;
-    if (km->d == 64) {
+    if (km->d % 64 == 0 && km->d <= 1024) {
         float sx = 1.0f;
         if (max_abs > 0.f) {
             int ex;
@@ -790,7 +797,7 @@ int at_kmeans_begin_on(at_kmeans *km, float max_abs, int64_t n_total, void *stre
         AT_LAUNCH_OK();
         km->index->ext_sx = km->rows_sx;
         km->index->ext_shift = nullptr;   // until the first accumulate builds the image and fixes its centre
-        if (km->index->k > 0 && assign_tc_supported(km->index)) {
+        if (km->index->k > 0 && (assign_tc_supported(km->index) || assign_tc_wide_supported(km->index))) {
             int rc = index_refresh(km->index, st);
             if (rc != AT_OK) return rc;
         }
@@ -848,18 +855,19 @@ int at_kmeans_accumulate(at_kmeans *km, const float *x, int64_t n_local, int l2n
     int32_t *labels = labels32 ? labels32 : km->labels;
     // tensor path: the operand image of the rows is built once and re-used while (x, n_local) stay the same
     at_tc_rows *rows = nullptr;
-    const bool tc = algo == AT_ALGO_TENSOR || (algo == AT_ALGO_AUTO && assign_tc_supported(km->index) && km->index->k >= 64);
-    if (tc && assign_tc_supported(km->index) && km->rows_sx) {
+    const bool tc_any = assign_tc_supported(km->index) || assign_tc_wide_supported(km->index);
+    const bool tc = algo == AT_ALGO_TENSOR || (algo == AT_ALGO_AUTO && tc_any && km->index->k >= 64);
+    if (tc && tc_any && km->rows_sx) {
         if (!km->rows_valid || km->rows.x != x || km->rows.n != n_local) {
             // centre of the image = mean of the centroids it is first searched with, fixed until the image is rebuilt;
             // the index's operands are re-derived for it
-            if (!km->rows_shift) AT_CUDA_OK(cudaMalloc(&km->rows_shift, 64 * sizeof(float)));
-            rc = tc_mean(km->index->c, km->k, km->rows_shift, st);
+            if (!km->rows_shift) AT_CUDA_OK(cudaMalloc(&km->rows_shift, km->d * sizeof(float)));
+            rc = tc_mean(km->index->c, km->k, km->d, km->rows_shift, st);
             if (rc != AT_OK) return rc;
             km->index->ext_shift = km->rows_shift;
             rc = index_refresh(km->index, st);
             if (rc != AT_OK) return rc;
-            rc = tc_rows_build(&km->rows, x, n_local, 0, km->rows_sx, km->rows_shift, st);
+            rc = tc_rows_build(&km->rows, x, n_local, 0, km->rows_sx, km->rows_shift, st, km->d);
             if (rc != AT_OK) return rc;
             km->rows_valid = true;
         }

@@ -367,3 +367,52 @@ def test_wide_row_search_and_update_match_the_oracle():
     rel = np.linalg.norm(got - ref["centroids"], axis=1) / np.maximum(np.linalg.norm(ref["centroids"], axis=1), 1e-30)
     assert int(stats.cpu().numpy()[1]) == ref["nsplit"] and mism.mean() < 1e-3
     assert (rel[~touched] <= 1e-4).all()
+
+
+@pytest.mark.parametrize("n,d,k", [(30000, 640, 500), (9000, 128, 1000), (70000, 320, 130), (20000, 1024, 512)])
+def test_wide_row_tensor_search_equals_the_exact_wide_row_kernel(n, d, k):
+    """d = 64 NS (the use_convolution regime, d = 640): the slice-accumulating tcgen05 search must return the labels of the
+    exact fp32 tile kernel (k_assign_gemm), whose sample is checked against the scalar FAISS restatement."""
+    import torch
+    from at_b200 import FlatL2, _lib, row_l2norm
+    from oracle import faiss_ref
+
+    g = torch.Generator(device="cuda").manual_seed(n + d + k)
+    base = torch.rand(n, 64, device="cuda", generator=g)
+    x = row_l2norm((base.repeat(1, d // 64) * (1.0 + 0.3 * torch.rand(n, d, device="cuda", generator=g))).contiguous())
+    c = (x[torch.randperm(n, device="cuda", generator=g)[:k]] + 0.01 * torch.randn(k, d, device="cuda", generator=g)).contiguous()
+    ix = FlatL2(d)
+    ix.set_centroids(c)
+    le, _ = ix.search(x, algo=_lib.ALGO_SIMT, want_dist=False)
+    lt, _ = ix.search(x, algo=_lib.ALGO_TENSOR, want_dist=False)
+    _, full = ix.tc_stats()
+    print(f"wide tensor search n={n} d={d} k={k}: mismatches {int((le != lt).sum())}, rows scanned exactly {full / n:.2%}")
+    assert torch.equal(le, lt)
+    la, _ = ix.search(x, want_dist=False)   # ALGO_AUTO: whichever it picks, the same labels
+    assert torch.equal(la, le)
+    idx = torch.linspace(0, n - 1, 1500, device="cuda").long()
+    ref, d1, d2 = faiss_ref.assign_l2_scalar(x[idx].cpu().numpy(), c.cpu().numpy())
+    mism = lt[idx].cpu().numpy() != ref
+    assert ((d2 - d1)[mism] / np.maximum(d1[mism], 1e-30) < 1e-3).all() and mism.mean() < 2e-2
+
+
+def test_wide_row_lloyd_tensor_vs_exact_bit_identical():
+    """k-means over 640-value rows: the tensor path (row image built once, centred on the first centroids' mean) and the exact
+    path give the same labels in every iteration, hence bit-identical centroids (exact integer sums)."""
+    import torch
+    from at_b200 import LloydTrainer, _lib, row_l2norm
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, d, k = 60000, 640, 200
+    x = row_l2norm(torch.rand(n, 64, device="cuda", generator=g).repeat(1, 10) * (1.0 + 0.3 * torch.rand(n, d, device="cuda", generator=g)))
+    init = x[:k].contiguous()
+    outs = []
+    for algo in (_lib.ALGO_SIMT, _lib.ALGO_TENSOR):
+        tr = LloydTrainer(d, k, algo=algo)
+        tr.begin(x)
+        tr.set_centroids(init)
+        lab = torch.empty(n, dtype=torch.int32, device="cuda")
+        for _ in range(5):
+            tr.step(x, None, lab)
+        outs.append((lab.clone(), tr.get_centroids()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

@@ -41,8 +41,14 @@ ms, wn = timed(lambda: at_b200.row_l2norm(wide))
 print(f"at_row_l2norm (d=640) {ms:.3f} ms = {n * 640 * 8 / ms / 1e6:.0f} GB/s")
 ix = FlatL2(640)
 ix.set_centroids(wn[torch.randperm(n, device='cuda')[:k]].contiguous())
+from at_b200 import _lib
+ms, _ = timed(lambda: ix.search(wn, want_dist=False, algo=_lib.ALGO_SIMT), reps=3)
+print(f"exact wide-row search (fp32 tile kernel) K={k}: {ms:.2f} ms = {2.0 * n * k * 640 / ms / 1e9:.1f} TFLOP/s fp32 (2NKd)")
+lab_e, _ = ix.search(wn, want_dist=False, algo=_lib.ALGO_SIMT)
 ms, _ = timed(lambda: ix.search(wn, want_dist=False), reps=3)
-print(f"exact wide-row search K={k}: {ms:.2f} ms = {2.0 * n * k * 640 / ms / 1e9:.1f} TFLOP/s fp32 (2NKd)")
+lab_t, _ = ix.search(wn, want_dist=False)
+print(f"wide-row tensor search (tcgen05, slices accumulated, image built per call) K={k}: {ms:.2f} ms = "
+      f"{2.0 * n * k * 640 / ms / 1e9:.1f} TFLOP/s algorithmic; labels equal to the exact kernel's: {bool((lab_e == lab_t).all())}")
 tr = LloydTrainer(640, k)
 tr.begin(wn)
 tr.set_centroids(wn[:k].contiguous())
