@@ -123,8 +123,9 @@ int at_row_l2norm(const float *x, int64_t n, int d, float *out, void *stream);
  * conv_output.transpose(1, 2).reshape(-1, num_kernels * n_mels): out[i, m * num_kernels + c] = bias[c] + sum_t weight[c][t] *
  * x[i, m + t - kernel_size // 2].  x (n, n_mels), weight (num_kernels, kernel_size), bias (num_kernels), out (n, n_mels *
  * num_kernels): device fp32.  Odd kernel_size <= 15 (an even one changes the width), num_kernels <= 256.  The wide rows go
- * through at_row_l2norm, at_kmeans_* and at_index_search (d up to 1024; rows wider than 128 values use a tiled exact fp32
- * search and must be normalised beforehand). */
+ * through at_row_l2norm, at_kmeans_* and at_index_search (d up to 1024; rows wider than 128 values must be normalised
+ * beforehand and are searched by the exact fp32 tile kernel or, for d a multiple of 64 and labels only, by the
+ * slice-accumulating tcgen05 kernel, which returns the exact kernel's labels). */
 int at_conv_expand(const float *x, int64_t n, int n_mels, const float *weight, const float *bias, int num_kernels,
                    int kernel_size, float *out, void *stream);
 
