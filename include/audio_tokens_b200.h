@@ -154,9 +154,10 @@ int at_index_tc_stats(at_index *index, uint64_t out[2]);
 const float *at_index_centroids(const at_index *index);
 /* search(x, 1).  l2norm_rows != 0 applies normalize_vectors to each row while loading.
  * Any of labels32 / labels64 / dist may be NULL.  algo: AT_ALGO_*; AUTO picks the tcgen05 kernel when
- * d == 64 and k >= 64, else the exact fp32 SIMT kernel.  Both return the argmin of the same fp32 formula
- * (the tensor path certifies each row from its accumulators or re-checks the candidates with it) and, in dist,
- * that formula's value for the returned label. */
+ * d == 64 and k >= 64 (or d a multiple of 64 up to 1024, k >= 64, pre-normalised rows, labels only and at least 8 M
+ * row x centroid pairs: the slice-accumulating form), else the exact fp32 SIMT kernel.  Both return the argmin of the
+ * same fp32 formula (the tensor path certifies each row from its accumulators or re-checks / re-scans it with that
+ * formula) and, in dist, that formula's value for the returned label. */
 int at_index_search(at_index *index, const float *x, int64_t n, int l2norm_rows, int algo,
                     int32_t *labels32, int64_t *labels64, float *dist, void *stream);
 
