@@ -911,7 +911,8 @@ __global__ void __launch_bounds__(256) k_exact_dist(const float *__restrict__ x,
 // slice: warp 3 brings the RT row tiles' slice (RT x 16 KB per stage, 2 stages), warp 0 the centroid tile's slice (16 KB,
 // 4 stages), in the order (super tile, centroid tile, slice) -- the row slices are fetched again for every centroid tile
 // (L2 / HBM traffic NS x 16 KB x RT per centroid tile; the tensor pipe, 41 MMAs per accumulator at NS = 10, is what binds).
-// Uncertified rows all go to the exact-scan list (k_assign_gemm over the list); there is no wide candidate re-check.
+// Uncertified rows: the candidate columns are re-checked by k_tc_tail_wide with the exact wide kernel's arithmetic, the rows
+// without a usable candidate list go through k_assign_gemm over the list.
 constexpr uint32_t W_MAIN = TM * 128;                    // one 64-value slice of 128 rows / centroids: 16,384 B
 constexpr uint32_t W_AUG = TM * 32;                      // 4,096 B
 constexpr int WA_SLOTS = 2, WB_SLOTS = 4;
@@ -1361,6 +1362,49 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     return AT_OK;
 }
 
+// Candidate re-check of the wide search: block q works through candidate queue q, four lanes per row -- lane t evaluates
+// candidate column t with the EXACT wide kernel's arithmetic (k_assign_gemm: |x|^2 and <x, c> each ONE sequential fp32 FMA
+// chain over the d values, |c|^2 from the index, (|x|^2 + |c|^2) - 2 <x, c> clamped at 0), the lowest index wins exact ties.
+__global__ void __launch_bounds__(256) k_tc_tail_wide(const float *__restrict__ x, int d, const float *__restrict__ c,
+                                                      const float *__restrict__ cn, const uint4 *__restrict__ tail_all,
+                                                      const unsigned int *__restrict__ tail_count, int64_t nsuper, int workers,
+                                                      int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
+                                                      float *__restrict__ dist, unsigned long long *__restrict__ counters) {
+    const int q = (int)blockIdx.x, t = threadIdx.x & 3;
+    const unsigned int n_cand = tail_count[2 + q];
+    const uint4 *__restrict__ tail = tail_all + tc_queue_base(nsuper, workers, q / (RT * 4), q % (RT * 4));
+    const unsigned int per_pass = blockDim.x >> 2;
+    // warp-uniform trip count (the 4-lane reductions shuffle with the full mask)
+    for (unsigned int e0 = 0; e0 < n_cand; e0 += per_pass) {
+        const unsigned int e = e0 + (threadIdx.x >> 2);
+        const bool live = e < n_cand;
+        const uint4 cc = tail[live ? e : e0];
+        const int64_t row = (int64_t)cc.x;
+        const int col = t == 0 ? (int)(cc.y & 0xFFFFu) : t == 1 ? (int)(cc.y >> 16) : t == 2 ? (int)(cc.z & 0xFFFFu) : (int)(cc.z >> 16);
+        const float *xr = x + row * d, *cr = c + (size_t)col * d;
+        float xn = 0.f, ip = 0.f;
+        for (int i = 0; i < d; i += 4) {   // d is a multiple of 64
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + i)), cv = __ldg(reinterpret_cast<const float4 *>(cr + i));
+            xn = fmaf(xv.x, xv.x, xn), xn = fmaf(xv.y, xv.y, xn), xn = fmaf(xv.z, xv.z, xn), xn = fmaf(xv.w, xv.w, xn);
+            ip = fmaf(xv.x, cv.x, ip), ip = fmaf(xv.y, cv.y, ip), ip = fmaf(xv.z, cv.z, ip), ip = fmaf(xv.w, cv.w, ip);
+        }
+        float bd = l2_expanded(xn, __ldg(cn + col), ip);
+        int best = col;
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+            if (od < bd || (od == bd && ob < best)) bd = od, best = ob;
+        }
+        if (live && t == 0) {
+            if (labels32) labels32[row] = best;
+            if (labels64) labels64[row] = best;
+            if (dist) dist[row] = bd;
+        }
+    }
+    if (counters && threadIdx.x == 0 && n_cand) atomicAdd(&counters[0], (unsigned long long)n_cand);
+}
+
 // rows: a prepared image of exactly these rows (k-means), or nullptr to build one in the index's own workspace.  Labels only
 // (callers that want exact distances of wide rows use the exact kernel).
 int assign_tc_wide_search(at_index *ix, const float *x, int64_t n, int32_t *labels32, int64_t *labels64, float *dist,
@@ -1387,7 +1431,11 @@ int assign_tc_wide_search(at_index *ix, const float *x, int64_t n, int32_t *labe
                                                         ix->d / 64, ix->tc_scale, 128u, labels32, labels64, dist, rows->tail,
                                                         rows->full, rows->tail_count);
     AT_LAUNCH_OK();
-    // every uncertified row: the exact wide-row kernel over the list
+    // uncertified rows: the (at most four) candidate columns with the exact kernel's arithmetic, the rest (rare) through the
+    // exact wide-row kernel over the list
+    k_tc_tail_wide<<<grid * RT * 4, 256, 0, st>>>(x, ix->d, ix->c, ix->cn, rows->tail, rows->tail_count, nsuper, grid, labels32,
+                                                 labels64, dist, ix->tc_counters);
+    AT_LAUNCH_OK();
     return launch_assign_gemm_list(ix, x, rows->full, rows->tail_count + 1, n, labels32, labels64, dist, st);
 }
 
