@@ -113,7 +113,9 @@ class IndexFlatL2:
         self._xb = np.zeros((0, self.d), dtype=np.float32)
         self._ix.k = 0
 
-    def search(self, x, k: int = 1, l2norm_rows: bool = False, chunk_rows: int = 1 << 22):
+    def search(self, x, k: int = 1, l2norm_rows: bool = False, chunk_rows: int = 1 << 22, want_dist: bool = True):
+        """FAISS's search(x, k).  want_dist=False (not a FAISS argument; the stage classes discard D) returns (None, I) and
+        lets the library skip the exact-distance pass -- and take the tensor path for rows wider than 64 values."""
         import torch
 
         if k != 1:
@@ -125,7 +127,7 @@ class IndexFlatL2:
             x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2 and x.shape[1] == self.d
         n = x.shape[0]
-        D = np.empty((n, 1), dtype=np.float32)
+        D = np.empty((n, 1), dtype=np.float32) if want_dist else None
         I = np.empty((n, 1), dtype=np.int64)
         for a in range(0, n, chunk_rows):
             b = min(n, a + chunk_rows)
@@ -135,7 +137,8 @@ class IndexFlatL2:
                 from . import row_l2norm
 
                 xd = row_l2norm(xd)
-            lab, dist = self._ix.search(xd, l2norm_rows=fused, labels_dtype=torch.int64)
+            lab, dist = self._ix.search(xd, l2norm_rows=fused, labels_dtype=torch.int64, want_dist=want_dist)
             I[a:b, 0] = lab.cpu().numpy()
-            D[a:b, 0] = dist.cpu().numpy()
+            if want_dist:
+                D[a:b, 0] = dist.cpu().numpy()
         return D, I

@@ -69,10 +69,10 @@ class SpecTokenizer:
         if self.config.use_convolution:
             # conv expansion + normalize_vectors on the device, then the wide-row exact search
             wide = at_b200.row_l2norm(self.apply_convolution(batch_data))
-            _, tokens = self.index.search(wide, 1)
+            _, tokens = self.index.search(wide, 1, want_dist=False)   # the reference discards D (:77)
         else:
             # normalize_vectors + index.search(x, 1) in one kernel; int64 labels like faiss
-            _, tokens = self.index.search(batch_data, 1, l2norm_rows=True)
+            _, tokens = self.index.search(batch_data, 1, l2norm_rows=True, want_dist=False)   # the reference discards D (:77)
         tokens = np.squeeze(tokens, 1)
         start = 0
         for spec_file, n_frames in zip(batch_files, lengths):

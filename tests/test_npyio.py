@@ -69,7 +69,7 @@ def test_spec_tokenizer_process_batch_splits_tokens_per_file(tmp_path):
     files = sorted(_write_files(src, n=9, seed=5))
 
     class FakeIndex:
-        def search(self, x, k, l2norm_rows=False):
+        def search(self, x, k, l2norm_rows=False, want_dist=True):
             assert k == 1 and l2norm_rows and x.dtype == np.float32 and x.shape[1] == 64
             lab = np.arange(x.shape[0], dtype=np.int64)[:, None]   # token = global frame number: easy to check
             return np.zeros((x.shape[0], 1), dtype=np.float32), lab
