@@ -1200,6 +1200,7 @@ int assign_tc_prepare(at_index *ix, cudaStream_t st) {
 
 void tc_rows_free(at_tc_rows *r) {
     cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->full), cudaFree(r->tail_count);
+    cudaFree(r->keys);
     *r = at_tc_rows();
 }
 
@@ -1251,14 +1252,15 @@ int tc_rows_build(at_tc_rows *r, const float *x, int64_t n, int l2norm, const fl
     }
     if (n_pad > r->cap || d != r->d) {
         AT_CUDA_OK(cudaStreamSynchronize(st));
-        cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->full);
-        r->img = nullptr, r->erow = r->xns = nullptr, r->tail = nullptr, r->full = nullptr, r->cap = 0;
+        cudaFree(r->img), cudaFree(r->erow), cudaFree(r->xns), cudaFree(r->tail), cudaFree(r->full), cudaFree(r->keys);
+        r->img = nullptr, r->erow = r->xns = nullptr, r->tail = nullptr, r->full = nullptr, r->keys = nullptr, r->cap = 0;
         AT_CUDA_OK(cudaMalloc(&r->img, (size_t)(n_pad / TM) * (d == 64 ? (size_t)A_TILE_BYTES : wide_tile_bytes(d / 64))));
         r->d = d;
         AT_CUDA_OK(cudaMalloc(&r->erow, sizeof(float) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->xns, sizeof(float) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->tail, sizeof(uint4) * (size_t)n_pad));
         AT_CUDA_OK(cudaMalloc(&r->full, sizeof(uint32_t) * (size_t)n_pad));
+        if (d != 64) AT_CUDA_OK(cudaMalloc(&r->keys, sizeof(unsigned long long) * (size_t)n_pad));
         r->cap = n_pad;
     }
     const int sms = sm_count() > 0 ? sm_count() : 1;
@@ -1362,41 +1364,54 @@ int assign_tc_search(at_index *ix, const float *x, int64_t n, int l2norm_rows, i
     return AT_OK;
 }
 
-// Candidate re-check of the wide search: block q works through candidate queue q, four lanes per row -- lane t evaluates
-// candidate column t with the EXACT wide kernel's arithmetic (k_assign_gemm: |x|^2 and <x, c> each ONE sequential fp32 FMA
-// chain over the d values, |c|^2 from the index, (|x|^2 + |c|^2) - 2 <x, c> clamped at 0), the lowest index wins exact ties.
-__global__ void __launch_bounds__(256) k_tc_tail_wide(const float *__restrict__ x, int d, const float *__restrict__ c,
-                                                      const float *__restrict__ cn, const uint4 *__restrict__ tail_all,
-                                                      const unsigned int *__restrict__ tail_count, int64_t nsuper, int workers,
-                                                      int32_t *__restrict__ labels32, int64_t *__restrict__ labels64,
-                                                      float *__restrict__ dist, unsigned long long *__restrict__ counters) {
-    const int q = (int)blockIdx.x, t = threadIdx.x & 3;
+// Candidate re-check of the wide search: block q works through candidate queue q, a warp per row.  The warp stages the row
+// and its (at most four) candidate centroids in shared memory with coalesced loads (a thread walking its own 2.5 KB row
+// touches a new sector with every 16 bytes and the kernel becomes sector-bound: measured 0.22 ms), then lanes 0-3 evaluate
+// one candidate each with the EXACT wide kernel's arithmetic (k_assign_gemm: |x|^2 and <x, c> each ONE sequential fp32 FMA
+// chain over the d values, |c|^2 from the index, (|x|^2 + |c|^2) - 2 <x, c> clamped at 0); the lowest index wins exact ties.
+constexpr int TAILW_WARPS = 8;
+__global__ void __launch_bounds__(TAILW_WARPS * 32) k_tc_tail_wide(
+    const float *__restrict__ x, int d, const float *__restrict__ c, const float *__restrict__ cn,
+    const uint4 *__restrict__ tail_all, const unsigned int *__restrict__ tail_count, int64_t nsuper, int workers,
+    int32_t *__restrict__ labels32, int64_t *__restrict__ labels64, float *__restrict__ dist,
+    unsigned long long *__restrict__ counters) {
+    extern __shared__ __align__(16) float s_stage[];   // per warp: 5 rows of d floats (the row, then the candidates)
+    const int q = (int)blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned int n_cand = tail_count[2 + q];
     const uint4 *__restrict__ tail = tail_all + tc_queue_base(nsuper, workers, q / (RT * 4), q % (RT * 4));
-    const unsigned int per_pass = blockDim.x >> 2;
-    // warp-uniform trip count (the 4-lane reductions shuffle with the full mask)
-    for (unsigned int e0 = 0; e0 < n_cand; e0 += per_pass) {
-        const unsigned int e = e0 + (threadIdx.x >> 2);
-        const bool live = e < n_cand;
-        const uint4 cc = tail[live ? e : e0];
+    float *sx = s_stage + (size_t)w * 5 * d;
+    for (unsigned int e = w; e < n_cand; e += TAILW_WARPS) {
+        const uint4 cc = tail[e];
         const int64_t row = (int64_t)cc.x;
-        const int col = t == 0 ? (int)(cc.y & 0xFFFFu) : t == 1 ? (int)(cc.y >> 16) : t == 2 ? (int)(cc.z & 0xFFFFu) : (int)(cc.z >> 16);
-        const float *xr = x + row * d, *cr = c + (size_t)col * d;
-        float xn = 0.f, ip = 0.f;
-        for (int i = 0; i < d; i += 4) {   // d is a multiple of 64
-            const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr + i)), cv = __ldg(reinterpret_cast<const float4 *>(cr + i));
-            xn = fmaf(xv.x, xv.x, xn), xn = fmaf(xv.y, xv.y, xn), xn = fmaf(xv.z, xv.z, xn), xn = fmaf(xv.w, xv.w, xn);
-            ip = fmaf(xv.x, cv.x, ip), ip = fmaf(xv.y, cv.y, ip), ip = fmaf(xv.z, cv.z, ip), ip = fmaf(xv.w, cv.w, ip);
+        const int cols[4] = {(int)(cc.y & 0xFFFFu), (int)(cc.y >> 16), (int)(cc.z & 0xFFFFu), (int)(cc.z >> 16)};
+        __syncwarp();   // the previous entry's chains are done with the buffer
+        for (int i = lane; i < d / 4; i += 32) {
+            reinterpret_cast<float4 *>(sx)[i] = __ldg(reinterpret_cast<const float4 *>(x + row * d) + i);
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+                reinterpret_cast<float4 *>(sx + (size_t)(t + 1) * d)[i] = __ldg(reinterpret_cast<const float4 *>(c + (size_t)cols[t] * d) + i);
         }
-        float bd = l2_expanded(xn, __ldg(cn + col), ip);
-        int best = col;
+        __syncwarp();
+        float bd = INFINITY;
+        int best = 0x7FFFFFFF;
+        if (lane < 4) {
+            const float *cr = sx + (size_t)(lane + 1) * d;
+            float xn = 0.f, ip = 0.f;
+            for (int i = 0; i < d; i += 4) {
+                const float4 xv = *reinterpret_cast<const float4 *>(sx + i), cv = *reinterpret_cast<const float4 *>(cr + i);
+                xn = fmaf(xv.x, xv.x, xn), xn = fmaf(xv.y, xv.y, xn), xn = fmaf(xv.z, xv.z, xn), xn = fmaf(xv.w, xv.w, xn);
+                ip = fmaf(xv.x, cv.x, ip), ip = fmaf(xv.y, cv.y, ip), ip = fmaf(xv.z, cv.z, ip), ip = fmaf(xv.w, cv.w, ip);
+            }
+            best = cols[lane];
+            bd = l2_expanded(xn, __ldg(cn + best), ip);
+        }
 #pragma unroll
         for (int o = 1; o < 4; o <<= 1) {
             const float od = __shfl_xor_sync(0xffffffffu, bd, o);
             const int ob = __shfl_xor_sync(0xffffffffu, best, o);
             if (od < bd || (od == bd && ob < best)) bd = od, best = ob;
         }
-        if (live && t == 0) {
+        if (lane == 0) {
             if (labels32) labels32[row] = best;
             if (labels64) labels64[row] = best;
             if (dist) dist[row] = bd;
@@ -1433,10 +1448,17 @@ int assign_tc_wide_search(at_index *ix, const float *x, int64_t n, int32_t *labe
     AT_LAUNCH_OK();
     // uncertified rows: the (at most four) candidate columns with the exact kernel's arithmetic, the rest (rare) through the
     // exact wide-row kernel over the list
-    k_tc_tail_wide<<<grid * RT * 4, 256, 0, st>>>(x, ix->d, ix->c, ix->cn, rows->tail, rows->tail_count, nsuper, grid, labels32,
-                                                 labels64, dist, ix->tc_counters);
+    const size_t tail_smem = sizeof(float) * (size_t)TAILW_WARPS * 5 * (size_t)ix->d;   // <= 160 KB at d = 1024
+    static bool tail_configured[MAX_DEVICES] = {};
+    if (!tail_configured[dev]) {
+        AT_CUDA_OK(cudaFuncSetAttribute(k_tc_tail_wide, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(float) * TAILW_WARPS * 5 * 1024)));
+        tail_configured[dev] = true;
+    }
+    k_tc_tail_wide<<<grid * RT * 4, TAILW_WARPS * 32, tail_smem, st>>>(x, ix->d, ix->c, ix->cn, rows->tail, rows->tail_count, nsuper,
+                                                                       grid, labels32, labels64, dist, ix->tc_counters);
     AT_LAUNCH_OK();
-    return launch_assign_gemm_list(ix, x, rows->full, rows->tail_count + 1, n, labels32, labels64, dist, st);
+    return launch_assign_gemm_list(ix, x, rows->full, rows->tail_count + 1, n, rows->keys, labels32, labels64, dist, st);
 }
 
 }  // namespace at

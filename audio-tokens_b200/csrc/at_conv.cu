@@ -69,22 +69,28 @@ __device__ __forceinline__ u64g gfma2(u64g a, u64g b, u64g c) {
 }
 __device__ __forceinline__ void gunpack(u64g v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
-// list != nullptr: the rows are list[0 .. *n_list) (the uncertified rows of the wide tensor search) instead of 0 .. n.
+// list != nullptr: the rows are list[0 .. *n_list) (the uncertified rows of the wide tensor search) instead of 0 .. n; the
+// grid is then (row tiles, centroid tiles): a short list would otherwise leave most of the GPU idle behind a few blocks that
+// each sweep all centroids.  Block (., y) handles centroid tile y only and folds its result into keys[list position] =
+// (distance bits << 32 | column) with atomicMin (non-negative floats order like their patterns; equal distances: the lower
+// column), k_gemm_keys turns the keys into labels.  The row tiles are walked with a grid stride.
 __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict__ x, int64_t n, int d, const float *__restrict__ c,
                                                         const float *__restrict__ cn, int k, int32_t *__restrict__ labels32,
                                                         int64_t *__restrict__ labels64, float *__restrict__ dist,
                                                         const uint32_t *__restrict__ list,
                                                         const unsigned int *__restrict__ n_list,
-                                                        unsigned long long *__restrict__ counters) {
+                                                        unsigned long long *__restrict__ counters,
+                                                        unsigned long long *__restrict__ keys) {
     __shared__ __align__(16) float2 sa[2][GK][GM];   // (a, a): rows duplicated            16 KB
     __shared__ __align__(16) float sb[2][GK][GN];    //                                      8 KB
     __shared__ float s_xn[GM];
     __shared__ int64_t s_row[GM];                    // global row of the block's row slot (-1: none)
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    const int64_t row0 = (int64_t)blockIdx.x * GM;
     if (list) n = (int64_t)*n_list;
-    if (counters && blockIdx.x == 0 && tid == 0) atomicAdd(&counters[1], (unsigned long long)n);   // rows scanned exactly
-    if (row0 >= n) return;   // block-uniform
+    if (counters && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) atomicAdd(&counters[1], (unsigned long long)n);   // rows scanned exactly
+    const int jbeg = keys ? (int)blockIdx.y * GN : 0, jend = keys ? min(k, jbeg + GN) : k;
+    for (int64_t row0 = (int64_t)blockIdx.x * GM; row0 < n; row0 += (int64_t)gridDim.x * GM) {   // block-uniform
+    __syncthreads();   // the previous row tile is done with s_row / s_xn
     if (tid < GM) s_row[tid] = row0 + tid < n ? (list ? (int64_t)list[row0 + tid] : row0 + tid) : -1;
     __syncthreads();
     // |x|^2 of the block's rows: one sequential FMA chain per row (thread t < 128 walks row t)
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict_
 #pragma unroll
     for (int r = 0; r < 8; r++) best[r] = INFINITY, bidx[r] = 0x7FFFFFFF;
     const int nchunk = (d + GK - 1) / GK;
-    for (int j0 = 0; j0 < k; j0 += GN) {
+    for (int j0 = jbeg; j0 < jend; j0 += GN) {
         u64g acc[8][4];   // acc[r][q]: row r of the thread, columns 2q, 2q+1 of its eight
 #pragma unroll
         for (int r = 0; r < 8; r++)
@@ -191,30 +197,64 @@ __global__ void __launch_bounds__(256, 2) k_assign_gemm(const float *__restrict_
     if (tx == 0) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            const int64_t row = s_row[(r < 4 ? 0 : 64) + ty * 4 + (r & 3)];
+            const int slot = (r < 4 ? 0 : 64) + ty * 4 + (r & 3);
+            const int64_t row = s_row[slot];
             if (row >= 0) {
-                const int bj = bidx[r] == 0x7FFFFFFF ? 0 : bidx[r];
-                if (labels32) labels32[row] = bj;
-                if (labels64) labels64[row] = bj;
-                if (dist) dist[row] = best[r];
+                if (keys) {
+                    if (bidx[r] != 0x7FFFFFFF)
+                        atomicMin(&keys[row0 + slot], ((unsigned long long)__float_as_uint(best[r]) << 32) | (unsigned int)bidx[r]);
+                } else {
+                    const int bj = bidx[r] == 0x7FFFFFFF ? 0 : bidx[r];
+                    if (labels32) labels32[row] = bj;
+                    if (labels64) labels64[row] = bj;
+                    if (dist) dist[row] = best[r];
+                }
             }
         }
+    }
+    }   // row tiles
+}
+
+// keys[0 .. *n_list) = all ones (nothing seen)
+__global__ void k_gemm_keys_init(unsigned long long *__restrict__ keys, const unsigned int *__restrict__ n_list) {
+    const unsigned int n = *n_list;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) keys[i] = ~0ull;
+}
+// keys -> labels (and distances) of the listed rows; a row whose every distance was NaN keeps label 0 like the exact kernels
+__global__ void k_gemm_keys(const uint32_t *__restrict__ list, const unsigned int *__restrict__ n_list,
+                            const unsigned long long *__restrict__ keys, int32_t *__restrict__ labels32,
+                            int64_t *__restrict__ labels64, float *__restrict__ dist) {
+    const unsigned int n = *n_list;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        const int64_t row = (int64_t)list[i];
+        const int bj = key == ~0ull ? 0 : (int)(unsigned int)key;
+        if (labels32) labels32[row] = bj;
+        if (labels64) labels64[row] = bj;
+        if (dist) dist[row] = key == ~0ull ? INFINITY : __uint_as_float((unsigned int)(key >> 32));
     }
 }
 
 int launch_assign_gemm(const at_index *ix, const float *x, int64_t n, int32_t *l32, int64_t *l64, float *dist, cudaStream_t st) {
     k_assign_gemm<<<(unsigned)ceil_div(n, GM), 256, 0, st>>>(x, n, ix->d, ix->c, ix->cn, ix->k, l32, l64, dist, nullptr, nullptr,
-                                                             nullptr);
+                                                             nullptr, nullptr);
     AT_LAUNCH_OK();
     return AT_OK;
 }
 
-// the listed rows only (blocks beyond the list's length leave at once; the length lives on the device)
+// the listed rows only (the length lives on the device): (row tiles, centroid tiles) grid + keys, see k_assign_gemm
 int launch_assign_gemm_list(const at_index *ix, const float *x, const uint32_t *list, const unsigned int *n_list, int64_t n_max,
-                            int32_t *l32, int64_t *l64, float *dist, cudaStream_t st) {
-    const int64_t blocks = ceil_div(n_max, GM);
-    k_assign_gemm<<<(unsigned)blocks, 256, 0, st>>>(x, n_max, ix->d, ix->c, ix->cn, ix->k, l32, l64, dist, list, n_list,
-                                                    ix->tc_counters);
+                            unsigned long long *keys, int32_t *l32, int64_t *l64, float *dist, cudaStream_t st) {
+    const int sms = sm_count() > 0 ? sm_count() : 1;
+    int64_t gx = ceil_div(n_max, GM);
+    if (gx > 2 * sms) gx = 2 * sms;   // grid stride over longer lists
+    k_gemm_keys_init<<<sms, 256, 0, st>>>(keys, n_list);
+    AT_LAUNCH_OK();
+    k_assign_gemm<<<dim3((unsigned)gx, (unsigned)ceil_div(ix->k, GN)), 256, 0, st>>>(x, n_max, ix->d, ix->c, ix->cn, ix->k, nullptr,
+                                                                                    nullptr, nullptr, list, n_list,
+                                                                                    ix->tc_counters, keys);
+    AT_LAUNCH_OK();
+    k_gemm_keys<<<sms, 256, 0, st>>>(list, n_list, keys, l32, l64, dist);
     AT_LAUNCH_OK();
     return AT_OK;
 }

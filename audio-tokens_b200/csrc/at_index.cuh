@@ -12,6 +12,7 @@ struct at_tc_rows {
     uint4 *tail = nullptr;      // (n_pad) uncertified rows of the last search with a candidate list, one queue per scanning
                                 // warp of k_assign_tc (no shared counter): {row, candidate columns 0|1, 2|3, -}
     uint32_t *full = nullptr;   // (n_pad) uncertified rows that need an exact scan (dense list)
+    unsigned long long *keys = nullptr;   // (n_pad, wide rows only) (distance, column) keys of the listed rows' exact scans
     unsigned int *tail_count = nullptr;   // [1] rows in `full`, [2 + q] entries of candidate queue q
     int tail_queues = 0;        // queues allocated in tail_count
     int64_t cap = 0;            // rows allocated (multiple of 256)
@@ -140,7 +141,7 @@ int assign_tc_wide_search(at_index *ix, const float *x, int64_t n, int32_t *labe
                           at_tc_rows *rows, cudaStream_t st);
 // at_conv.cu: the exact wide-row kernel over a list of rows (list, *n_list on the device; at most n_max)
 int launch_assign_gemm_list(const at_index *ix, const float *x, const uint32_t *list, const unsigned int *n_list, int64_t n_max,
-                            int32_t *l32, int64_t *l64, float *dist, cudaStream_t st);
+                            unsigned long long *keys, int32_t *l32, int64_t *l64, float *dist, cudaStream_t st);
 void tc_rows_free(at_tc_rows *r);
 bool assign_tc_supported(const at_index *ix);
 // at_conv.cu: exact fp32 search for rows wider than 128 values (pre-normalised rows)
