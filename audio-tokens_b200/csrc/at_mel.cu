@@ -485,15 +485,26 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 float acc = 0.f;
                 if (wt_in_smem) {
                     const float4 *w4 = reinterpret_cast<const float4 *>(s_wt + s_par[3 * m + 2]);
+                    // two independent chains (even / odd segments) and four segments in flight: one chain of dependent FMAs
+                    // behind 128-bit shared loads left this phase waiting on the loads (24 % of the warp time, ncu)
+                    float acc1 = 0.f;
+                    int i = 0;
 #pragma unroll 2
-                    for (int i = 0; i < cnt4; i++) {
-                        const float4 w = w4[i];  // broadcast: the lanes of a filter read the same segment
+                    for (; i + 1 < cnt4; i += 2) {
+                        const float4 w = w4[i], w2 = w4[i + 1];  // broadcast: the lanes of a filter read the same segment
                         const float4 pw = *reinterpret_cast<const float4 *>(prow + 4 * i);   // conflict-free: rows are 516 floats apart
-                        acc = fmaf(w.x, pw.x, acc);
-                        acc = fmaf(w.y, pw.y, acc);
-                        acc = fmaf(w.z, pw.z, acc);
-                        acc = fmaf(w.w, pw.w, acc);
+                        const float4 pw2 = *reinterpret_cast<const float4 *>(prow + 4 * i + 4);
+                        acc = fmaf(w.x, pw.x, acc), acc1 = fmaf(w2.x, pw2.x, acc1);
+                        acc = fmaf(w.y, pw.y, acc), acc1 = fmaf(w2.y, pw2.y, acc1);
+                        acc = fmaf(w.z, pw.z, acc), acc1 = fmaf(w2.z, pw2.z, acc1);
+                        acc = fmaf(w.w, pw.w, acc), acc1 = fmaf(w2.w, pw2.w, acc1);
                     }
+                    if (i < cnt4) {
+                        const float4 w = w4[i];
+                        const float4 pw = *reinterpret_cast<const float4 *>(prow + 4 * i);
+                        acc = fmaf(w.x, pw.x, acc), acc = fmaf(w.y, pw.y, acc), acc = fmaf(w.z, pw.z, acc), acc = fmaf(w.w, pw.w, acc);
+                    }
+                    acc += acc1;
                 } else {
                     const float *w = wt + woff[m];
                     for (int i = 0; i < 4 * cnt4; i++) acc = fmaf(__ldg(w + i), prow[i], acc);
@@ -549,39 +560,57 @@ k_mel(const float *__restrict__ wave, const int64_t *__restrict__ sample_offsets
                 const float inv_range = __fdiv_rn(1.0f, range);  // range == 0 -> inf -> 0 * inf = NaN like the reference's 0/0
                 const int g = tid & 15, hw = (tid >> 4) & 1;
                 const bool vec = (n_mels & 3) == 0 && n_mels <= 256;
+                constexpr int RSTEP = MEL_THREADS / 16;   // rows per pass of the group
+                if (vec && n_mels <= 64) {
+                    // one float4 per lane (the 64-mel configuration of the reference); four rows in flight per half-warp: the tile
+                    // comes back from L2 and a single dependent load per pass left this loop waiting (13 % of the warp time, ncu)
+                    constexpr int EU = 4;
+                    const bool col_on = 4 * g < n_mels;
+                    // warp-uniform trip count (both half-warps iterate together: the shuffles below need all 32 lanes)
+                    for (int64_t r0 = (int64_t)(tid >> 5) * 2; r0 < T; r0 += RSTEP * EU) {
+                        float4 v[EU];
+                        bool on[EU];
+#pragma unroll
+                        for (int u = 0; u < EU; u++) {
+                            const int64_t r = r0 + u * RSTEP + hw;
+                            on[u] = r < T && col_on;
+                            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (on[u]) v[u] = __ldcg(reinterpret_cast<const float4 *>(dst + r * n_mels + 4 * g));
+                        }
+#pragma unroll
+                        for (int u = 0; u < EU; u++) {
+                            const int64_t r = r0 + u * RSTEP + hw;
+                            float4 w = v[u];
+                            if (normalize) {
+                                w.x = __fmul_rn(__fsub_rn(w.x, mn), inv_range), w.y = __fmul_rn(__fsub_rn(w.y, mn), inv_range);
+                                w.z = __fmul_rn(__fsub_rn(w.z, mn), inv_range), w.w = __fmul_rn(__fsub_rn(w.w, mn), inv_range);
+                                if (on[u]) {
+                                    nonfinite |= !(isfinite(w.x) && isfinite(w.y) && isfinite(w.z) && isfinite(w.w));
+                                    *reinterpret_cast<float4 *>(dst + r * n_mels + 4 * g) = w;
+                                } else {
+                                    w = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+                            if (out_l2) {
+                                float q = w.x * w.x;
+                                q = fmaf(w.y, w.y, q), q = fmaf(w.z, w.z, q), q = fmaf(w.w, w.w, q);
+                                const float den = l2_denominator(half16_sum(q));
+                                if (on[u]) {
+                                    const float4 o4 = make_float4(__fdiv_rn(w.x, den), __fdiv_rn(w.y, den), __fdiv_rn(w.z, den),
+                                                                  __fdiv_rn(w.w, den));
+                                    l2max = fmaxf(fmaxf(l2max, fmaxf(fabsf(o4.x), fabsf(o4.y))), fmaxf(fabsf(o4.z), fabsf(o4.w)));
+                                    *reinterpret_cast<float4 *>(out_l2 + (cur.f0 + r) * n_mels + 4 * g) = o4;
+                                }
+                            }
+                        }
+                    }
+                } else
                 // warp-uniform trip count (both half-warps iterate together: the shuffles below need all 32 lanes)
-                for (int64_t r0 = (int64_t)(tid >> 5) * 2; r0 < T; r0 += MEL_THREADS / 16) {
+                for (int64_t r0 = (int64_t)(tid >> 5) * 2; r0 < T; r0 += RSTEP) {
                     const int64_t r = r0 + hw;
                     const bool live = r < T;
                     float *row = dst + (live ? r : 0) * n_mels;
                     float q = 0.f;
-                    if (vec && n_mels <= 64) {   // one float4 per lane (the 64-mel configuration of the reference)
-                        const bool on = live && 4 * g < n_mels;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (on) v = __ldcg(reinterpret_cast<const float4 *>(row + 4 * g));
-                        if (normalize) {
-                            v.x = __fmul_rn(__fsub_rn(v.x, mn), inv_range), v.y = __fmul_rn(__fsub_rn(v.y, mn), inv_range);
-                            v.z = __fmul_rn(__fsub_rn(v.z, mn), inv_range), v.w = __fmul_rn(__fsub_rn(v.w, mn), inv_range);
-                            if (on) {
-                                nonfinite |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
-                                *reinterpret_cast<float4 *>(row + 4 * g) = v;
-                            } else {
-                                v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                        }
-                        if (out_l2) {
-                            q = v.x * v.x;
-                            q = fmaf(v.y, v.y, q), q = fmaf(v.z, v.z, q), q = fmaf(v.w, v.w, q);
-                            const float den = l2_denominator(half16_sum(q));
-                            if (on) {
-                                const float4 o4 = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den),
-                                                              __fdiv_rn(v.w, den));
-                                l2max = fmaxf(fmaxf(l2max, fmaxf(fabsf(o4.x), fabsf(o4.y))), fmaxf(fabsf(o4.z), fabsf(o4.w)));
-                                *reinterpret_cast<float4 *>(out_l2 + (cur.f0 + r) * n_mels + 4 * g) = o4;
-                            }
-                        }
-                        continue;
-                    }
                     if (vec) {
                         float4 v[4];
 #pragma unroll
