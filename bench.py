@@ -444,6 +444,54 @@ def config_c4(spec_rows, pk):
             "target_tokens_per_s": 0.39e9}
 
 
+def config_conv(spec_rows, pk, n_rows=862000, K=500):
+    """SURVEY.md section 8f-4 (config.use_convolution, reference defaults num_kernels = 10, kernel_size = 3, vocab_size = 500):
+    Conv1d expansion 64 -> 640 values per frame, row normalisation, nearest-centroid search of the wide rows on the
+    slice-accumulating tcgen05 kernel against the exact fp32 tile kernel (labels must be equal), one Lloyd iteration."""
+    import torch
+
+    import at_b200
+    from at_b200 import FlatL2, LloydTrainer, _lib
+
+    x = spec_rows[:n_rows].contiguous()
+    n = x.shape[0]
+    g = torch.Generator().manual_seed(42)
+    conv_w = (torch.rand(10, 3, generator=g) * 2 - 1).mul_(3 ** -0.5).cuda()   # nn.Conv1d's default range for fan-in 3
+    conv_b = (torch.rand(10, generator=g) * 2 - 1).mul_(3 ** -0.5).cuda()
+
+    def timed(fn, reps=3):
+        for _ in range(2):
+            out = fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    ms_exp, wide = timed(lambda: at_b200.conv_expand(x, conv_w, conv_b))
+    ms_norm, wn = timed(lambda: at_b200.row_l2norm(wide))
+    del wide
+    ix = FlatL2(640)
+    gd = torch.Generator("cuda").manual_seed(3)
+    ix.set_centroids(wn[torch.randperm(n, device="cuda", generator=gd)[:K]].contiguous())
+    ms_exact, (lab_e, _) = timed(lambda: ix.search(wn, want_dist=False, algo=_lib.ALGO_SIMT), reps=2)
+    ms_tc, (lab_t, _) = timed(lambda: ix.search(wn, want_dist=False, algo=_lib.ALGO_TENSOR))
+    tr = LloydTrainer(640, K)
+    tr.begin(wn)
+    tr.set_centroids(wn[:K].contiguous())
+    ms_it, _ = timed(lambda: tr.step(wn, None))
+    fl = 2.0 * n * K * 640
+    return {"workload": f"use_convolution: {n} frames -> Conv1d(1, 10, 3) -> 640-value rows, K={K}",
+            "conv_expand_ms": ms_exp, "row_l2norm_ms": ms_norm,
+            "search_tensor_ms": ms_tc, "search_tensor_tflops": fl / (ms_tc * 1e-3) / 1e12,
+            "search_tensor_frac_of_sustained_tensor_peak": fl / (ms_tc * 1e-3) / 1e12 / pk["tensor_sustained"],
+            "search_exact_fp32_ms": ms_exact, "labels_equal_to_exact_kernel": bool(torch.equal(lab_e, lab_t)),
+            "lloyd_iteration_ms": ms_it,
+            "note": "search_tensor_ms includes the per-call build of the rows' fp16 image (k-means builds it once per training set)"}
+
+
 def config_c5(hp_plan_args, wave, clips_target, world, pk):
     """BASELINE.json configs[4] per GPU: clips streamed from pinned HOST int16 PCM chunks through spectrogram + tokenize at
     K = 4096 (fixed centroids), tokens read back to the host, nothing else kept (HotPath.stream_tokenize).  The host chunks
@@ -812,6 +860,10 @@ def run_b200(args):
                 cfgs["C4"] = config_c4(bufs["spec"].reshape(-1, N_MELS), peaks())
             except Exception as ex:
                 cfgs["C4"] = {"error": repr(ex)[:300]}
+            try:
+                cfgs["use_convolution"] = config_conv(bufs["spec"].reshape(-1, N_MELS), peaks())
+            except Exception as ex:
+                cfgs["use_convolution"] = {"error": repr(ex)[:300]}
         c5_err, c5 = None, None
         try:
             barrier()
