@@ -49,6 +49,7 @@ class SpecTokenizer:
             all_tokens = self.tokenize_directory(source_spec_dir, tokenized_dir)
             if split == "train":
                 self.analyze_tokens(all_tokens)
+                self.plot_token_distribution(all_tokens)
 
     def tokenize_directory(self, source_dir: Path, tokenized_dir: Path):
         all_tokens = []
@@ -112,7 +113,7 @@ class SpecTokenizer:
 
     def analyze_tokens(self, all_tokens):
         """Token histogram (the reference builds a Counter over a Python list; here a device bincount) and the
-        same log lines.  The matplotlib plots / Zipf fit of the reference are cosmetic and not reproduced."""
+        same log lines (:141-144).  The bar plot is not drawn."""
         if len(all_tokens) == 0:
             return
         k = self.index.ntotal
@@ -127,6 +128,56 @@ class SpecTokenizer:
         self.logger.info(f"Unique tokens: {len(used)}")
         self.logger.info(f"Most common token: [({int(order[0])}, {int(counts[order[0]])})]")
         self.logger.info(f"Least common token: ({int(order[-1])}, {int(counts[order[-1]])})")
+
+    @staticmethod
+    def token_statistics(counts):
+        """The numbers plot_token_distribution / analyze_zipf_and_tail print (reference :177-236) from a histogram: tokens by
+        descending frequency (ties: lower token id first -- the reference keeps first-seen order), the number of tokens that
+        account for 80 % of the occurrences, and the least-squares line through the middle 80 % of the log-log rank /
+        frequency curve (scipy.stats.linregress in the reference: slope and r^2)."""
+        counts = np.asarray(counts, dtype=np.int64)
+        used = np.nonzero(counts)[0]
+        order = used[np.argsort(-counts[used], kind="stable")]
+        freq = counts[order]
+        total = int(freq.sum())
+        cum = np.cumsum(freq) / total
+        tail_start = int(np.searchsorted(cum, 0.8))
+        out = dict(tokens=order, frequencies=freq, total=total, top_80_percent=tail_start + 1, tail_start=tail_start,
+                   tail_proportion=1 - tail_start / len(freq), slope=float("nan"), r_squared=float("nan"))
+        lo, hi = int(0.1 * len(freq)), int(0.9 * len(freq))
+        if hi - lo >= 2:
+            lx, ly = np.log(np.arange(1, len(freq) + 1))[lo:hi], np.log(freq.astype(np.float64))[lo:hi]
+            dx, dy = lx - lx.mean(), ly - ly.mean()
+            sxx, sxy, syy = float(dx @ dx), float(dx @ dy), float(dy @ dy)
+            out["slope"] = sxy / sxx
+            out["r_squared"] = (sxy * sxy) / (sxx * syy) if syy > 0 else 0.0
+        return out
+
+    def plot_token_distribution(self, all_tokens):
+        """The statistics the reference prints here and in analyze_zipf_and_tail (:177-236), from the device histogram of
+        analyze_tokens; the three figures are not drawn."""
+        if len(all_tokens) == 0:
+            return
+        if self.token_counts is None or int(self.token_counts.sum()) != len(all_tokens):
+            self.analyze_tokens(all_tokens)
+        st = self.token_statistics(self.token_counts)
+        tokens, freq = st["tokens"], st["frequencies"]
+        print(f"Total unique tokens: {len(tokens)}")
+        print(f"Total token occurrences: {st['total']}")
+        print(f"Most common token (rank 1): Token {int(tokens[0])} (used {int(freq[0])} times)")
+        print(f"Least common token (rank {len(tokens)}): Token {int(tokens[-1])} (used {int(freq[-1])} times)")
+        print(f"Top {st['top_80_percent']} tokens account for 80% of all token occurrences")
+        print(f"Frequency ratio between most and least common: {freq[0] / freq[-1]:.2f}")
+        self.analyze_zipf_and_tail(freq)
+
+    def analyze_zipf_and_tail(self, frequencies):
+        """Reference :201-236 on a descending frequency array."""
+        counts = np.asarray(frequencies, dtype=np.int64)
+        st = self.token_statistics(counts)   # already sorted: the stable ordering keeps it
+        print(f"Zipf's law slope: {st['slope']:.2f} (closer to -1 indicates closer fit to Zipf's law)")
+        print(f"R-squared value: {st['r_squared']:.2f}")
+        print(f"Proportion of tokens in the tail (last 20% of occurrences): {st['tail_proportion']:.2%}")
+        print(f"Number of tokens accounting for 80% of occurrences: {st['tail_start']}")
 
 
 if __name__ == "__main__":

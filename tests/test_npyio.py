@@ -90,3 +90,32 @@ def test_spec_tokenizer_process_batch_splits_tokens_per_file(tmp_path):
         assert np.array_equal(tok, np.arange(pos, pos + n))
         pos += n
     assert st.process_batch([], dst) == []
+
+
+def test_token_statistics_match_the_reference_expressions():
+    """SpecTokenizer.token_statistics (the numbers of plot_token_distribution / analyze_zipf_and_tail, reference
+    processors/spec_tokenizer.py:146-236) against the reference's own expressions: Counter, sorted, np.cumsum / searchsorted,
+    scipy.stats.linregress over the middle 80 % of the log-log curve."""
+    from collections import Counter
+
+    from scipy import stats
+
+    from processors.spec_tokenizer import SpecTokenizer
+
+    rng = np.random.default_rng(3)
+    k = 300
+    all_tokens = rng.zipf(1.3, size=200000) % k   # long-tailed, a few unused ids
+    counts = np.bincount(all_tokens, minlength=k)
+    st = SpecTokenizer.token_statistics(counts)
+    token_counts = Counter(all_tokens.tolist())
+    sorted_counts = sorted(token_counts.items(), key=lambda x: x[1], reverse=True)
+    tokens, frequencies = zip(*sorted_counts)
+    assert list(st["frequencies"]) == list(frequencies) and st["total"] == sum(frequencies) and len(st["tokens"]) == len(tokens)
+    cumulative_freq = np.cumsum(frequencies) / sum(frequencies)
+    assert st["top_80_percent"] == np.searchsorted(cumulative_freq, 0.8) + 1
+    ranks = np.arange(1, len(frequencies) + 1)
+    a, b = int(0.1 * len(frequencies)), int(0.9 * len(frequencies))
+    slope, _, r_value, _, _ = stats.linregress(np.log(ranks)[a:b], np.log(frequencies)[a:b])
+    assert abs(st["slope"] - slope) < 1e-9 and abs(st["r_squared"] - r_value ** 2) < 1e-9
+    tail_start = np.searchsorted(cumulative_freq, 0.8)
+    assert st["tail_start"] == tail_start and abs(st["tail_proportion"] - (1 - tail_start / len(frequencies))) < 1e-12
