@@ -11,6 +11,11 @@
  *
  * There is no CPU fallback: without a CUDA device every compute entry point fails with AT_ERR_CUDA.
  *
+ * Threading (the reference is single-threaded Python): a plan / index / k-means object may be used by
+ * one thread at a time; different objects may be used from different threads.  The error message is thread-local; the
+ * launch counter of at_kernel_launches() and the at_profile_* timers are process-wide and meant for one measuring thread.
+ * Per-device kernel attributes are set on first use of each device, so a process may drive several GPUs.
+ *
  * Reference interface each group replaces (paths relative to the reference repo):
  *
  *   at_mel_*     processors/spectrogram_generator.py:28-34 (MelSpectrogram + AmplitudeToDB construction),
