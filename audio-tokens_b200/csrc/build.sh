@@ -14,5 +14,5 @@ for f in at_util at_kmeans at_mel at_assign_tc at_resample at_peer at_tokens at_
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$OBJ"/at_util.o "$OBJ"/at_kmeans.o "$OBJ"/at_mel.o "$OBJ"/at_assign_tc.o "$OBJ"/at_resample.o "$OBJ"/at_peer.o "$OBJ"/at_tokens.o "$OBJ"/at_conv.o -lcudart
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT" "$OBJ"/at_util.o "$OBJ"/at_kmeans.o "$OBJ"/at_mel.o "$OBJ"/at_assign_tc.o "$OBJ"/at_resample.o "$OBJ"/at_peer.o "$OBJ"/at_tokens.o "$OBJ"/at_conv.o -lcudart
 echo "built $OUT"

@@ -63,3 +63,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_library_holds_blackwell_tensor_and_bulk_copy_instructions():
+    """The built library is sm_100a code whose SASS carries the 5th-generation tensor-core path (tcgen05.mma -> UTC*MMA,
+    tcgen05.ld -> LDTM), the bulk-copy engine (cp.async.bulk -> UBLKCP) and packed fp32 (FFMA2 / FADD2), and none of the
+    legacy tensor instructions (mma.sync -> HMMA): a changed build flag or a silent fallback would show here."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+
+    from at_b200 import _lib
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool) and not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", out))
+    assert archs == {"sm_100a"}, archs
+    ops = collections.Counter(m.group(1).split(".")[0] for m in re.finditer(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]+)", out, re.M))
+    assert ops["UTCHMMA"] >= 10 and ops["LDTM"] >= 8 and ops["UBLKCP"] >= 4, {k: ops[k] for k in ("UTCHMMA", "LDTM", "UBLKCP")}
+    assert ops["FFMA2"] > 0 and ops["FADD2"] > 0
+    assert ops["HMMA"] == 0 and ops["HGMMA"] == 0
+    fns = set(re.findall(r"Function : (\S+)", out))
+    for name in ("k_mel", "k_assign_tc", "k_assign_tc_wide", "k_tc_tail", "k_tc_full", "k_gather_sum", "k_finalize_split",
+                 "k_conv_expand", "k_assign_gemm", "k_peer", "k_tokens"):
+        assert any(name in f for f in fns), name
