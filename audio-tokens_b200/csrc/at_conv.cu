@@ -18,15 +18,17 @@ namespace at {
 // write consecutive floats of the output row (coalesced) and nothing is divided inside the loops.  CONV_ROWS rows are
 // staged in shared memory per block step (zero padded at both ends: no bounds tests on the taps).
 constexpr int CONV_ROWS = 8, CONV_MAX_KS = 15;
+template <int KS>   // taps (compile time: the tap loop is exactly KS FMAs, no predicates)
 __global__ void __launch_bounds__(256) k_conv_expand(const float *__restrict__ x, int64_t n, int n_mels,
-                                                     const float *__restrict__ w, const float *__restrict__ b, int kc, int ks,
+                                                     const float *__restrict__ w, const float *__restrict__ b, int kc,
                                                      float *__restrict__ out) {
+    constexpr int ks = KS;
     extern __shared__ float s_x[];   // CONV_ROWS rows of (pad + n_mels + pad) floats
     const int pad = ks / 2, stride = n_mels + 2 * pad;
     const int c = (int)threadIdx.x % kc, m0 = (int)threadIdx.x / kc, mstep = (int)blockDim.x / kc;
-    float wr[CONV_MAX_KS];
+    float wr[KS];
 #pragma unroll
-    for (int t = 0; t < CONV_MAX_KS; t++) wr[t] = t < ks ? w[c * ks + t] : 0.f;
+    for (int t = 0; t < KS; t++) wr[t] = w[c * ks + t];
     const float bias = b[c];
     const int64_t d_out = (int64_t)n_mels * kc;
     for (int64_t r0 = (int64_t)blockIdx.x * CONV_ROWS; r0 < n; r0 += (int64_t)gridDim.x * CONV_ROWS) {
@@ -43,8 +45,7 @@ __global__ void __launch_bounds__(256) k_conv_expand(const float *__restrict__ x
             for (int m = m0; m < n_mels; m += mstep) {
                 float acc = bias;
 #pragma unroll
-                for (int t = 0; t < CONV_MAX_KS; t++)
-                    if (t < ks) acc = fmaf(wr[t], xr[m + t], acc);   // ascending taps, like the first version (same rounding)
+                for (int t = 0; t < KS; t++) acc = fmaf(wr[t], xr[m + t], acc);   // ascending taps (same rounding as before)
                 orow[(int64_t)m * kc] = acc;
             }
         }
@@ -279,7 +280,17 @@ extern "C" int at_conv_expand(const float *x, int64_t n, int n_mels, const float
         set_error("at_conv_expand: rows of %d mel bins do not fit the staging buffer", n_mels);
         return AT_ERR_UNSUPPORTED;
     }
-    k_conv_expand<<<blocks, threads, smem, (cudaStream_t)stream>>>(x, n, n_mels, weight, bias, num_kernels, kernel_size, out);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kernel_size) {
+        case 1: k_conv_expand<1><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+        case 3: k_conv_expand<3><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+        case 5: k_conv_expand<5><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+        case 7: k_conv_expand<7><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+        case 9: k_conv_expand<9><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+        case 11: k_conv_expand<11><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+        case 13: k_conv_expand<13><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+        default: k_conv_expand<15><<<blocks, threads, smem, st>>>(x, n, n_mels, weight, bias, num_kernels, out); break;
+    }
     AT_LAUNCH_OK();
     return AT_OK;
 }
